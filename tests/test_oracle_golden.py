@@ -1,0 +1,101 @@
+"""Pins oracle/tim_oracle.py to the outputs of the real reference (tests/golden/*.npz, minted by
+tools/make_golden.py from /root/reference on CPU fp32). Runs without a GPU and without the reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.tim_oracle import TIMOracle
+from tim_b200.config import TIMConfig, state_dict_spec, named_config
+from tim_b200.synth import synth_inputs, synth_state_dict, rel_l2
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+MANIFEST = json.load(open(os.path.join(GOLD, "manifest.json")))["cases"]
+OUT_KEYS = ("verb", "noun", "action", "audio", "reg_v", "reg_a")
+
+
+def load_case(name):
+    c = MANIFEST[name]
+    cfg = TIMConfig(**c["cfg"])
+    sd = synth_state_dict(cfg, c["weight_seed"], c["style"])
+    inp = synth_inputs(cfg, c["B"], c["Qv"], c["Qa"], c["input_seed"], shared_queries=c["shared_queries"])
+    gold = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    if c["pyramid"]:
+        inp["times"][:, cfg.F_tot:] = pyramid_queries()
+    return cfg, sd, inp, gold, c
+
+
+def pyramid_queries(query_size=0.01):
+    """detection/.../tim.py:144-155 generate_queries, restated in numpy (float32 like torch.arange)."""
+    out = []
+    while query_size < 1.0:
+        # torch.arange(0., 1., step) has ceil((1-0)/step) elements
+        n = int(np.ceil(1.0 / (query_size / 2)))
+        st = (np.arange(n, dtype=np.float64) * (query_size / 2)).astype(np.float32)
+        en = st + np.float32(query_size)
+        out.append(np.round(np.stack([st, en], -1), 3))
+        query_size *= 2
+    return np.concatenate(out, 0)[None].astype(np.float32)
+
+
+@pytest.mark.parametrize("name", sorted(MANIFEST))
+def test_oracle_matches_reference_golden(name):
+    cfg, sd, inp, gold, c = load_case(name)
+    o = TIMOracle(cfg, sd, np.float32).forward(inp.get("vis"), inp.get("aud"), inp["times"], c["Qv"], c["Qa"])
+    for k in OUT_KEYS:
+        assert (o[k] is None) == (k not in gold), k
+    for k, g in gold.items():
+        assert o[k].shape == g.shape, (k, o[k].shape, g.shape)
+        assert o[k].dtype == np.float32
+        e = rel_l2(o[k], g)
+        assert e <= 1e-5, f"{name}/{k}: rel-L2 {e:.3e} > 1e-5 (fp32 tolerance of BASELINE.json)"
+
+
+def test_pyramid_has_399_queries():
+    q = pyramid_queries()
+    assert q.shape == (1, 399, 2)          # SURVEY.md §8(a9) [probe]
+
+
+def test_mask_structure():
+    cfg, Qv, Qa = named_config("cfg1")
+    o = TIMOracle(cfg, {}, np.float32)
+    S = cfg.seq_len(Qv, Qa)
+    m = o.mask(S)
+    assert S == 70 and m.shape == (S, S)
+    assert not m[:, :cfg.F_tot].any()                       # every token sees all feature tokens
+    assert not m[np.arange(S), np.arange(S)].any()          # ... and itself
+    off = m[cfg.F_tot:, cfg.F_tot:]
+    assert (off | np.eye(S - cfg.F_tot, dtype=bool)).all()  # queries never see other queries
+
+
+def test_query_subset_invariance():
+    """a query's logits do not depend on which other queries are present."""
+    cfg, sd, inp, gold, c = load_case("recog_av_small")
+    o = TIMOracle(cfg, sd, np.float64)
+    full = o.forward(inp["vis"], inp["aud"], inp["times"], c["Qv"], c["Qa"])
+    F = cfg.F_tot
+    keep = np.r_[np.arange(F), F, F + c["Qv"]]              # first visual + first audio query only
+    sub = o.forward(inp["vis"], inp["aud"], inp["times"][:, keep], 1, 1)
+    B = c["B"]
+    np.testing.assert_allclose(sub["action"], full["action"].reshape(B, c["Qv"], -1)[:, 0], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(sub["audio"], full["audio"].reshape(B, c["Qa"], -1)[:, 0], rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(sub["feats"], full["feats"], rtol=1e-9, atol=1e-11)
+
+
+def test_state_dict_spec_counts():
+    cfg, _, _ = named_config("cfg1")
+    n = sum(int(np.prod(s)) for s in state_dict_spec(cfg).values())
+    assert n == 16_304_280                                  # SURVEY.md §8(c) [probe]
+    cfg4, _, _ = named_config("cfg4")
+    assert len(state_dict_spec(cfg4)) == 105                # 105 keys for 6L visual det
+    assert sum(int(np.prod(s)) for s in state_dict_spec(cfg4).values()) > 50_000_000
+
+
+def test_flop_formula_matches_survey():
+    cfg2, Qv, Qa = named_config("cfg2")
+    assert abs(cfg2.flops_fwd_per_clip(Qv, Qa) / 1e9 - 21.17) < 0.05
+    cfg3, Qv, Qa = named_config("cfg3")
+    assert abs(cfg3.flops_fwd_per_clip(Qv, Qa) / 1e9 - 123.7) < 0.5
+    cfg4, Qv, Qa = named_config("cfg4")
+    assert abs(cfg4.flops_fwd_per_clip(Qv, Qa) / 1e9 - 227.7) < 0.5
