@@ -1,0 +1,120 @@
+/* libtim_b200 — C ABI of the B200-native TIM encoder forward.
+ *
+ * The reference (JacobChalk/TIM) has no FFI: its seam for this path is the Python nn.Module
+ *     TIM.forward(inputs, forward_type, ...)      recognition/time_interval_machine/models/tim.py:174-191
+ *                                                 detection/time_interval_machine/models/tim.py:415-430
+ * plus the state_dict key layout (utils/checkpoint.py:17-36). Each entry point below names the reference
+ * code it replaces; tim_b200/plugin.py binds them with ctypes and INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all device buffers passed in are owned by the caller (PyTorch) and only
+ *    borrowed for the call. The context owns its packed weights and its workspace.
+ *  - every function returns TIM_OK (0) or a negative tim_status; tim_last_error() gives the message. The library
+ *    never calls exit()/abort() and has NO CPU fallback: without a B200 (sm_100) device tim_create() fails.
+ *  - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream). Device entry points
+ *    only enqueue work on it and never synchronise; one host thread per context.
+ */
+#ifndef TIM_B200_H
+#define TIM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TIM_ABI_VERSION 1
+
+typedef enum {
+    TIM_OK = 0,
+    TIM_ERR_INVALID = -1,      /* bad argument / unsupported configuration */
+    TIM_ERR_CUDA = -2,         /* a CUDA runtime / driver call failed */
+    TIM_ERR_NO_DEVICE = -3,    /* no sm_100 device: the library refuses to run (no fallback) */
+    TIM_ERR_WEIGHTS = -4,      /* unknown key, wrong shape, or weights missing at forward time */
+    TIM_ERR_NOMEM = -5
+} tim_status;
+
+enum { TIM_FP32 = 0, TIM_BF16 = 1, TIM_FP16 = 2 };                      /* compute_dtype */
+enum { TIM_AUDIO_VISUAL = 0, TIM_VISUAL = 1, TIM_AUDIO = 2 };           /* modalities */
+enum { TIM_RECOGNITION = 0, TIM_DETECTION = 1 };                        /* variant */
+
+/* Constructor arguments of the reference TIM (tim.py:18-34) flattened to ints.
+ * n_* = 0 means "head absent" (follows head.py's isinstance(num_class...) logic, see tim_b200/config.py). */
+typedef struct {
+    int32_t variant;            /* TIM_RECOGNITION | TIM_DETECTION (detection adds reg heads, shares query rows between heads) */
+    int32_t d_model;            /* transformer width is 2*d_model (tim.py:115-121) */
+    int32_t nhead;
+    int32_t num_layers;
+    int32_t ff_dim;             /* d_model * feedforward_scale */
+    int32_t vis_dim, aud_dim;   /* input feature widths */
+    int32_t num_feats;          /* feature tokens per modality */
+    int32_t input_modality;     /* which embedders exist */
+    int32_t data_modality;      /* which CLS queries / heads exist */
+    int32_t include_verb_noun;  /* recognition: separate verb/noun CLS token groups (encodings.py:166-171) */
+    int32_t n_verb, n_noun, n_action, n_audio;
+    int32_t compute_dtype;      /* TIM_FP32: CUDA-core fp32 everywhere (parity mode, <=1e-5 rel);
+                                   TIM_BF16 / TIM_FP16: 16-bit tcgen05 operands, fp32 accumulate / softmax / LayerNorm / residual */
+} tim_config;
+
+/* Caller-allocated outputs of the encoder; NULL where the reference returns None. fp32, contiguous.
+ * Shapes follow head.py's flatten(0,1): [B*Qv, n_*] / [B*Qa, n_audio]; reg [B*Q, 2]; feats [B, F_tot, 2*d_model]. */
+typedef struct {
+    float* verb;
+    float* noun;
+    float* action;
+    float* audio;
+    float* reg_visual;
+    float* reg_audio;
+    float* feats;               /* x[:, :num_feats] of tim.py:172 (may be NULL to skip) */
+} tim_outputs;
+
+typedef struct tim_ctx tim_ctx;
+
+int tim_abi_version(void);
+
+/* One context per (process, device); replaces TIM.__init__/_create_model (tim.py:17-145) for the hot path. */
+int tim_create(tim_ctx** out, const tim_config* cfg, int device);
+void tim_destroy(tim_ctx* ctx);
+const char* tim_last_error(const tim_ctx* ctx);        /* ctx may be NULL: error of the last failed tim_create() */
+
+/* Load one parameter by its reference state_dict key (checkpoint contract, utils/checkpoint.py:17-36).
+ * `data` is a device pointer to contiguous fp32 with the reference's shape; the library packs its own copy
+ * (16-bit operand copy for GEMM weights, 1/sqrt(head_dim)*log2(e) folded into the q rows of in_proj).
+ * Keys off the hot path (drloc_mlp.*, pool.*) are accepted and ignored. Call again after optimizer.step(). */
+int tim_set_weight(tim_ctx* ctx, const char* key, const float* data, const int64_t* shape, int ndim, void* stream);
+int tim_weights_missing(const tim_ctx* ctx, char* buf, size_t buflen);   /* number of required keys not yet set; names into buf */
+
+/* forward_type == "time_mlp" (tim.py:181-182): times [B, T, 2] fp32 -> out [B, T, d_model] fp32 (device pointers). */
+int tim_time_mlp_fwd(tim_ctx* ctx, const float* times, float* out, int B, int T, void* stream);
+
+/* forward_type == "encoder" (tim.py:147-172; detection forward_inference :378-400 after its own time_mlp):
+ * vis [B, F, vis_dim], aud [B, F, aud_dim] (NULL if the modality is absent), time_enc [B, T, d_model], all fp32 device.
+ * T = F_tot + Qv + Qa (time rows: vis feats, aud feats, visual queries, audio queries). */
+int tim_encoder_fwd(tim_ctx* ctx, const float* vis, const float* aud, const float* time_enc, int B, int T, int Qv, int Qa,
+                    const tim_outputs* outs, void* stream);
+
+/* End-to-end call on HOST buffers (pinned or pageable): time_mlp + encoder with the H2D input copies and D2H
+ * result copies inside the call, chunked over clips and overlapped on three internal streams. Blocks until the
+ * outputs are in host memory. `times` is [B, T, 2]; outputs as in tim_outputs but host pointers.
+ * h2d_bytes / d2h_bytes (optional) receive the bytes moved. */
+int tim_forward_host(tim_ctx* ctx, const float* vis, const float* aud, const float* times, int B, int T, int Qv, int Qa,
+                     const tim_outputs* host_outs, int clips_per_chunk, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+
+/* Introspection used by bench.py / tests. */
+size_t tim_workspace_bytes(const tim_ctx* ctx);         /* bytes currently held by the context's workspace */
+uint64_t tim_launch_count(const tim_ctx* ctx);          /* kernels launched by this context so far */
+int tim_seq_len(const tim_config* cfg, int Qv, int Qa); /* S = F_tot + query tokens (pure host arithmetic) */
+
+/* Single-kernel test hooks (tests/ only): C[M,N] = act(A[M,K] W[N,K]^T + bias) (+resid), fp32 in / fp32 out,
+ * computed through the selected compute path (the 16-bit paths cast A and W on device first). */
+int tim_test_linear(int compute_dtype, const float* A, const float* W, const float* bias, const float* resid, float* out,
+                    int M, int N, int K, int act, void* stream);
+/* attention over a two-stream qkv buffer [(B*Ft + B*Qt), 3*H*hd] fp32 -> out [(B*Ft + B*Qt), H*hd] fp32.
+ * The q columns must already carry the hd^-0.5 * log2(e) factor that tim_set_weight folds into in_proj. */
+int tim_test_attention(int compute_dtype, const float* qkv, float* out, int B, int Ft, int Qt, int H, int hd, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TIM_B200_H */

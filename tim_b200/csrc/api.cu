@@ -1,0 +1,903 @@
+// C ABI of libtim_b200 (declared in include/tim_b200.h): context, weight packing keyed by the reference's
+// state_dict names, and the host-side schedule of the forward (which kernels run in which order on which buffers).
+// The arithmetic lives in gemm_umma.cu / gemm_simt.cu / attention.cu / elementwise.cu.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/tim_b200.h"
+#include "kernels.h"
+
+using namespace tim;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct LinearW {
+    int N = 0, K = 0;
+    void* w = nullptr;          // [N, K] in the compute dtype
+    float* bias = nullptr;      // [N] fp32
+    CUtensorMap tmB;            // 16-bit modes only
+    int block_n = 0;
+    int scale_rows = 0;         // leading rows (and bias entries) multiplied by `scale` when packed (q part of in_proj)
+    float scale = 1.0f;
+};
+
+struct Slot {                   // one state_dict key
+    enum Kind { LIN_W, LIN_B, VEC } kind;
+    LinearW* lin = nullptr;
+    float* vec = nullptr;       // VEC destination
+    std::vector<int64_t> shape;
+    bool set = false;
+};
+
+struct Layer {
+    LinearW in_proj, out_proj, lin1, lin2;
+    float *n1g, *n1b, *n2g, *n2b;
+};
+
+struct RegHead {
+    LinearW l0, l2;
+    float* w4 = nullptr;        // [2, E/2]
+    float* b4 = nullptr;        // [2]
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct tim_ctx {
+    tim_config cfg;
+    int device = 0, num_sms = 0;
+    int d = 0, E = 0, FF = 0, H = 0, hd = 0, L = 0, F = 0, Fv = 0, Fa = 0, Ft = 0;
+    bool vis_data = false, aud_data = false, vn_tokens = false;
+    size_t esize = 4;           // bytes per element of the compute dtype
+    std::string err;
+    uint64_t launches = 0;
+    EncodeTiledFn encode = nullptr;
+
+    // weights
+    std::map<std::string, Slot> slots;
+    std::vector<void*> allocs;
+    float *t0w = nullptr, *t0b = nullptr, *tlg = nullptr, *tlb = nullptr;
+    LinearW t2, t4, emb_v, emb_a;
+    float *lnv_g = nullptr, *lnv_b = nullptr, *lna_g = nullptr, *lna_b = nullptr;
+    float *mod_v = nullptr, *mod_a = nullptr;
+    float *cls_verb = nullptr, *cls_noun = nullptr, *cls_action = nullptr, *cls_audio = nullptr;
+    std::vector<Layer> layers;
+    LinearW h_verb, h_noun, h_action, h_audio;
+    RegHead reg_v, reg_a;
+
+    // workspace arena (grow-only)
+    uint8_t* ws = nullptr;
+    size_t ws_bytes = 0;
+    // staging for tim_forward_host
+    uint8_t* io = nullptr;
+    size_t io_bytes = 0;
+    cudaStream_t s_h2d = nullptr, s_comp = nullptr, s_d2h = nullptr;
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof(buf), fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+};
+
+namespace {
+
+#define CU_OK(ctx, expr)                                                                                   \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess)                                                                             \
+            return (ctx)->fail(TIM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define LAUNCH(ctx, expr)                                                                                  \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        (ctx)->launches++;                                                                                 \
+        if (_e != cudaSuccess)                                                                             \
+            return (ctx)->fail(TIM_ERR_CUDA, "launch %s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define TIM_TRY(expr)              \
+    do {                           \
+        int _r = (expr);           \
+        if (_r != TIM_OK) return _r; \
+    } while (0)
+
+int dev_alloc(tim_ctx* c, void** p, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) return c->fail(TIM_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    c->allocs.push_back(*p);
+    return TIM_OK;
+}
+
+int get_encode_fn(tim_ctx* c) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn)
+        return c->fail(TIM_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable: %s", cudaGetErrorString(e));
+    c->encode = reinterpret_cast<EncodeTiledFn>(fn);
+    return TIM_OK;
+}
+
+// 16-bit K-major operand map: dims (K, rows, groups), box (64, box_r, box_g), 128-byte swizzle, zero OOB fill.
+int make_tmap(tim_ctx* c, CUtensorMap* tm, const void* base, int K, long long rows, long long groups, int box_r, int box_g) {
+    if (K % 8) return c->fail(TIM_ERR_INVALID, "tcgen05 path needs K %% 8 == 0 (got K=%d)", K);
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return c->fail(TIM_ERR_INVALID, "operand base not 16-byte aligned");
+    const CUtensorMapDataType dt = c->cfg.compute_dtype == TIM_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(groups)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(K) * 2, static_cast<cuuint64_t>(K) * 2 * static_cast<cuuint64_t>(rows)};
+    cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_r), static_cast<cuuint32_t>(box_g)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = c->encode(tm, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return c->fail(TIM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) K=%d rows=%lld groups=%lld box=(%d,%d)", static_cast<int>(r), K, rows, groups, box_r, box_g);
+    return TIM_OK;
+}
+
+int make_tmap_w(tim_ctx* c, LinearW& w) {
+    const CUtensorMapDataType dt = c->cfg.compute_dtype == TIM_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    if (w.K % 8) return c->fail(TIM_ERR_INVALID, "tcgen05 path needs K %% 8 == 0 (weight K=%d)", w.K);
+    w.block_n = umma_block_n(w.N);
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(w.K), static_cast<cuuint64_t>(w.N)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(w.K) * 2};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(w.block_n)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = c->encode(&w.tmB, dt, 2, w.w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return c->fail(TIM_ERR_CUDA, "cuTensorMapEncodeTiled(weight %dx%d) failed (%d)", w.N, w.K, static_cast<int>(r));
+    return TIM_OK;
+}
+
+int add_linear(tim_ctx* c, const std::string& prefix, LinearW& w, int N, int K, int scale_rows = 0, float scale = 1.0f,
+               const char* wname = "weight", const char* bname = "bias") {
+    w.N = N; w.K = K; w.scale_rows = scale_rows; w.scale = scale;
+    TIM_TRY(dev_alloc(c, &w.w, static_cast<size_t>(N) * K * c->esize));
+    TIM_TRY(dev_alloc(c, reinterpret_cast<void**>(&w.bias), static_cast<size_t>(N) * sizeof(float)));
+    if (c->cfg.compute_dtype != TIM_FP32) TIM_TRY(make_tmap_w(c, w));
+    Slot sw; sw.kind = Slot::LIN_W; sw.lin = &w; sw.shape = {N, K};
+    Slot sb; sb.kind = Slot::LIN_B; sb.lin = &w; sb.shape = {N};
+    c->slots[prefix + wname] = sw;
+    c->slots[prefix + bname] = sb;
+    return TIM_OK;
+}
+
+int add_vec(tim_ctx* c, const std::string& key, float** dst, std::vector<int64_t> shape) {
+    size_t n = 1;
+    for (auto s : shape) n *= static_cast<size_t>(s);
+    TIM_TRY(dev_alloc(c, reinterpret_cast<void**>(dst), n * sizeof(float)));
+    Slot s; s.kind = Slot::VEC; s.vec = *dst; s.shape = shape;
+    c->slots[key] = s;
+    return TIM_OK;
+}
+
+int build_weights(tim_ctx* c) {
+    const tim_config& g = c->cfg;
+    const int d = c->d, E = c->E, FF = c->FF;
+    TIM_TRY(add_vec(c, "time_mlp.0.weight", &c->t0w, {d, 2}));
+    TIM_TRY(add_vec(c, "time_mlp.0.bias", &c->t0b, {d}));
+    TIM_TRY(add_linear(c, "time_mlp.2.", c->t2, d, d));
+    TIM_TRY(add_linear(c, "time_mlp.4.", c->t4, d, d));
+    TIM_TRY(add_vec(c, "time_mlp.6.weight", &c->tlg, {d}));
+    TIM_TRY(add_vec(c, "time_mlp.6.bias", &c->tlb, {d}));
+    const std::string fe = "feature_encoding.";
+    const bool recog = g.variant == TIM_RECOGNITION;
+    if (g.input_modality == TIM_AUDIO_VISUAL) {
+        TIM_TRY(add_vec(c, fe + "visual_modality_encoding", &c->mod_v, {1, 1, E}));
+        TIM_TRY(add_vec(c, fe + "audio_modality_encoding", &c->mod_a, {1, 1, E}));
+        if (c->vis_data) {
+            TIM_TRY(add_vec(c, fe + "visual_action_cls", &c->cls_action, {1, 1, d}));
+            if (c->vn_tokens) {
+                TIM_TRY(add_vec(c, fe + "visual_verb_cls", &c->cls_verb, {1, 1, d}));
+                TIM_TRY(add_vec(c, fe + "visual_noun_cls", &c->cls_noun, {1, 1, d}));
+            }
+        }
+        if (c->aud_data) TIM_TRY(add_vec(c, fe + "audio_action_cls", &c->cls_audio, {1, 1, d}));
+    } else if (g.input_modality == TIM_VISUAL) {
+        TIM_TRY(add_vec(c, fe + (recog ? "action_cls" : "visual_action_cls"), &c->cls_action, {1, 1, d}));
+        if (c->vn_tokens) {
+            TIM_TRY(add_vec(c, fe + "verb_cls", &c->cls_verb, {1, 1, d}));
+            TIM_TRY(add_vec(c, fe + "noun_cls", &c->cls_noun, {1, 1, d}));
+        }
+    } else {
+        TIM_TRY(add_vec(c, fe + (recog ? "action_cls" : "audio_action_cls"), &c->cls_audio, {1, 1, d}));
+    }
+    if (c->Fv) {
+        TIM_TRY(add_linear(c, fe + "visual_embedder.1.", c->emb_v, d, g.vis_dim));
+        TIM_TRY(add_vec(c, fe + "visual_embedder.3.weight", &c->lnv_g, {d}));
+        TIM_TRY(add_vec(c, fe + "visual_embedder.3.bias", &c->lnv_b, {d}));
+    }
+    if (c->Fa) {
+        TIM_TRY(add_linear(c, fe + "audio_embedder.1.", c->emb_a, d, g.aud_dim));
+        TIM_TRY(add_vec(c, fe + "audio_embedder.3.weight", &c->lna_g, {d}));
+        TIM_TRY(add_vec(c, fe + "audio_embedder.3.bias", &c->lna_b, {d}));
+    }
+    if (g.n_verb) TIM_TRY(add_linear(c, "cls_head.fc_visual_verb.", c->h_verb, g.n_verb, E));
+    if (g.n_noun) TIM_TRY(add_linear(c, "cls_head.fc_visual_noun.", c->h_noun, g.n_noun, E));
+    if (g.n_action) TIM_TRY(add_linear(c, "cls_head.fc_visual_action.", c->h_action, g.n_action, E));
+    if (g.n_audio) TIM_TRY(add_linear(c, "cls_head.fc_audio_action.", c->h_audio, g.n_audio, E));
+    if (g.variant == TIM_DETECTION) {
+        auto add_reg = [&](const std::string& p, RegHead& r) -> int {
+            TIM_TRY(add_linear(c, p + "0.", r.l0, E / 2, E));
+            TIM_TRY(add_linear(c, p + "2.", r.l2, E / 2, E / 2));
+            TIM_TRY(add_vec(c, p + "4.weight", &r.w4, {2, E / 2}));
+            TIM_TRY(add_vec(c, p + "4.bias", &r.b4, {2}));
+            return TIM_OK;
+        };
+        if (c->vis_data) TIM_TRY(add_reg("reg_head.fc_visual_action.", c->reg_v));
+        if (c->aud_data) TIM_TRY(add_reg("reg_head.fc_audio_action.", c->reg_a));
+    }
+    c->layers.resize(c->L);
+    const std::string enc = recog ? "transformer_encoder" : "backbone";
+    const float qscale = static_cast<float>(std::pow(static_cast<double>(c->hd), -0.5) * 1.4426950408889634074);
+    for (int l = 0; l < c->L; ++l) {
+        Layer& ly = c->layers[l];
+        const std::string p = enc + ".layers." + std::to_string(l) + ".";
+        TIM_TRY(add_linear(c, p + "self_attn.", ly.in_proj, 3 * E, E, E, qscale, "in_proj_weight", "in_proj_bias"));
+        TIM_TRY(add_linear(c, p + "self_attn.out_proj.", ly.out_proj, E, E));
+        TIM_TRY(add_vec(c, p + "norm1.weight", &ly.n1g, {E}));
+        TIM_TRY(add_vec(c, p + "norm1.bias", &ly.n1b, {E}));
+        TIM_TRY(add_linear(c, p + "linear1.", ly.lin1, FF, E));
+        TIM_TRY(add_linear(c, p + "linear2.", ly.lin2, E, FF));
+        TIM_TRY(add_vec(c, p + "norm2.weight", &ly.n2g, {E}));
+        TIM_TRY(add_vec(c, p + "norm2.bias", &ly.n2b, {E}));
+    }
+    return TIM_OK;
+}
+
+int ensure_ws(tim_ctx* c, size_t bytes) {
+    if (bytes <= c->ws_bytes) return TIM_OK;
+    if (c->ws) { cudaDeviceSynchronize(); cudaFree(c->ws); c->ws = nullptr; c->ws_bytes = 0; }
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->ws), bytes);
+    if (e != cudaSuccess) return c->fail(TIM_ERR_NOMEM, "workspace cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    c->ws_bytes = bytes;
+    return TIM_OK;
+}
+
+struct Arena {
+    uint8_t* base; size_t off = 0;
+    template <typename P> void take(P** p, size_t bytes) {
+        *p = base ? reinterpret_cast<P*>(base + off) : nullptr;
+        off += align_up(bytes ? bytes : 16, 256);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// one linear layer through the selected compute path
+// ------------------------------------------------------------------------------------------------------------------
+template <typename T>
+int run_linear(tim_ctx* c, const void* A, int lda, const LinearW& w, RowMap rm, Epilogue ep, cudaStream_t s) {
+    if (lda != w.K) return c->fail(TIM_ERR_INVALID, "linear: lda %d != K %d", lda, w.K);
+    if (rm.G <= 0 || rm.R <= 0) return TIM_OK;
+    if (!ep.bias) ep.bias = w.bias;
+    if constexpr (std::is_same<T, float>::value) {
+        ep.out_fp32 = 1;
+        LAUNCH(c, launch_linear_simt(static_cast<const float*>(A), lda, static_cast<const float*>(w.w), w.N, w.K, rm, ep, s));
+    } else {
+        UmmaParams p;
+        std::memset(&p, 0, sizeof(p));
+        TIM_TRY(make_tmap(c, &p.tmA, A, w.K, rm.a_group_rows, rm.G, rm.box_r, rm.box_g));
+        p.tmB = w.tmB;
+        p.N = w.N; p.K = w.K; p.rm = rm; p.ep = ep;
+        LAUNCH(c, launch_linear_umma<T>(p, w.block_n, c->num_sms, s));
+    }
+    return TIM_OK;
+}
+
+inline Epilogue epi(void* out, int ldo, bool out_fp32, int act = ACT_NONE, const float* resid = nullptr, int ldr = 0) {
+    Epilogue e;
+    e.bias = nullptr; e.resid = resid; e.ldr = ldr; e.out = out; e.ldo = ldo; e.out_fp32 = out_fp32 ? 1 : 0; e.act = act;
+    return e;
+}
+
+// rows of one query-token group [off, off+Q) inside each clip's Qt query rows
+inline RowMap group_rows(int B, int Qt, int off, int Q) {
+    RowMap rm;
+    rm.G = B; rm.R = Q;
+    if (Q <= 128) { rm.box_r = Q; rm.box_g = 128 / Q; if (rm.box_g > B) rm.box_g = B; if (rm.box_g > 256) rm.box_g = 256; }
+    else { rm.box_r = 128; rm.box_g = 1; }
+    rm.a_group_rows = Qt; rm.a_row_off = off;
+    rm.out_group_rows = Q; rm.out_row_off = 0;
+    return rm;
+}
+
+template <typename T>
+int time_mlp_impl(tim_ctx* c, const float* times, float* out, int B, int T_, cudaStream_t s, uint8_t* ws_base, size_t* ws_need) {
+    const int M = B * T_, d = c->d;
+    Arena a{ws_base};
+    T *t1, *t2; float* t3;
+    a.take(&t1, static_cast<size_t>(M) * d * sizeof(T));
+    a.take(&t2, static_cast<size_t>(M) * d * sizeof(T));
+    a.take(&t3, static_cast<size_t>(M) * d * sizeof(float));
+    if (ws_need) { *ws_need = a.off; return TIM_OK; }
+    constexpr bool f32 = std::is_same<T, float>::value;
+    LAUNCH(c, launch_time_l1<T>(times, c->t0w, c->t0b, t1, M, d, s));
+    TIM_TRY(run_linear<T>(c, t1, d, c->t2, plain_rows(M), epi(t2, d, f32, ACT_RELU), s));
+    TIM_TRY(run_linear<T>(c, t2, d, c->t4, plain_rows(M), epi(t3, d, true, ACT_RELU), s));
+    LAUNCH(c, launch_layernorm<T>(t3, d, c->tlg, c->tlb, out, d, static_cast<T*>(nullptr), 0, M, d, s));
+    return TIM_OK;
+}
+
+struct QueryPlan {
+    int Qv = 0, Qa = 0, Qt = 0;
+    int n_groups = 0;
+    TokenGroup groups[4];
+    int off_verb = -1, off_noun = -1, off_action = -1, off_audio = -1;
+};
+
+int plan_queries(tim_ctx* c, int T_, int Qv, int Qa, QueryPlan* qp) {
+    const tim_config& g = c->cfg;
+    qp->Qv = c->vis_data ? Qv : 0;
+    qp->Qa = c->aud_data ? Qa : 0;
+    if (qp->Qv < 0 || qp->Qa < 0) return c->fail(TIM_ERR_INVALID, "negative query count");
+    int off = 0;
+    auto add = [&](const float* cls, const float* mod, int te_off, int count, int* where) {
+        TokenGroup& tg = qp->groups[qp->n_groups++];
+        tg.cls = cls; tg.mod = mod; tg.te_off = te_off; tg.count = count;
+        *where = off; off += count;
+    };
+    const bool av = g.input_modality == TIM_AUDIO_VISUAL;
+    if (qp->Qv > 0) {
+        const int te_off = c->Ft;
+        const float* mod = av ? c->mod_v : nullptr;
+        if (c->vn_tokens) {
+            add(c->cls_verb, mod, te_off, qp->Qv, &qp->off_verb);
+            add(c->cls_noun, mod, te_off, qp->Qv, &qp->off_noun);
+        }
+        add(c->cls_action, mod, te_off, qp->Qv, &qp->off_action);
+        if (te_off + qp->Qv > T_) return c->fail(TIM_ERR_INVALID, "time encodings too short: T=%d < %d", T_, te_off + qp->Qv);
+    }
+    if (qp->Qa > 0) {
+        const int te_off = av ? T_ - qp->Qa : c->Ft;      // encodings.py:241 uses query_time_encoding[:, -num_a_queries:]
+        if (te_off < c->Ft || te_off + qp->Qa > T_) return c->fail(TIM_ERR_INVALID, "time encodings too short for %d audio queries (T=%d)", qp->Qa, T_);
+        add(c->cls_audio, av ? c->mod_a : nullptr, te_off, qp->Qa, &qp->off_audio);
+    }
+    qp->Qt = off;
+    if (T_ < c->Ft) return c->fail(TIM_ERR_INVALID, "T=%d smaller than the %d feature tokens", T_, c->Ft);
+    return TIM_OK;
+}
+
+template <typename T>
+int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te, int B, int T_, int Qv, int Qa,
+                 const tim_outputs* o, cudaStream_t s, uint8_t* ws_base, size_t* ws_need) {
+    constexpr bool f32 = std::is_same<T, float>::value;
+    const tim_config& g = c->cfg;
+    const int d = c->d, E = c->E, FF = c->FF;
+    QueryPlan qp;
+    TIM_TRY(plan_queries(c, T_, Qv, Qa, &qp));
+    const int Ft = c->Ft, Qt = qp.Qt;
+    const size_t Mf = static_cast<size_t>(B) * Ft, Mq = static_cast<size_t>(B) * Qt, M = Mf + Mq;
+    if (M > 0x7fffffffull) return c->fail(TIM_ERR_INVALID, "too many token rows (%zu)", M);
+
+    Arena a{ws_base};
+    float *x32, *z, *embv, *emba; T *x16, *qkv, *att, *hid, *vis16, *aud16, *r1, *r2;
+    a.take(&x32, M * E * sizeof(float));
+    a.take(&z, M * E * sizeof(float));
+    a.take(&x16, f32 ? 0 : M * E * sizeof(T));
+    a.take(&qkv, M * 3 * E * sizeof(T));
+    a.take(&att, M * E * sizeof(T));
+    a.take(&hid, M * FF * sizeof(T));
+    a.take(&embv, static_cast<size_t>(B) * c->Fv * d * sizeof(float));
+    a.take(&emba, static_cast<size_t>(B) * c->Fa * d * sizeof(float));
+    a.take(&vis16, f32 ? 0 : static_cast<size_t>(B) * c->Fv * g.vis_dim * sizeof(T));
+    a.take(&aud16, f32 ? 0 : static_cast<size_t>(B) * c->Fa * g.aud_dim * sizeof(T));
+    const size_t regrows = static_cast<size_t>(B) * (qp.Qv > qp.Qa ? qp.Qv : qp.Qa);
+    a.take(&r1, g.variant == TIM_DETECTION ? regrows * (E / 2) * sizeof(T) : 0);
+    a.take(&r2, g.variant == TIM_DETECTION ? regrows * (E / 2) * sizeof(T) : 0);
+    if (ws_need) { *ws_need = a.off; return TIM_OK; }
+
+    // ---- embedders: Linear -> GELU (epilogue) -> pre-LN rows; LN happens while assembling tokens ----
+    const int Mv = B * c->Fv, Ma = B * c->Fa;
+    if (c->Fv) {
+        if (!vis) return c->fail(TIM_ERR_INVALID, "visual input is NULL");
+        const void* A = vis;
+        if constexpr (!f32) { LAUNCH(c, launch_cast<T>(vis, vis16, Mv, g.vis_dim, 0, 1.0f, s)); A = vis16; }
+        TIM_TRY(run_linear<T>(c, A, g.vis_dim, c->emb_v, plain_rows(Mv), epi(embv, d, true, ACT_GELU), s));
+    }
+    if (c->Fa) {
+        if (!aud) return c->fail(TIM_ERR_INVALID, "audio input is NULL");
+        const void* A = aud;
+        if constexpr (!f32) { LAUNCH(c, launch_cast<T>(aud, aud16, Ma, g.aud_dim, 0, 1.0f, s)); A = aud16; }
+        TIM_TRY(run_linear<T>(c, A, g.aud_dim, c->emb_a, plain_rows(Ma), epi(emba, d, true, ACT_GELU), s));
+    }
+    // ---- token assembly into the two-stream buffer ----
+    AssembleParams ap;
+    std::memset(&ap, 0, sizeof(ap));
+    ap.B = B; ap.d = d; ap.T = T_; ap.Fv = c->Fv; ap.Fa = c->Fa;
+    ap.emb_v = embv; ap.emb_a = emba;
+    ap.ln_v_g = c->lnv_g; ap.ln_v_b = c->lnv_b; ap.ln_a_g = c->lna_g; ap.ln_a_b = c->lna_b;
+    ap.mod_v = g.input_modality == TIM_AUDIO_VISUAL ? c->mod_v : nullptr;
+    ap.mod_a = g.input_modality == TIM_AUDIO_VISUAL ? c->mod_a : nullptr;
+    ap.te = te; ap.n_groups = qp.n_groups;
+    for (int i = 0; i < qp.n_groups; ++i) ap.groups[i] = qp.groups[i];
+    ap.Qt = Qt; ap.x32 = x32; ap.x16 = f32 ? nullptr : x16;
+    LAUNCH(c, launch_assemble<T>(ap, s));
+
+    // ---- encoder layers (post-LN): x = LN1(x + out_proj(attn(in_proj(x)))); x = LN2(x + W2 gelu(W1 x)) ----
+    const int Mi = static_cast<int>(M);
+    const void* xin = f32 ? static_cast<const void*>(x32) : static_cast<const void*>(x16);
+    T* x16o = f32 ? nullptr : x16;
+    for (int l = 0; l < c->L; ++l) {
+        Layer& ly = c->layers[l];
+        TIM_TRY(run_linear<T>(c, xin, E, ly.in_proj, plain_rows(Mi), epi(qkv, 3 * E, f32), s));
+        if constexpr (f32) {
+            LAUNCH(c, launch_attention_simt(reinterpret_cast<const float*>(qkv), reinterpret_cast<float*>(att), B, Ft, Qt, c->H, c->hd, s));
+        } else {
+            LAUNCH(c, launch_attention_mma<T>(qkv, att, B, Ft, Qt, c->H, c->hd, s));
+        }
+        TIM_TRY(run_linear<T>(c, att, E, ly.out_proj, plain_rows(Mi), epi(z, E, true, ACT_NONE, x32, E), s));
+        LAUNCH(c, launch_layernorm<T>(z, E, ly.n1g, ly.n1b, x32, E, x16o, E, Mi, E, s));
+        TIM_TRY(run_linear<T>(c, xin, E, ly.lin1, plain_rows(Mi), epi(hid, FF, f32, ACT_GELU), s));
+        TIM_TRY(run_linear<T>(c, hid, FF, ly.lin2, plain_rows(Mi), epi(z, E, true, ACT_NONE, x32, E), s));
+        LAUNCH(c, launch_layernorm<T>(z, E, ly.n2g, ly.n2b, x32, E, x16o, E, Mi, E, s));
+    }
+
+    // ---- heads read slices of the query stream ----
+    const uint8_t* qbase = reinterpret_cast<const uint8_t*>(xin) + Mf * E * sizeof(T);
+    auto cls = [&](const LinearW& w, int off, int Q, float* out) -> int {
+        if (!w.N || Q <= 0) return TIM_OK;
+        if (!out) return c->fail(TIM_ERR_INVALID, "output pointer for a %d-class head is NULL", w.N);
+        return run_linear<T>(c, qbase, E, w, group_rows(B, Qt, off, Q), epi(out, w.N, true), s);
+    };
+    auto reg = [&](RegHead& r, int off, int Q, float* out) -> int {
+        if (Q <= 0) return TIM_OK;
+        if (!out) return c->fail(TIM_ERR_INVALID, "regression output pointer is NULL");
+        RowMap rm = group_rows(B, Qt, off, Q);
+        TIM_TRY(run_linear<T>(c, qbase, E, r.l0, rm, epi(r1, E / 2, f32, ACT_RELU), s));
+        TIM_TRY(run_linear<T>(c, r1, E / 2, r.l2, plain_rows(B * Q), epi(r2, E / 2, f32, ACT_RELU), s));
+        LAUNCH(c, launch_reg_final<T>(r2, E / 2, r.w4, r.b4, out, B * Q, E / 2, s));
+        return TIM_OK;
+    };
+    if (g.variant == TIM_RECOGNITION) {
+        if (qp.Qv > 0) {
+            if (g.n_verb && qp.off_verb >= 0) TIM_TRY(cls(c->h_verb, qp.off_verb, qp.Qv, o->verb));
+            if (g.n_noun && qp.off_noun >= 0) TIM_TRY(cls(c->h_noun, qp.off_noun, qp.Qv, o->noun));
+            TIM_TRY(cls(c->h_action, qp.off_action, qp.Qv, o->action));
+        }
+        if (qp.Qa > 0) TIM_TRY(cls(c->h_audio, qp.off_audio, qp.Qa, o->audio));
+    } else {
+        if (qp.Qv > 0) {
+            TIM_TRY(cls(c->h_verb, qp.off_action, qp.Qv, o->verb));
+            TIM_TRY(cls(c->h_noun, qp.off_action, qp.Qv, o->noun));
+            TIM_TRY(cls(c->h_action, qp.off_action, qp.Qv, o->action));
+            TIM_TRY(reg(c->reg_v, qp.off_action, qp.Qv, o->reg_visual));
+        }
+        if (qp.Qa > 0) {
+            TIM_TRY(cls(c->h_audio, qp.off_audio, qp.Qa, o->audio));
+            TIM_TRY(reg(c->reg_a, qp.off_audio, qp.Qa, o->reg_audio));
+        }
+    }
+    if (o->feats && Mf) CU_OK(c, cudaMemcpyAsync(o->feats, x32, Mf * E * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return TIM_OK;
+}
+
+int check_ready(tim_ctx* c) {
+    for (auto& kv : c->slots)
+        if (!kv.second.set) return c->fail(TIM_ERR_WEIGHTS, "weight '%s' has not been set", kv.first.c_str());
+    return TIM_OK;
+}
+
+template <typename F>
+int dispatch_dtype(tim_ctx* c, F&& f) {
+    switch (c->cfg.compute_dtype) {
+        case TIM_FP32: return f(float{});
+        case TIM_BF16: return f(__nv_bfloat16{});
+        case TIM_FP16: return f(__half{});
+    }
+    return c->fail(TIM_ERR_INVALID, "bad compute_dtype %d", c->cfg.compute_dtype);
+}
+
+int time_mlp_ws(tim_ctx* c, int B, int T_, size_t* need) {
+    return dispatch_dtype(c, [&](auto tag) { return time_mlp_impl<decltype(tag)>(c, nullptr, nullptr, B, T_, nullptr, nullptr, need); });
+}
+int encoder_ws(tim_ctx* c, int B, int T_, int Qv, int Qa, size_t* need) {
+    tim_outputs o; std::memset(&o, 0, sizeof(o));
+    return dispatch_dtype(c, [&](auto tag) { return encoder_impl<decltype(tag)>(c, nullptr, nullptr, nullptr, B, T_, Qv, Qa, &o, nullptr, nullptr, need); });
+}
+
+}  // namespace
+
+// ======================================================================================================================
+// extern "C"
+// ======================================================================================================================
+extern "C" {
+
+int tim_abi_version(void) { return TIM_ABI_VERSION; }
+
+const char* tim_last_error(const tim_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int tim_seq_len(const tim_config* g, int Qv, int Qa) {
+    if (!g) return -1;
+    const int Ft = g->num_feats * (g->input_modality == TIM_AUDIO_VISUAL ? 2 : 1);
+    const bool vis = g->data_modality != TIM_AUDIO, aud = g->data_modality != TIM_VISUAL;
+    const bool vn = g->variant == TIM_RECOGNITION && g->include_verb_noun && vis;
+    int q = 0;
+    if (vis && Qv > 0) q += Qv * (vn ? 3 : 1);
+    if (aud && Qa > 0) q += Qa;
+    return Ft + q;
+}
+
+int tim_create(tim_ctx** out, const tim_config* cfg, int device) {
+    if (!out || !cfg) { g_create_error = "tim_create: NULL argument"; return TIM_ERR_INVALID; }
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) {
+        g_create_error = std::string("tim_create: no CUDA device (") + cudaGetErrorString(e) + "); libtim_b200 has no CPU fallback";
+        return TIM_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "tim_create: bad device index"; return TIM_ERR_INVALID; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+        g_create_error = "tim_create: device is not sm_100 (B200); libtim_b200 is built for sm_100a only and has no fallback";
+        return TIM_ERR_NO_DEVICE;
+    }
+    tim_ctx* c = new tim_ctx();
+    auto bail = [&](int code) { g_create_error = c->err; tim_destroy(c); return code; };
+    c->cfg = *cfg;
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    const tim_config& g = c->cfg;
+    if (g.d_model <= 0 || g.nhead <= 0 || g.num_layers < 0 || g.ff_dim <= 0 || g.num_feats <= 0 || (2 * g.d_model) % g.nhead)
+        return bail(c->fail(TIM_ERR_INVALID, "bad model dims"));
+    if (g.compute_dtype < TIM_FP32 || g.compute_dtype > TIM_FP16) return bail(c->fail(TIM_ERR_INVALID, "bad compute_dtype"));
+    if (g.input_modality != TIM_AUDIO_VISUAL && g.data_modality != g.input_modality)
+        return bail(c->fail(TIM_ERR_INVALID, "uni-modal input requires data_modality == input_modality"));
+    c->d = g.d_model; c->E = 2 * g.d_model; c->FF = g.ff_dim; c->H = g.nhead; c->hd = c->E / g.nhead; c->L = g.num_layers;
+    c->F = g.num_feats;
+    c->Fv = g.input_modality != TIM_AUDIO ? g.num_feats : 0;
+    c->Fa = g.input_modality != TIM_VISUAL ? g.num_feats : 0;
+    c->Ft = c->Fv + c->Fa;
+    c->vis_data = g.data_modality != TIM_AUDIO;
+    c->aud_data = g.data_modality != TIM_VISUAL;
+    c->vn_tokens = g.variant == TIM_RECOGNITION && g.include_verb_noun && c->vis_data;
+    c->esize = g.compute_dtype == TIM_FP32 ? 4 : 2;
+    if (c->d % 4) return bail(c->fail(TIM_ERR_INVALID, "d_model must be a multiple of 4"));
+    if (c->vis_data && !g.n_action) return bail(c->fail(TIM_ERR_INVALID, "visual data modality needs n_action > 0"));
+    if (c->aud_data && !g.n_audio) return bail(c->fail(TIM_ERR_INVALID, "audio data modality needs n_audio > 0"));
+    if (c->vn_tokens && (!g.n_verb || !g.n_noun)) return bail(c->fail(TIM_ERR_INVALID, "include_verb_noun needs n_verb and n_noun"));
+    if (g.compute_dtype != TIM_FP32) {
+        const int hd = c->hd;
+        if (!(hd == 16 || hd == 32 || hd == 64 || hd == 128 || hd == 192))
+            return bail(c->fail(TIM_ERR_INVALID, "16-bit attention supports head_dim in {16,32,64,128,192}, got %d", hd));
+        if (c->Ft > 128) return bail(c->fail(TIM_ERR_INVALID, "16-bit attention supports at most 128 feature tokens per clip, got %d", c->Ft));
+        if (c->d % 8 || g.vis_dim % 8 || g.aud_dim % 8 || c->FF % 8)
+            return bail(c->fail(TIM_ERR_INVALID, "tcgen05 path needs all reduction dims to be multiples of 8"));
+    } else if (attention_simt_smem(c->Ft, c->hd) > 227 * 1024) {
+        return bail(c->fail(TIM_ERR_INVALID, "fp32 attention: %d feature tokens x head_dim %d exceed shared memory", c->Ft, c->hd));
+    }
+    if (cudaSetDevice(device) != cudaSuccess) return bail(c->fail(TIM_ERR_CUDA, "cudaSetDevice failed"));
+    if (g.compute_dtype != TIM_FP32) { int r = get_encode_fn(c); if (r) return bail(r); }
+    int r = build_weights(c);
+    if (r) return bail(r);
+    *out = c;
+    return TIM_OK;
+}
+
+void tim_destroy(tim_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (void* p : c->allocs) cudaFree(p);
+    if (c->ws) cudaFree(c->ws);
+    if (c->io) cudaFree(c->io);
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_comp) cudaStreamDestroy(c->s_comp);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+    delete c;
+}
+
+int tim_set_weight(tim_ctx* c, const char* key, const float* data, const int64_t* shape, int ndim, void* stream) {
+    if (!c || !key) return TIM_ERR_INVALID;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!std::strncmp(key, "drloc_mlp.", 10) || !std::strncmp(key, "pool.", 5)) return TIM_OK;   // off the hot path
+    auto it = c->slots.find(key);
+    if (it == c->slots.end()) return c->fail(TIM_ERR_WEIGHTS, "unknown state_dict key '%s' for this configuration", key);
+    Slot& sl = it->second;
+    if (!data || !shape) return c->fail(TIM_ERR_INVALID, "NULL data/shape for '%s'", key);
+    bool ok = static_cast<size_t>(ndim) == sl.shape.size();
+    for (int i = 0; ok && i < ndim; ++i) ok = shape[i] == sl.shape[i];
+    if (!ok) return c->fail(TIM_ERR_WEIGHTS, "shape mismatch for '%s'", key);
+    CU_OK(c, cudaSetDevice(c->device));
+    if (sl.kind == Slot::VEC) {
+        size_t n = 1;
+        for (auto v : sl.shape) n *= static_cast<size_t>(v);
+        CU_OK(c, cudaMemcpyAsync(sl.vec, data, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    } else if (sl.kind == Slot::LIN_B) {
+        LinearW& w = *sl.lin;
+        if (w.scale_rows % 4) return c->fail(TIM_ERR_INVALID, "q rows (%d) must be a multiple of 4", w.scale_rows);
+        LAUNCH(c, launch_scale_copy(data, w.bias, w.N, 1, w.scale_rows, w.scale, s));
+    } else {
+        LinearW& w = *sl.lin;
+        if ((static_cast<size_t>(w.scale_rows) * w.K) % 4) return c->fail(TIM_ERR_INVALID, "scaled prefix not float4 aligned");
+        switch (c->cfg.compute_dtype) {
+            case TIM_FP32: LAUNCH(c, launch_scale_copy(data, static_cast<float*>(w.w), w.N, w.K, w.scale_rows, w.scale, s)); break;
+            case TIM_BF16: LAUNCH(c, launch_cast<__nv_bfloat16>(data, static_cast<__nv_bfloat16*>(w.w), w.N, w.K, w.scale_rows, w.scale, s)); break;
+            case TIM_FP16: LAUNCH(c, launch_cast<__half>(data, static_cast<__half*>(w.w), w.N, w.K, w.scale_rows, w.scale, s)); break;
+        }
+    }
+    sl.set = true;
+    return TIM_OK;
+}
+
+int tim_weights_missing(const tim_ctx* c, char* buf, size_t buflen) {
+    if (!c) return TIM_ERR_INVALID;
+    int n = 0;
+    std::string names;
+    for (auto& kv : c->slots)
+        if (!kv.second.set) { ++n; names += kv.first; names += '\n'; }
+    if (buf && buflen) { std::strncpy(buf, names.c_str(), buflen - 1); buf[buflen - 1] = 0; }
+    return n;
+}
+
+int tim_time_mlp_fwd(tim_ctx* c, const float* times, float* out, int B, int T_, void* stream) {
+    if (!c) return TIM_ERR_INVALID;
+    if (!times || !out || B <= 0 || T_ <= 0) return c->fail(TIM_ERR_INVALID, "tim_time_mlp_fwd: bad arguments");
+    TIM_TRY(check_ready(c));
+    CU_OK(c, cudaSetDevice(c->device));
+    size_t need = 0;
+    TIM_TRY(time_mlp_ws(c, B, T_, &need));
+    TIM_TRY(ensure_ws(c, need));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return dispatch_dtype(c, [&](auto tag) { return time_mlp_impl<decltype(tag)>(c, times, out, B, T_, s, c->ws, nullptr); });
+}
+
+int tim_encoder_fwd(tim_ctx* c, const float* vis, const float* aud, const float* te, int B, int T_, int Qv, int Qa,
+                    const tim_outputs* outs, void* stream) {
+    if (!c) return TIM_ERR_INVALID;
+    if (!te || !outs || B <= 0 || T_ <= 0) return c->fail(TIM_ERR_INVALID, "tim_encoder_fwd: bad arguments");
+    TIM_TRY(check_ready(c));
+    CU_OK(c, cudaSetDevice(c->device));
+    size_t need = 0;
+    TIM_TRY(encoder_ws(c, B, T_, Qv, Qa, &need));
+    TIM_TRY(ensure_ws(c, need));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return dispatch_dtype(c, [&](auto tag) { return encoder_impl<decltype(tag)>(c, vis, aud, te, B, T_, Qv, Qa, outs, s, c->ws, nullptr); });
+}
+
+int tim_forward_host(tim_ctx* c, const float* vis, const float* aud, const float* times, int B, int T_, int Qv, int Qa,
+                     const tim_outputs* ho, int cpc, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+    if (!c) return TIM_ERR_INVALID;
+    if (!times || !ho || B <= 0 || T_ <= 0) return c->fail(TIM_ERR_INVALID, "tim_forward_host: bad arguments");
+    TIM_TRY(check_ready(c));
+    CU_OK(c, cudaSetDevice(c->device));
+    const tim_config& g = c->cfg;
+    if (cpc <= 0 || cpc > B) cpc = B;
+    QueryPlan qp;
+    TIM_TRY(plan_queries(c, T_, Qv, Qa, &qp));
+    if (!c->s_h2d) {
+        CU_OK(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+        CU_OK(c, cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+        CU_OK(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    }
+    // per-clip sizes (floats)
+    const size_t n_vis = static_cast<size_t>(c->Fv) * g.vis_dim, n_aud = static_cast<size_t>(c->Fa) * g.aud_dim;
+    const size_t n_times = static_cast<size_t>(T_) * 2, n_te = static_cast<size_t>(T_) * c->d;
+    const size_t n_verb = ho->verb ? static_cast<size_t>(qp.Qv) * g.n_verb : 0, n_noun = ho->noun ? static_cast<size_t>(qp.Qv) * g.n_noun : 0;
+    const size_t n_act = ho->action ? static_cast<size_t>(qp.Qv) * g.n_action : 0, n_au = ho->audio ? static_cast<size_t>(qp.Qa) * g.n_audio : 0;
+    const size_t n_rv = ho->reg_visual ? static_cast<size_t>(qp.Qv) * 2 : 0, n_ra = ho->reg_audio ? static_cast<size_t>(qp.Qa) * 2 : 0;
+    const size_t n_feats = ho->feats ? static_cast<size_t>(c->Ft) * c->E : 0;
+    // two staging sets (double buffering across chunks)
+    struct Set { float *vis, *aud, *times, *te, *verb, *noun, *act, *au, *rv, *ra, *feats; };
+    Set st[2];
+    size_t io_need = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        Arena a{pass ? c->io : nullptr};
+        for (int k = 0; k < 2; ++k) {
+            a.take(&st[k].vis, cpc * n_vis * 4); a.take(&st[k].aud, cpc * n_aud * 4); a.take(&st[k].times, cpc * n_times * 4);
+            a.take(&st[k].te, cpc * n_te * 4); a.take(&st[k].verb, cpc * n_verb * 4); a.take(&st[k].noun, cpc * n_noun * 4);
+            a.take(&st[k].act, cpc * n_act * 4); a.take(&st[k].au, cpc * n_au * 4); a.take(&st[k].rv, cpc * n_rv * 4);
+            a.take(&st[k].ra, cpc * n_ra * 4); a.take(&st[k].feats, cpc * n_feats * 4);
+        }
+        if (!pass) {
+            io_need = a.off;
+            if (io_need > c->io_bytes) {
+                if (c->io) { cudaDeviceSynchronize(); cudaFree(c->io); c->io = nullptr; c->io_bytes = 0; }
+                cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->io), io_need);
+                if (e != cudaSuccess) return c->fail(TIM_ERR_NOMEM, "staging cudaMalloc(%zu) failed: %s", io_need, cudaGetErrorString(e));
+                c->io_bytes = io_need;
+            }
+        }
+    }
+    size_t need_t = 0, need_e = 0;
+    TIM_TRY(time_mlp_ws(c, cpc, T_, &need_t));
+    TIM_TRY(encoder_ws(c, cpc, T_, Qv, Qa, &need_e));
+    TIM_TRY(ensure_ws(c, need_t > need_e ? need_t : need_e));
+
+    const int nchunks = (B + cpc - 1) / cpc;
+    std::vector<cudaEvent_t> ev_in(nchunks), ev_comp(nchunks), ev_out(nchunks);
+    for (int i = 0; i < nchunks; ++i) {
+        CU_OK(c, cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+        CU_OK(c, cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
+        CU_OK(c, cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+    }
+    uint64_t up = 0, down = 0;
+    int rc = TIM_OK;
+    auto h2d = [&](float* dst, const float* src, size_t n) -> cudaError_t {
+        if (!n) return cudaSuccess;
+        up += n * 4;
+        return cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyHostToDevice, c->s_h2d);
+    };
+    auto d2h = [&](float* dst, const float* src, size_t n) -> cudaError_t {
+        if (!n) return cudaSuccess;
+        down += n * 4;
+        return cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToHost, c->s_d2h);
+    };
+    for (int i = 0; i < nchunks && rc == TIM_OK; ++i) {
+        const int b0 = i * cpc, nb = (B - b0 < cpc) ? B - b0 : cpc;
+        Set& s = st[i & 1];
+        // inputs of chunk i may overwrite set (i&1) once chunk i-2 has been computed
+        if (i >= 2) CU_OK(c, cudaStreamWaitEvent(c->s_h2d, ev_comp[i - 2], 0));
+        if (c->Fv) CU_OK(c, h2d(s.vis, vis + b0 * n_vis, nb * n_vis));
+        if (c->Fa) CU_OK(c, h2d(s.aud, aud + b0 * n_aud, nb * n_aud));
+        CU_OK(c, h2d(s.times, times + b0 * n_times, nb * n_times));
+        CU_OK(c, cudaEventRecord(ev_in[i], c->s_h2d));
+        // compute: needs its inputs, and its output set free (chunk i-2 copied out)
+        CU_OK(c, cudaStreamWaitEvent(c->s_comp, ev_in[i], 0));
+        if (i >= 2) CU_OK(c, cudaStreamWaitEvent(c->s_comp, ev_out[i - 2], 0));
+        rc = dispatch_dtype(c, [&](auto tag) { return time_mlp_impl<decltype(tag)>(c, s.times, s.te, nb, T_, c->s_comp, c->ws, nullptr); });
+        if (rc != TIM_OK) break;
+        tim_outputs dout;
+        dout.verb = n_verb ? s.verb : nullptr; dout.noun = n_noun ? s.noun : nullptr; dout.action = n_act ? s.act : nullptr;
+        dout.audio = n_au ? s.au : nullptr; dout.reg_visual = n_rv ? s.rv : nullptr; dout.reg_audio = n_ra ? s.ra : nullptr;
+        dout.feats = n_feats ? s.feats : nullptr;
+        rc = dispatch_dtype(c, [&](auto tag) { return encoder_impl<decltype(tag)>(c, s.vis, s.aud, s.te, nb, T_, Qv, Qa, &dout, c->s_comp, c->ws, nullptr); });
+        if (rc != TIM_OK) break;
+        CU_OK(c, cudaEventRecord(ev_comp[i], c->s_comp));
+        CU_OK(c, cudaStreamWaitEvent(c->s_d2h, ev_comp[i], 0));
+        if (n_verb) CU_OK(c, d2h(ho->verb + b0 * n_verb, s.verb, nb * n_verb));
+        if (n_noun) CU_OK(c, d2h(ho->noun + b0 * n_noun, s.noun, nb * n_noun));
+        if (n_act) CU_OK(c, d2h(ho->action + b0 * n_act, s.act, nb * n_act));
+        if (n_au) CU_OK(c, d2h(ho->audio + b0 * n_au, s.au, nb * n_au));
+        if (n_rv) CU_OK(c, d2h(ho->reg_visual + b0 * n_rv, s.rv, nb * n_rv));
+        if (n_ra) CU_OK(c, d2h(ho->reg_audio + b0 * n_ra, s.ra, nb * n_ra));
+        if (n_feats) CU_OK(c, d2h(ho->feats + b0 * n_feats, s.feats, nb * n_feats));
+        CU_OK(c, cudaEventRecord(ev_out[i], c->s_d2h));
+    }
+    cudaError_t e1 = cudaStreamSynchronize(c->s_h2d), e2 = cudaStreamSynchronize(c->s_comp), e3 = cudaStreamSynchronize(c->s_d2h);
+    for (int i = 0; i < nchunks; ++i) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_comp[i]); cudaEventDestroy(ev_out[i]); }
+    if (rc != TIM_OK) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        return c->fail(TIM_ERR_CUDA, "tim_forward_host: stream sync failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+    if (h2d_bytes) *h2d_bytes = up;
+    if (d2h_bytes) *d2h_bytes = down;
+    return TIM_OK;
+}
+
+size_t tim_workspace_bytes(const tim_ctx* c) { return c ? c->ws_bytes + c->io_bytes : 0; }
+uint64_t tim_launch_count(const tim_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------- single-kernel test hooks
+namespace {
+struct TmpCtx {           // minimal context for the test hooks (no weights)
+    tim_ctx c;
+    std::vector<void*> tmp;
+    ~TmpCtx() { for (void* p : tmp) cudaFree(p); }
+    template <typename P> cudaError_t alloc(P** p, size_t bytes) {
+        cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), bytes ? bytes : 16);
+        if (e == cudaSuccess) tmp.push_back(*p);
+        return e;
+    }
+};
+}  // namespace
+
+extern "C" {
+
+int tim_test_linear(int dtype, const float* A, const float* W, const float* bias, const float* resid, float* out, int M, int N,
+                    int K, int act, void* stream) {
+    TmpCtx t;
+    tim_ctx* c = &t.c;
+    auto fin = [&](int r) { g_create_error = c->err; return r; };
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
+        g_create_error = "tim_test_linear: no sm_100 device";
+        return TIM_ERR_NO_DEVICE;
+    }
+    c->num_sms = prop.multiProcessorCount; c->device = dev;
+    c->cfg.compute_dtype = dtype;
+    c->esize = dtype == TIM_FP32 ? 4 : 2;
+    LinearW w;
+    w.N = N; w.K = K; w.bias = const_cast<float*>(bias);
+    Epilogue ep = epi(out, N, true, act, resid, N);
+    float* zero_bias = nullptr;
+    if (!bias) {
+        if (t.alloc(&zero_bias, N * sizeof(float)) != cudaSuccess) return fin(c->fail(TIM_ERR_NOMEM, "alloc"));
+        cudaMemsetAsync(zero_bias, 0, N * sizeof(float), s);
+        w.bias = zero_bias;
+    }
+    int r;
+    if (dtype == TIM_FP32) {
+        w.w = const_cast<float*>(W);
+        r = run_linear<float>(c, A, K, w, plain_rows(M), ep, s);
+    } else {
+        r = get_encode_fn(c);
+        if (r) return fin(r);
+        void *a16 = nullptr, *w16 = nullptr;
+        if (t.alloc(&a16, static_cast<size_t>(M) * K * 2) != cudaSuccess || t.alloc(&w16, static_cast<size_t>(N) * K * 2) != cudaSuccess)
+            return fin(c->fail(TIM_ERR_NOMEM, "alloc"));
+        w.w = w16;
+        if (dtype == TIM_BF16) {
+            launch_cast<__nv_bfloat16>(A, static_cast<__nv_bfloat16*>(a16), M, K, 0, 1.0f, s);
+            launch_cast<__nv_bfloat16>(W, static_cast<__nv_bfloat16*>(w16), N, K, 0, 1.0f, s);
+        } else {
+            launch_cast<__half>(A, static_cast<__half*>(a16), M, K, 0, 1.0f, s);
+            launch_cast<__half>(W, static_cast<__half*>(w16), N, K, 0, 1.0f, s);
+        }
+        r = make_tmap_w(c, w);
+        if (r) return fin(r);
+        r = dtype == TIM_BF16 ? run_linear<__nv_bfloat16>(c, a16, K, w, plain_rows(M), ep, s)
+                              : run_linear<__half>(c, a16, K, w, plain_rows(M), ep, s);
+    }
+    if (r) return fin(r);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return fin(c->fail(TIM_ERR_CUDA, "tim_test_linear: %s", cudaGetErrorString(e)));
+    return TIM_OK;
+}
+
+int tim_test_attention(int dtype, const float* qkv, float* out, int B, int Ft, int Qt, int H, int hd, void* stream) {
+    TmpCtx t;
+    tim_ctx* c = &t.c;
+    auto fin = [&](int r) { g_create_error = c->err; return r; };
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t M = static_cast<size_t>(B) * (Ft + Qt), E = static_cast<size_t>(H) * hd;
+    cudaError_t e = cudaSuccess;
+    const float* scaled = qkv;          // the caller pre-scales q by hd^-0.5 * log2(e), as the packed in_proj weights do
+    if (dtype == TIM_FP32) {
+        e = launch_attention_simt(scaled, out, B, Ft, Qt, H, hd, s);
+    } else {
+        void *q16 = nullptr, *o16 = nullptr;
+        if (t.alloc(&q16, M * 3 * E * 2) != cudaSuccess || t.alloc(&o16, M * E * 2) != cudaSuccess) return fin(c->fail(TIM_ERR_NOMEM, "alloc"));
+        if (dtype == TIM_BF16) {
+            launch_cast<__nv_bfloat16>(scaled, static_cast<__nv_bfloat16*>(q16), M, 3 * E, 0, 1.0f, s);
+            e = launch_attention_mma<__nv_bfloat16>(static_cast<__nv_bfloat16*>(q16), static_cast<__nv_bfloat16*>(o16), B, Ft, Qt, H, hd, s);
+        } else {
+            launch_cast<__half>(scaled, static_cast<__half*>(q16), M, 3 * E, 0, 1.0f, s);
+            e = launch_attention_mma<__half>(static_cast<__half*>(q16), static_cast<__half*>(o16), B, Ft, Qt, H, hd, s);
+        }
+        if (e == cudaSuccess) {
+            // widen back to fp32 with a plain device loop (cast kernels only go fp32 -> T): use cudaMemcpy2D-free host path
+            std::vector<uint16_t> h(M * E);
+            e = cudaStreamSynchronize(s);
+            if (e == cudaSuccess) e = cudaMemcpy(h.data(), o16, M * E * 2, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) {
+                std::vector<float> f(M * E);
+                for (size_t i = 0; i < M * E; ++i) {
+                    if (dtype == TIM_BF16) { uint32_t u = static_cast<uint32_t>(h[i]) << 16; std::memcpy(&f[i], &u, 4); }
+                    else {
+                        __half_raw hr; hr.x = h[i];
+                        f[i] = __half2float(__half(hr));
+                    }
+                }
+                e = cudaMemcpy(out, f.data(), M * E * 4, cudaMemcpyHostToDevice);
+            }
+        }
+    }
+    if (e != cudaSuccess) return fin(c->fail(TIM_ERR_CUDA, "tim_test_attention: %s", cudaGetErrorString(e)));
+    e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return fin(c->fail(TIM_ERR_CUDA, "tim_test_attention: %s", cudaGetErrorString(e)));
+    return TIM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,264 @@
+// HBM-bound row kernels of the TIM forward: first time-MLP layer, LayerNorm, token assembly, casts, last regression
+// layer. One warp per row, 128-bit loads where the row is wide, warp-shuffle reductions; nothing here is GEMM-shaped.
+//
+// Reference ops replaced:
+//   time_mlp layer 0 (Linear(2, d) + ReLU)          recognition/.../models/tim.py:66-68
+//   LayerNorm (norm1 / norm2 / time_mlp.6 / embedder.3)   transformers.py:105,109 ; tim.py:73 ; encodings.py:144,152
+//   token concat / CLS expand / modality add        encodings.py:181-251 (and the uni-modal variants :41-75,102-121)
+//   reg head last layer + Sigmoid                   detection/.../helpers/head.py:101-103
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace tim {
+namespace {
+
+constexpr int ROWS_PER_CTA = 8;      // 8 warps, one row each
+
+template <typename TO>
+__global__ void __launch_bounds__(256) time_l1_kernel(const float* __restrict__ times, const float* __restrict__ W,
+                                                      const float* __restrict__ b, TO* __restrict__ out, int M, int d) {
+    const size_t total = static_cast<size_t>(M) * d;
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const size_t m = i / d;
+        const int c = static_cast<int>(i - m * d);
+        const float2 t = *reinterpret_cast<const float2*>(times + 2 * m);
+        const float2 w = *reinterpret_cast<const float2*>(W + 2 * c);
+        // same association as x @ W.T + b: (t0*w0 + t1*w1) + b
+        const float v = fmaf(t.y, w.y, t.x * w.x) + b[c];
+        out[i] = from_float<TO>(fmaxf(v, 0.0f));
+    }
+}
+
+// two-pass (mean, then centred variance) LayerNorm statistics of one row held by a warp
+__device__ __forceinline__ void row_stats(const float* __restrict__ row, int n, int lane, float& mean, float& rstd) {
+    float s = 0.0f;
+    for (int c = lane * 4; c < n; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(row + c);
+        s += (v.x + v.y) + (v.z + v.w);
+    }
+    mean = warp_sum(s) / static_cast<float>(n);
+    float q = 0.0f;
+    for (int c = lane * 4; c < n; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(row + c);
+        const float a = v.x - mean, b2 = v.y - mean, c2 = v.z - mean, d2 = v.w - mean;
+        q += (a * a + b2 * b2) + (c2 * c2 + d2 * d2);
+    }
+    rstd = rsqrtf(warp_sum(q) / static_cast<float>(n) + 1e-5f);
+}
+
+template <typename T> __device__ __forceinline__ void store4(T* p, float a, float b, float c, float d);
+template <> __device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+}
+template <> __device__ __forceinline__ void store4<__half>(__half* p, float a, float b, float c, float d) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack2<__half>(a, b), pack2<__half>(c, d));
+}
+template <> __device__ __forceinline__ void store4<__nv_bfloat16>(__nv_bfloat16* p, float a, float b, float c, float d) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack2<__nv_bfloat16>(a, b), pack2<__nv_bfloat16>(c, d));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(ROWS_PER_CTA * 32) layernorm_kernel(const float* __restrict__ in, int ldi,
+                                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                      float* __restrict__ out32, int ld32, T* __restrict__ out16, int ld16,
+                                                                      int M, int n) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const float* x = in + static_cast<size_t>(row) * ldi;
+    float mean, rstd;
+    row_stats(x, n, lane, mean, rstd);
+    for (int c = lane * 4; c < n; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(x + c);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+        const float y0 = (v.x - mean) * rstd * g.x + b.x, y1 = (v.y - mean) * rstd * g.y + b.y;
+        const float y2 = (v.z - mean) * rstd * g.z + b.z, y3 = (v.w - mean) * rstd * g.w + b.w;
+        if (out32) store4<float>(out32 + static_cast<size_t>(row) * ld32 + c, y0, y1, y2, y3);
+        if (out16) store4<T>(out16 + static_cast<size_t>(row) * ld16 + c, y0, y1, y2, y3);
+    }
+}
+
+// One warp per token row of the two-stream buffer.
+//   feature row (b, f):  [ LN(emb[b, f]) | te[b, f_t] ] + mod
+//   query row  (b, q):   [ cls          | te[b, t_q] ] + mod
+template <typename T>
+__global__ void __launch_bounds__(ROWS_PER_CTA * 32) assemble_kernel(const AssembleParams p) {
+    const int lane = threadIdx.x & 31;
+    const size_t row = static_cast<size_t>(blockIdx.x) * ROWS_PER_CTA + (threadIdx.x >> 5);
+    const int Ft = p.Fv + p.Fa;
+    const size_t n_feat = static_cast<size_t>(p.B) * Ft;
+    const size_t n_rows = n_feat + static_cast<size_t>(p.B) * p.Qt;
+    if (row >= n_rows) return;
+    const int d = p.d, E = 2 * p.d;
+    const float* left = nullptr;      // d values for the left half (pre-LN embedder row, or the CLS parameter)
+    const float* g = nullptr; const float* bt = nullptr;
+    const float* mod = nullptr;
+    int b, te_row;
+    if (row < n_feat) {
+        b = static_cast<int>(row / Ft);
+        const int f = static_cast<int>(row - static_cast<size_t>(b) * Ft);
+        te_row = f;                   // time rows are ordered [vis F | aud F | queries], like the token rows
+        if (f < p.Fv) {
+            left = p.emb_v + (static_cast<size_t>(b) * p.Fv + f) * d; g = p.ln_v_g; bt = p.ln_v_b; mod = p.mod_v;
+        } else {
+            left = p.emb_a + (static_cast<size_t>(b) * p.Fa + (f - p.Fv)) * d; g = p.ln_a_g; bt = p.ln_a_b; mod = p.mod_a;
+        }
+    } else {
+        const size_t qr = row - n_feat;
+        b = static_cast<int>(qr / p.Qt);
+        int q = static_cast<int>(qr - static_cast<size_t>(b) * p.Qt);
+        int gi = 0;
+        while (gi < p.n_groups - 1 && q >= p.groups[gi].count) { q -= p.groups[gi].count; ++gi; }
+        left = p.groups[gi].cls; mod = p.groups[gi].mod;
+        te_row = p.groups[gi].te_off + q;
+    }
+    float mean = 0.0f, rstd = 1.0f;
+    if (g) row_stats(left, d, lane, mean, rstd);
+    const float* te = p.te + (static_cast<size_t>(b) * p.T + te_row) * d;
+    float* o32 = p.x32 + row * E;
+    T* o16 = p.x16 ? reinterpret_cast<T*>(p.x16) + row * E : nullptr;
+    for (int c = lane * 4; c < E; c += 128) {
+        float4 v;
+        if (c < d) {
+            v = *reinterpret_cast<const float4*>(left + c);
+            if (g) {
+                const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c));
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(bt + c));
+                v.x = (v.x - mean) * rstd * gg.x + bb.x; v.y = (v.y - mean) * rstd * gg.y + bb.y;
+                v.z = (v.z - mean) * rstd * gg.z + bb.z; v.w = (v.w - mean) * rstd * gg.w + bb.w;
+            }
+        } else {
+            v = *reinterpret_cast<const float4*>(te + (c - d));
+        }
+        if (mod) {
+            const float4 m = __ldg(reinterpret_cast<const float4*>(mod + c));
+            v.x += m.x; v.y += m.y; v.z += m.z; v.w += m.w;
+        }
+        store4<float>(o32 + c, v.x, v.y, v.z, v.w);
+        if (o16) store4<T>(o16 + c, v.x, v.y, v.z, v.w);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ in, T* __restrict__ out, size_t n4, size_t scale_n4, float scale) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        float4 v = *reinterpret_cast<const float4*>(in + 4 * i);
+        if (i < scale_n4) { v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale; }
+        store4<T>(out + 4 * i, v.x, v.y, v.z, v.w);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) cast_tail_kernel(const float* __restrict__ in, T* __restrict__ out, size_t start, size_t n,
+                                                        size_t scale_n, float scale) {
+    const size_t i = start + blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+    if (i < n) out[i] = from_float<T>(i < scale_n ? in[i] * scale : in[i]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(ROWS_PER_CTA * 32) reg_final_kernel(const T* __restrict__ h, int ldh, const float* __restrict__ W,
+                                                                      const float* __restrict__ b, float* __restrict__ out, int rows, int K) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const T* x = h + static_cast<size_t>(row) * ldh;
+    float a0 = 0.0f, a1 = 0.0f;
+    for (int c = lane; c < K; c += 32) {
+        const float v = to_float<T>(x[c]);
+        a0 = fmaf(v, W[c], a0);
+        a1 = fmaf(v, W[K + c], a1);
+    }
+    a0 = warp_sum(a0); a1 = warp_sum(a1);
+    if (lane == 0) {
+        out[2 * static_cast<size_t>(row)] = 1.0f / (1.0f + expf(-(a0 + b[0])));
+        out[2 * static_cast<size_t>(row) + 1] = 1.0f / (1.0f + expf(-(a1 + b[1])));
+    }
+}
+
+inline int grid_for(size_t n, int block, int cap = 148 * 16) {
+    size_t g = (n + block - 1) / block;
+    if (g > static_cast<size_t>(cap)) g = cap;
+    return g ? static_cast<int>(g) : 1;
+}
+
+}  // namespace
+
+template <typename TO>
+cudaError_t launch_time_l1(const float* times, const float* W, const float* b, TO* out, int M, int d, cudaStream_t s) {
+    if (M <= 0) return cudaSuccess;
+    time_l1_kernel<TO><<<grid_for(static_cast<size_t>(M) * d, 256), 256, 0, s>>>(times, W, b, out, M, d);
+    return cudaGetLastError();
+}
+template cudaError_t launch_time_l1<float>(const float*, const float*, const float*, float*, int, int, cudaStream_t);
+template cudaError_t launch_time_l1<__half>(const float*, const float*, const float*, __half*, int, int, cudaStream_t);
+template cudaError_t launch_time_l1<__nv_bfloat16>(const float*, const float*, const float*, __nv_bfloat16*, int, int, cudaStream_t);
+
+template <typename T>
+cudaError_t launch_layernorm(const float* in, int ldi, const float* gamma, const float* beta, float* out32, int ld32, T* out16,
+                             int ld16, int M, int n, cudaStream_t s) {
+    if (M <= 0) return cudaSuccess;
+    if ((n & 3) || (ldi & 3) || (out32 && (ld32 & 3)) || (out16 && (ld16 & 3))) return cudaErrorInvalidValue;
+    layernorm_kernel<T><<<(M + ROWS_PER_CTA - 1) / ROWS_PER_CTA, ROWS_PER_CTA * 32, 0, s>>>(in, ldi, gamma, beta, out32, ld32, out16, ld16, M, n);
+    return cudaGetLastError();
+}
+template cudaError_t launch_layernorm<float>(const float*, int, const float*, const float*, float*, int, float*, int, int, int, cudaStream_t);
+template cudaError_t launch_layernorm<__half>(const float*, int, const float*, const float*, float*, int, __half*, int, int, int, cudaStream_t);
+template cudaError_t launch_layernorm<__nv_bfloat16>(const float*, int, const float*, const float*, float*, int, __nv_bfloat16*, int, int, int, cudaStream_t);
+
+template <typename T>
+cudaError_t launch_assemble(const AssembleParams& p, cudaStream_t s) {
+    if (p.d & 3) return cudaErrorInvalidValue;
+    const size_t rows = static_cast<size_t>(p.B) * (p.Fv + p.Fa + p.Qt);
+    if (!rows) return cudaSuccess;
+    assemble_kernel<T><<<static_cast<unsigned>((rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA), ROWS_PER_CTA * 32, 0, s>>>(p);
+    return cudaGetLastError();
+}
+template cudaError_t launch_assemble<float>(const AssembleParams&, cudaStream_t);
+template cudaError_t launch_assemble<__half>(const AssembleParams&, cudaStream_t);
+template cudaError_t launch_assemble<__nv_bfloat16>(const AssembleParams&, cudaStream_t);
+
+template <typename T>
+cudaError_t launch_cast(const float* in, T* out, size_t rows, size_t cols, size_t scale_rows, float scale, cudaStream_t s) {
+    const size_t n = rows * cols, scale_n = scale_rows * cols;
+    if (!n) return cudaSuccess;
+    const size_t n4 = n / 4;
+    // the scaled prefix must end on a float4 boundary for the vector body (true for every packed weight: cols % 4 == 0)
+    if (scale_n % 4) return cudaErrorInvalidValue;
+    if (n4) {
+        cast_kernel<T><<<grid_for(n4, 256), 256, 0, s>>>(in, out, n4, scale_n / 4, scale);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    if (n % 4) cast_tail_kernel<T><<<1, 256, 0, s>>>(in, out, n4 * 4, n, scale_n, scale);
+    return cudaGetLastError();
+}
+template cudaError_t launch_cast<__half>(const float*, __half*, size_t, size_t, size_t, float, cudaStream_t);
+template cudaError_t launch_cast<__nv_bfloat16>(const float*, __nv_bfloat16*, size_t, size_t, size_t, float, cudaStream_t);
+
+cudaError_t launch_scale_copy(const float* in, float* out, size_t rows, size_t cols, size_t scale_rows, float scale, cudaStream_t s) {
+    const size_t n = rows * cols, scale_n = scale_rows * cols;
+    if (!n) return cudaSuccess;
+    if (scale_n % 4) return cudaErrorInvalidValue;
+    const size_t n4 = n / 4;
+    if (n4) {
+        cast_kernel<float><<<grid_for(n4, 256), 256, 0, s>>>(in, out, n4, scale_n / 4, scale);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    if (n % 4) cast_tail_kernel<float><<<1, 256, 0, s>>>(in, out, n4 * 4, n, scale_n, scale);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_reg_final(const T* h, int ldh, const float* W, const float* b, float* out, int rows, int K, cudaStream_t s) {
+    if (rows <= 0) return cudaSuccess;
+    reg_final_kernel<T><<<(rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA, ROWS_PER_CTA * 32, 0, s>>>(h, ldh, W, b, out, rows, K);
+    return cudaGetLastError();
+}
+template cudaError_t launch_reg_final<float>(const float*, int, const float*, const float*, float*, int, int, cudaStream_t);
+template cudaError_t launch_reg_final<__half>(const __half*, int, const float*, const float*, float*, int, int, cudaStream_t);
+template cudaError_t launch_reg_final<__nv_bfloat16>(const __nv_bfloat16*, int, const float*, const float*, float*, int, int, cudaStream_t);
+
+}  // namespace tim

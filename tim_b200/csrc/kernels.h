@@ -1,0 +1,111 @@
+// Host-side launch interface of the TIM kernels (implemented in the .cu files of this directory).
+// Plain pointers + sizes only; no torch types.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tim {
+
+enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+
+// How the rows of a linear layer's A operand / output are laid out.
+// Logical rows are (group g, row r), g < G, r < R. One tile covers box_g groups x box_r rows (<= 128 rows).
+//   A row in memory   : g * a_group_rows + a_row_off + r      (SIMT path; the UMMA path bakes this into a 3-D tensor map
+//                                                               (K, a_group_rows, G) and uses coordinates (k, a_row_off + r, g))
+//   output/resid row  : g * out_group_rows + out_row_off + r
+// A plain [M, K] matrix is G = 1, R = M, box_r = 128, box_g = 1.
+struct RowMap {
+    int G, R;
+    int box_r, box_g;
+    int a_group_rows, a_row_off;
+    int out_group_rows, out_row_off;
+};
+inline RowMap plain_rows(int M) { return RowMap{1, M, 128, 1, M, 0, M, 0}; }
+
+// out = act(acc + bias) (+ resid), stored as fp32 or as the 16-bit operand type.
+struct Epilogue {
+    const float* bias;    // [N] or nullptr
+    const float* resid;   // fp32 [rows, ldr] or nullptr (added after the activation)
+    int ldr;
+    void* out;            // [rows, ldo]
+    int ldo;
+    int out_fp32;         // 1: float*, 0: T*
+    int act;              // Act
+};
+
+// ---- tcgen05 GEMM: C[rows, N] = A[rows, K] * W[N, K]^T, 16-bit operands, fp32 accumulate in TMEM ----
+struct UmmaParams {
+    CUtensorMap tmA;      // 3-D (K, a_group_rows, G), box (64, box_r, box_g), SWIZZLE_128B
+    CUtensorMap tmB;      // 2-D (K, N), box (64, block_n), SWIZZLE_128B
+    int N, K;
+    RowMap rm;
+    Epilogue ep;
+    int tiles_r, tiles_m, tiles_n;
+};
+int umma_block_n(int N);   // tile width chosen for an N-column weight (64 / 128 / 256)
+template <typename T>
+cudaError_t launch_linear_umma(UmmaParams p, int block_n, int num_sms, cudaStream_t s);
+
+// ---- fp32 SIMT GEMM with the same row mapping / epilogue (fp32 parity mode) ----
+cudaError_t launch_linear_simt(const float* A, int lda, const float* W, int N, int K, RowMap rm, Epilogue ep,
+                               cudaStream_t s);
+
+// ---- attention over the two-stream token layout ----
+// qkv: [B*Ft + B*Qt, 3E]; feature rows of clip b at b*Ft.., query rows at B*Ft + b*Qt..
+// q columns are pre-scaled by head_dim^-0.5 * log2(e) (folded into the packed in_proj weights).
+// Every row attends to the Ft feature keys of its clip; query rows additionally to their own key.
+template <typename T>
+cudaError_t launch_attention_mma(const T* qkv, T* out, int B, int Ft, int Qt, int H, int hd, cudaStream_t s);
+cudaError_t launch_attention_simt(const float* qkv, float* out, int B, int Ft, int Qt, int H, int hd, cudaStream_t s);
+size_t attention_simt_smem(int Ft, int hd);
+
+// ---- elementwise / row kernels ----
+// relu(times[M,2] * W[d,2]^T + b) -> out[M, d]
+template <typename TO>
+cudaError_t launch_time_l1(const float* times, const float* W, const float* b, TO* out, int M, int d, cudaStream_t s);
+
+// LayerNorm over rows of `in` [M, n] (row stride ldi); writes fp32 (out32, stride ld32) and/or T (out16, stride ld16)
+template <typename T>
+cudaError_t launch_layernorm(const float* in, int ldi, const float* gamma, const float* beta, float* out32, int ld32,
+                             T* out16, int ld16, int M, int n, cudaStream_t s);
+
+// Token assembly (encodings.py forward): see elementwise.cu for the row plan
+struct TokenGroup {          // a run of `count` query tokens per clip
+    const float* cls;        // [d] CLS parameter (left half)
+    const float* mod;        // [E] modality encoding or nullptr
+    int te_off;              // first time-encoding row (inside a clip's T rows) feeding the right half
+    int count;
+};
+struct AssembleParams {
+    int B, d, T;             // clips, d_model, time rows per clip
+    int Fv, Fa;              // feature tokens per modality (0 if absent)
+    const float* emb_v;      // [B*Fv, d] pre-LayerNorm embedder output (after GELU)
+    const float* emb_a;      // [B*Fa, d]
+    const float* ln_v_g; const float* ln_v_b;
+    const float* ln_a_g; const float* ln_a_b;
+    const float* mod_v; const float* mod_a;   // [E] or nullptr
+    const float* te;         // [B, T, d] time encodings
+    int n_groups;
+    TokenGroup groups[4];
+    int Qt;                  // query tokens per clip = sum(groups.count)
+    float* x32;              // [B*Ft + B*Qt, E] fp32 residual stream (two-stream layout)
+    void* x16;               // same rows, operand dtype (nullptr in fp32 mode)
+};
+template <typename T>
+cudaError_t launch_assemble(const AssembleParams& p, cudaStream_t s);
+
+// fp32 -> T cast, optional scaling of the first `scale_rows` rows (n = rows * cols, contiguous)
+template <typename T>
+cudaError_t launch_cast(const float* in, T* out, size_t rows, size_t cols, size_t scale_rows, float scale, cudaStream_t s);
+cudaError_t launch_scale_copy(const float* in, float* out, size_t rows, size_t cols, size_t scale_rows, float scale,
+                              cudaStream_t s);
+
+// last regression layer: sigmoid(h[rows, K] * W[2, K]^T + b) -> out[rows, 2] fp32
+template <typename T>
+cudaError_t launch_reg_final(const T* h, int ldh, const float* W, const float* b, float* out, int rows, int K,
+                             cudaStream_t s);
+
+}  // namespace tim

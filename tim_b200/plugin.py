@@ -1,0 +1,287 @@
+"""Host side of the drop-in: the reference's model interface on top of libtim_b200.
+
+The reference exposes no plugin API; its seam is TIM.forward (recognition/.../models/tim.py:174-191,
+detection/.../models/tim.py:415-430) and the state_dict layout. This module gives
+  * TIMEngine        - one library context: load_state_dict / time_mlp / encoder / forward_host
+  * patch_model()    - rebinds forward() of an existing reference TIM instance (same signature, same return
+                       structure, parameters stay nn.Parameters under the same names, so the reference's
+                       train/eval scripts, flags and checkpoints are untouched)
+PyTorch is used for device memory and streams only. There is no fallback: every call goes through the
+C ABI and raises if the library or a B200 is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import types
+from typing import Dict, Mapping, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .config import (DETECTION, DTYPE_CODES, RECOGNITION, TIMConfig, hot_path_keys, state_dict_spec)
+
+
+def _c_config(cfg: TIMConfig, compute_dtype: str) -> _lib.tim_config:
+    hc = cfg.head_classes()
+    return _lib.tim_config(
+        variant=_lib.VARIANT_CODES[cfg.variant], d_model=cfg.d_model, nhead=cfg.nhead, num_layers=cfg.num_layers,
+        ff_dim=cfg.FF, vis_dim=cfg.visual_input_dim, aud_dim=cfg.audio_input_dim, num_feats=cfg.num_feats,
+        input_modality=_lib.MODALITY_CODES[cfg.input_modality], data_modality=_lib.MODALITY_CODES[cfg.data_modality],
+        include_verb_noun=int(cfg.verb_noun_tokens), n_verb=hc["verb"], n_noun=hc["noun"], n_action=hc["action"],
+        n_audio=hc["audio"], compute_dtype=DTYPE_CODES[compute_dtype])
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class TIMEngine:
+    """One tim_ctx on one CUDA device."""
+
+    def __init__(self, cfg: TIMConfig, device: int = 0, compute_dtype: str = "fp16"):
+        if compute_dtype not in DTYPE_CODES:
+            raise ValueError(f"compute_dtype must be one of {sorted(DTYPE_CODES)}")
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.compute_dtype = compute_dtype
+        self.device = torch.device("cuda", device)
+        self._ctx = C.c_void_p()
+        self._cc = _c_config(cfg, compute_dtype)
+        _lib.check(self.lib.tim_create(C.byref(self._ctx), C.byref(self._cc), device))
+        self._keys = hot_path_keys(cfg)
+        self._spec = state_dict_spec(cfg, include_drloc=False)
+
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self.lib.tim_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def set_weight(self, key: str, value) -> None:
+        if isinstance(value, np.ndarray):
+            value = torch.from_numpy(value)
+        t = value.detach().to(device=self.device, dtype=torch.float32).contiguous()
+        shape = (C.c_int64 * t.dim())(*t.shape)
+        _lib.check(self.lib.tim_set_weight(self._ctx, key.encode(), _ptr(t), shape, t.dim(), self._stream()), self._ctx)
+        # the pack kernels were enqueued on the current stream; t may be a temporary
+        t.record_stream(torch.cuda.current_stream(self.device))
+
+    def load_state_dict(self, sd: Mapping[str, object], strict: bool = True) -> None:
+        """Accepts the reference's state_dict (extra keys such as drloc_mlp.* are ignored)."""
+        with torch.cuda.device(self.device):
+            for k in self._keys:
+                if k in sd:
+                    self.set_weight(k, sd[k])
+                elif strict:
+                    raise KeyError(f"state_dict is missing '{k}'")
+
+    def missing_weights(self):
+        buf = C.create_string_buffer(1 << 16)
+        n = self.lib.tim_weights_missing(self._ctx, buf, len(buf))
+        return [s for s in buf.value.decode().split("\n") if s] if n > 0 else []
+
+    # ------------------------------------------------------------------ forward (device tensors)
+    def _check_in(self, t: torch.Tensor, name: str, shape):
+        if t.device != self.device:
+            raise ValueError(f"{name} must live on {self.device}, got {t.device}")
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
+        return t.to(torch.float32).contiguous()
+
+    def time_mlp(self, times: torch.Tensor) -> torch.Tensor:
+        """tim.py:181-182 — times [B, T, 2] -> [B, T, d_model]."""
+        B, T = int(times.shape[0]), int(times.shape[1])
+        times = self._check_in(times, "times", (B, T, 2))
+        with torch.cuda.device(self.device):
+            out = torch.empty((B, T, self.cfg.d_model), device=self.device, dtype=torch.float32)
+            _lib.check(self.lib.tim_time_mlp_fwd(self._ctx, _ptr(times), _ptr(out), B, T, self._stream()), self._ctx)
+        return out
+
+    def _alloc_outputs(self, B: int, Qv: int, Qa: int, *, pinned: bool, want_feats: bool = True):
+        cfg = self.cfg
+        hc = cfg.head_classes()
+        qv = Qv if "visual" in cfg.data_modality else 0
+        qa = Qa if "audio" in cfg.data_modality else 0
+        kw = dict(dtype=torch.float32, device="cpu", pin_memory=True) if pinned else dict(dtype=torch.float32, device=self.device)
+        out: Dict[str, Optional[torch.Tensor]] = {k: None for k in ("verb", "noun", "action", "audio", "reg_v", "reg_a", "feats")}
+        if "visual" in cfg.data_modality:
+            if hc["verb"]:
+                out["verb"] = torch.empty((B * qv, hc["verb"]), **kw)
+                out["noun"] = torch.empty((B * qv, hc["noun"]), **kw)
+            out["action"] = torch.empty((B * qv, hc["action"]), **kw)
+            if cfg.has_reg_head:
+                out["reg_v"] = torch.empty((B * qv, 2), **kw)
+        if "audio" in cfg.data_modality:
+            out["audio"] = torch.empty((B * qa, hc["audio"]), **kw)
+            if cfg.has_reg_head:
+                out["reg_a"] = torch.empty((B * qa, 2), **kw)
+        if want_feats:
+            out["feats"] = torch.empty((B, cfg.F_tot, cfg.E), **kw)
+        co = _lib.tim_outputs(verb=_ptr(out["verb"]), noun=_ptr(out["noun"]), action=_ptr(out["action"]),
+                              audio=_ptr(out["audio"]), reg_visual=_ptr(out["reg_v"]), reg_audio=_ptr(out["reg_a"]),
+                              feats=_ptr(out["feats"]))
+        return out, co
+
+    def encoder(self, vis: Optional[torch.Tensor], aud: Optional[torch.Tensor], time_enc: torch.Tensor,
+                Qv: int, Qa: int, want_feats: bool = True) -> Dict[str, Optional[torch.Tensor]]:
+        """tim.py:147-172 — returns dict(verb, noun, action, audio, reg_v, reg_a, feats); None where absent."""
+        cfg = self.cfg
+        B, T = int(time_enc.shape[0]), int(time_enc.shape[1])
+        Qv, Qa = int(Qv or 0), int(Qa or 0)
+        time_enc = self._check_in(time_enc, "time_encodings", (B, T, cfg.d_model))
+        if cfg.has_visual_input:
+            vis = self._check_in(vis, "visual input", (B, cfg.num_feats, cfg.visual_input_dim))
+        if cfg.has_audio_input:
+            aud = self._check_in(aud, "audio input", (B, cfg.num_feats, cfg.audio_input_dim))
+        with torch.cuda.device(self.device):
+            out, co = self._alloc_outputs(B, Qv, Qa, pinned=False, want_feats=want_feats)
+            _lib.check(self.lib.tim_encoder_fwd(self._ctx, _ptr(vis if cfg.has_visual_input else None),
+                                                _ptr(aud if cfg.has_audio_input else None), _ptr(time_enc),
+                                                B, T, Qv, Qa, C.byref(co), self._stream()), self._ctx)
+        return out
+
+    # ------------------------------------------------------------------ forward (host tensors, end to end)
+    def forward_host(self, vis, aud, times: torch.Tensor, Qv: int, Qa: int, clips_per_chunk: int = 0,
+                     want_feats: bool = True, out=None):
+        """time_mlp + encoder on HOST tensors (pinned for full copy bandwidth); H2D/D2H copies are inside the call.
+        Returns (outputs dict of pinned host tensors, h2d_bytes, d2h_bytes)."""
+        cfg = self.cfg
+        B, T = int(times.shape[0]), int(times.shape[1])
+        for name, t in (("vis", vis), ("aud", aud), ("times", times)):
+            if t is not None and (t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous()):
+                raise ValueError(f"{name} must be a contiguous fp32 CPU tensor")
+        if out is None:
+            out = self._alloc_outputs(B, Qv, Qa, pinned=True, want_feats=want_feats)
+        outs, co = out
+        up, down = C.c_uint64(0), C.c_uint64(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tim_forward_host(self._ctx, _ptr(vis if cfg.has_visual_input else None),
+                                                 _ptr(aud if cfg.has_audio_input else None), _ptr(times), B, T,
+                                                 int(Qv or 0), int(Qa or 0), C.byref(co), int(clips_per_chunk),
+                                                 C.byref(up), C.byref(down)), self._ctx)
+        return outs, int(up.value), int(down.value)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.tim_launch_count(self._ctx))
+
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self.lib.tim_workspace_bytes(self._ctx))
+
+
+# =======================================================================================================
+# drop-in behind an existing reference TIM instance
+# =======================================================================================================
+def config_from_model(model: torch.nn.Module) -> TIMConfig:
+    """Recover the constructor arguments from a reference TIM instance (recognition or detection)."""
+    variant = DETECTION if hasattr(model, "backbone") else RECOGNITION
+    num_feats = model.feature_encoding.num_feats          # per modality (tim.py:87 doubles model.num_feats only)
+    return TIMConfig(num_class=model.num_class, visual_input_dim=model.visual_input_dim,
+                     audio_input_dim=model.audio_input_dim, d_model=model.d_model,
+                     feedforward_scale=model.dim_feedforward // model.d_model, nhead=model.nhead,
+                     num_layers=model.num_layers, input_modality=model.input_modality,
+                     data_modality=model.data_modality, num_feats=num_feats,
+                     include_verb_noun=bool(model.include_verb_noun), variant=variant)
+
+
+class _Binding:
+    """Keeps the engine's packed weights in sync with the module's parameters (re-packs a parameter when its
+    torch version counter moved, e.g. after optimizer.step() or load_state_dict)."""
+
+    def __init__(self, model, engine: TIMEngine):
+        self.engine = engine
+        self.versions: Dict[str, tuple] = {}
+        self.model = model
+
+    def sync(self):
+        sd = {k: v for k, v in self.model.named_parameters()}
+        for k in self.engine._keys:
+            p = sd[k]
+            tag = (p._version, p.data_ptr())
+            if self.versions.get(k) != tag:
+                self.engine.set_weight(k, p)
+                self.versions[k] = tag
+
+
+def _forward_recognition(self, inputs, forward_type, time_encodings=None, num_v_queries=None, num_a_queries=None):
+    """Same signature / returns as recognition/.../models/tim.py:174-191."""
+    b: _Binding = self._tim_b200
+    if forward_type == "drloc_mlp":                        # loss-side helper, stays in PyTorch
+        return self.drloc_mlp(inputs).squeeze(2)
+    if torch.is_grad_enabled() and self.training:
+        raise NotImplementedError("tim_b200: the training (backward) leg is not built yet; call under "
+                                  "model.eval() / torch.no_grad()")
+    if getattr(self, "pool_features", False):
+        raise NotImplementedError("tim_b200: AVGA feature pooling (AVE-only) is outside the hot path")
+    b.sync()
+    if forward_type == "time_mlp":
+        return b.engine.time_mlp(inputs)
+    if forward_type == "encoder":
+        o = b.engine.encoder(inputs[0], inputs[1], time_encodings, num_v_queries, num_a_queries)
+        return (o["verb"], o["noun"], o["action"], o["audio"]), o["feats"]
+    raise ValueError(f"unknown forward_type {forward_type!r}")
+
+
+def _forward_detection(self, inputs, forward_type, feature_times=None, target=None, label_queries=False):
+    """Same signature / returns as detection/.../models/tim.py:415-430 (inference branch :339-400)."""
+    b: _Binding = self._tim_b200
+    if forward_type == "drloc_mlp":
+        return self.drloc_mlp(inputs).squeeze(2)
+    if forward_type != "encoder":
+        raise ValueError(f"unknown forward_type {forward_type!r}")
+    if self.training:
+        raise NotImplementedError("tim_b200: the detection training leg (forward_train + backward) is not built yet")
+    b.sync()
+    cfg = b.engine.cfg
+    dev = feature_times.device
+    v_offsets = a_offsets = torch.empty(0, 2)
+    v_labels = a_labels = torch.empty(0, 4)
+    nv = na = 0
+    v_queries = a_queries = v_ious = a_ious = None
+    all_times = feature_times
+    B = all_times.shape[0]
+    if "visual" in cfg.data_modality:
+        v_queries = self.inference_queries.repeat(B, 1, 1).to(device=dev)
+        nv = v_queries.shape[1]
+        if label_queries:                                  # target prep stays in the reference's own PyTorch code
+            v_offsets, v_labels, v_ious = self.label_queries(v_queries, target, "visual", self.iou_threshold)
+        all_times = torch.cat([all_times, v_queries], dim=1)
+        v_queries = torch.flatten(v_queries, 0, 1)
+    if "audio" in cfg.data_modality:
+        a_queries = self.inference_queries.repeat(B, 1, 1).to(device=dev)
+        na = a_queries.shape[1]
+        if label_queries:
+            a_offsets, a_labels, a_ious = self.label_queries(a_queries, target, "audio", self.iou_threshold)
+        all_times = torch.cat([all_times, a_queries], dim=1)
+        a_queries = torch.flatten(a_queries, 0, 1)
+    te = b.engine.time_mlp(all_times)
+    o = b.engine.encoder(inputs[0], inputs[1], te, nv, na)
+    cls = (o["verb"], o["noun"], o["action"], o["audio"])
+    reg = (o["reg_v"], o["reg_a"])
+    return (cls, reg, o["feats"]), (v_offsets, a_offsets), (v_labels, a_labels), (v_queries, a_queries), (v_ious, a_ious)
+
+
+def patch_model(model: torch.nn.Module, compute_dtype: str = "fp16", device: Optional[int] = None) -> torch.nn.Module:
+    """Route model.forward through libtim_b200. `model` is a reference TIM (or DDP(module=TIM)) already on a GPU."""
+    inner = model.module if hasattr(model, "module") and not hasattr(model, "time_mlp") else model
+    p = next(inner.parameters())
+    if p.device.type != "cuda":
+        raise RuntimeError("tim_b200.patch_model: the model must be on a CUDA device (no CPU fallback)")
+    dev = p.device.index if device is None else device
+    cfg = config_from_model(inner)
+    engine = TIMEngine(cfg, dev, compute_dtype)
+    inner._tim_b200 = _Binding(inner, engine)
+    fwd = _forward_recognition if cfg.variant == RECOGNITION else _forward_detection
+    inner.forward = types.MethodType(fwd, inner)
+    return model
