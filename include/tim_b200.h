@@ -106,6 +106,13 @@ size_t tim_workspace_bytes(const tim_ctx* ctx);         /* bytes currently held 
 uint64_t tim_launch_count(const tim_ctx* ctx);          /* kernels launched by this context so far */
 int tim_seq_len(const tim_config* cfg, int Qv, int Qa); /* S = F_tot + query tokens (pure host arithmetic) */
 
+/* Live per-kernel-class timing (bench.py's roofline object): between begin and end every launch is bracketed by a
+ * CUDA-event pair on its own stream. Classes: 0 GEMM (tcgen05 / fp32 SIMT), 1 attention, 2 LayerNorm, 3 token
+ * assembly, 4 other row kernels. end() synchronises the device and fills ms / algorithmic FLOPs / launch counts. */
+#define TIM_PROFILE_CLASSES 5
+int tim_profile_begin(tim_ctx* ctx);
+int tim_profile_end(tim_ctx* ctx, double* ms, double* flops, uint64_t* count, int n_classes);
+
 /* Single-kernel test hooks (tests/ only): C[M,N] = act(A[M,K] W[N,K]^T + bias) (+resid), fp32 in / fp32 out,
  * computed through the selected compute path (the 16-bit paths cast A and W on device first). */
 int tim_test_linear(int compute_dtype, const float* A, const float* W, const float* bias, const float* resid, float* out,

@@ -1,0 +1,92 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every declared symbol, fails loudly without a
+device, and the host logic (config mirror, sharding over ranks with gloo) behaves."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from tim_b200 import build, _lib
+    build.build()                       # nvcc cross-compiles sm_100a without a GPU
+    return _lib.load()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from tim_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "tim_b200.h")).read()
+    declared = set(re.findall(r"^\s*(?:int|void|size_t|uint64_t|const char\*)\s+(tim_\w+)\s*\(", header, re.M))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.tim_abi_version() == _lib.ABI_VERSION
+
+
+def test_config_struct_matches_header():
+    from tim_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "tim_b200.h")).read()
+    body = re.search(r"typedef struct \{(.*?)\} tim_config;", header, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = [n.strip() for decl in re.findall(r"int32_t\s+([^;]+);", body) for n in decl.split(",")]
+    assert names == [f[0] for f in _lib.tim_config._fields_]
+    body = re.search(r"typedef struct \{(.*?)\} tim_outputs;", header, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    assert re.findall(r"float\*\s+(\w+);", body) == [f[0] for f in _lib.tim_outputs._fields_]
+
+
+def test_seq_len_host_arithmetic(lib):
+    from tim_b200.config import named_config
+    from tim_b200.plugin import _c_config
+    for name, S in (("cfg1", 70), ("cfg2", 200), ("cfg3", 528), ("cfg4", 2148)):
+        cfg, Qv, Qa = named_config(name)
+        cc = _c_config(cfg, "fp16")
+        assert lib.tim_seq_len(C.byref(cc), Qv, Qa) == S == cfg.seq_len(Qv, Qa)
+
+
+def test_no_device_is_a_loud_error(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from tim_b200._lib import TimError
+    from tim_b200.config import named_config
+    from tim_b200.plugin import TIMEngine
+    with pytest.raises(TimError, match="no CPU fallback"):
+        TIMEngine(named_config("cfg1")[0], 0, "fp16")
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure: nothing under tim_b200/ may import or execute it."""
+    pat = re.compile(r"^\s*(from|import)\s+oracle|oracle[./]tim_oracle|import_module\(.*oracle", re.M)
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "tim_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                assert not pat.search(open(os.path.join(dirpath, f)).read()), f
+
+
+def test_shard_ranges():
+    from tim_b200.dist import shard_range
+    for n, w in ((10, 3), (8, 8), (5, 8), (1000, 7)):
+        parts = [shard_range(n, r, w) for r in range(w)]
+        assert parts[0][0] == 0 and parts[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+        sizes = [b - a for a, b in parts]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def test_gloo_world2_sharded_forward_matches_single():
+    """N>1 host path on CPU: two gloo ranks each take their clip shard (no data-path collective), results are
+    gathered and must equal the unsharded run. The per-shard forward is the oracle here (no GPU in this test)."""
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29517",
+                        os.path.join(ROOT, "tests", "_gloo_worker.py")], capture_output=True, text=True, timeout=300,
+                       cwd=ROOT, env={**os.environ, "OMP_NUM_THREADS": "2"})
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "GLOO_SHARD_OK" in r.stdout

@@ -47,6 +47,8 @@ SYMBOLS = {
     "tim_workspace_bytes": (C.c_size_t, [C.c_void_p]),
     "tim_launch_count": (C.c_uint64, [C.c_void_p]),
     "tim_seq_len": (C.c_int, [C.POINTER(tim_config), C.c_int, C.c_int]),
+    "tim_profile_begin": (C.c_int, [C.c_void_p]),
+    "tim_profile_end": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
     "tim_test_linear": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tim_test_attention": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

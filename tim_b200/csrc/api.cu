@@ -65,6 +65,14 @@ struct tim_ctx {
     uint64_t launches = 0;
     EncodeTiledFn encode = nullptr;
 
+    // optional live profiling: CUDA-event pairs around every launch, accumulated per kernel class
+    bool profiling = false;
+    int cur_class = 0;
+    double cur_flops = 0.0;
+    struct ProfRec { cudaEvent_t a, b; int cls; double flops; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
+
     // weights
     std::map<std::string, Slot> slots;
     std::vector<void*> allocs;
@@ -98,6 +106,13 @@ struct tim_ctx {
 
 namespace {
 
+cudaEvent_t prof_event(tim_ctx* c) {
+    cudaEvent_t e = nullptr;
+    if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
+
 #define CU_OK(ctx, expr)                                                                                   \
     do {                                                                                                   \
         cudaError_t _e = (expr);                                                                           \
@@ -105,13 +120,20 @@ namespace {
             return (ctx)->fail(TIM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
-#define LAUNCH(ctx, expr)                                                                                  \
+// kernel classes for tim_profile_*: 0 tcgen05/SIMT GEMM, 1 attention, 2 LayerNorm, 3 token assembly, 4 other row kernels
+#define LAUNCH_C(ctx, cls_, flops_, stream_, expr)                                                         \
     do {                                                                                                   \
+        tim_ctx::ProfRec _pr;                                                                              \
+        const bool _prof = (ctx)->profiling;                                                               \
+        if (_prof) { _pr.a = prof_event(ctx); _pr.b = prof_event(ctx); _pr.cls = (cls_); _pr.flops = (flops_); \
+                     cudaEventRecord(_pr.a, (stream_)); }                                                  \
         cudaError_t _e = (expr);                                                                           \
         (ctx)->launches++;                                                                                 \
+        if (_prof) { cudaEventRecord(_pr.b, (stream_)); (ctx)->prof.push_back(_pr); }                      \
         if (_e != cudaSuccess)                                                                             \
             return (ctx)->fail(TIM_ERR_CUDA, "launch %s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
+#define LAUNCH(ctx, expr) LAUNCH_C(ctx, 4, 0.0, s, expr)
 
 #define TIM_TRY(expr)              \
     do {                           \
@@ -290,14 +312,15 @@ int run_linear(tim_ctx* c, const void* A, int lda, const LinearW& w, RowMap rm, 
     if (!ep.bias) ep.bias = w.bias;
     if constexpr (std::is_same<T, float>::value) {
         ep.out_fp32 = 1;
-        LAUNCH(c, launch_linear_simt(static_cast<const float*>(A), lda, static_cast<const float*>(w.w), w.N, w.K, rm, ep, s));
+        LAUNCH_C(c, 0, 2.0 * rm.G * rm.R * w.N * w.K, s,
+                 launch_linear_simt(static_cast<const float*>(A), lda, static_cast<const float*>(w.w), w.N, w.K, rm, ep, s));
     } else {
         UmmaParams p;
         std::memset(&p, 0, sizeof(p));
         TIM_TRY(make_tmap(c, &p.tmA, A, w.K, rm.a_group_rows, rm.G, rm.box_r, rm.box_g));
         p.tmB = w.tmB;
         p.N = w.N; p.K = w.K; p.rm = rm; p.ep = ep;
-        LAUNCH(c, launch_linear_umma<T>(p, w.block_n, c->num_sms, s));
+        LAUNCH_C(c, 0, 2.0 * rm.G * rm.R * w.N * w.K, s, launch_linear_umma<T>(p, w.block_n, c->num_sms, s));
     }
     return TIM_OK;
 }
@@ -429,25 +452,27 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
     ap.te = te; ap.n_groups = qp.n_groups;
     for (int i = 0; i < qp.n_groups; ++i) ap.groups[i] = qp.groups[i];
     ap.Qt = Qt; ap.x32 = x32; ap.x16 = f32 ? nullptr : x16;
-    LAUNCH(c, launch_assemble<T>(ap, s));
+    LAUNCH_C(c, 3, 0.0, s, launch_assemble<T>(ap, s));
 
     // ---- encoder layers (post-LN): x = LN1(x + out_proj(attn(in_proj(x)))); x = LN2(x + W2 gelu(W1 x)) ----
     const int Mi = static_cast<int>(M);
+    // algorithmic (mask-aware) attention FLOPs per layer: 4E(Ft^2 + Qt(Ft+1)) per clip
+    const double attn_flops = 4.0 * E * (static_cast<double>(Ft) * Ft + static_cast<double>(Qt) * (Ft + 1)) * B;
     const void* xin = f32 ? static_cast<const void*>(x32) : static_cast<const void*>(x16);
     T* x16o = f32 ? nullptr : x16;
     for (int l = 0; l < c->L; ++l) {
         Layer& ly = c->layers[l];
         TIM_TRY(run_linear<T>(c, xin, E, ly.in_proj, plain_rows(Mi), epi(qkv, 3 * E, f32), s));
         if constexpr (f32) {
-            LAUNCH(c, launch_attention_simt(reinterpret_cast<const float*>(qkv), reinterpret_cast<float*>(att), B, Ft, Qt, c->H, c->hd, s));
+            LAUNCH_C(c, 1, attn_flops, s, launch_attention_simt(reinterpret_cast<const float*>(qkv), reinterpret_cast<float*>(att), B, Ft, Qt, c->H, c->hd, s));
         } else {
-            LAUNCH(c, launch_attention_mma<T>(qkv, att, B, Ft, Qt, c->H, c->hd, s));
+            LAUNCH_C(c, 1, attn_flops, s, launch_attention_mma<T>(qkv, att, B, Ft, Qt, c->H, c->hd, s));
         }
         TIM_TRY(run_linear<T>(c, att, E, ly.out_proj, plain_rows(Mi), epi(z, E, true, ACT_NONE, x32, E), s));
-        LAUNCH(c, launch_layernorm<T>(z, E, ly.n1g, ly.n1b, x32, E, x16o, E, Mi, E, s));
+        LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(z, E, ly.n1g, ly.n1b, x32, E, x16o, E, Mi, E, s));
         TIM_TRY(run_linear<T>(c, xin, E, ly.lin1, plain_rows(Mi), epi(hid, FF, f32, ACT_GELU), s));
         TIM_TRY(run_linear<T>(c, hid, FF, ly.lin2, plain_rows(Mi), epi(z, E, true, ACT_NONE, x32, E), s));
-        LAUNCH(c, launch_layernorm<T>(z, E, ly.n2g, ly.n2b, x32, E, x16o, E, Mi, E, s));
+        LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(z, E, ly.n2g, ly.n2b, x32, E, x16o, E, Mi, E, s));
     }
 
     // ---- heads read slices of the query stream ----
@@ -599,6 +624,8 @@ void tim_destroy(tim_ctx* c) {
     for (void* p : c->allocs) cudaFree(p);
     if (c->ws) cudaFree(c->ws);
     if (c->io) cudaFree(c->io);
+    for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_comp) cudaStreamDestroy(c->s_comp);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
@@ -779,6 +806,34 @@ int tim_forward_host(tim_ctx* c, const float* vis, const float* aud, const float
         return c->fail(TIM_ERR_CUDA, "tim_forward_host: stream sync failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
     if (h2d_bytes) *h2d_bytes = up;
     if (d2h_bytes) *d2h_bytes = down;
+    return TIM_OK;
+}
+
+int tim_profile_begin(tim_ctx* c) {
+    if (!c) return TIM_ERR_INVALID;
+    for (auto& r : c->prof) { c->ev_pool.push_back(r.a); c->ev_pool.push_back(r.b); }
+    c->prof.clear();
+    c->profiling = true;
+    return TIM_OK;
+}
+
+int tim_profile_end(tim_ctx* c, double* ms, double* flops, uint64_t* count, int n_classes) {
+    if (!c) return TIM_ERR_INVALID;
+    c->profiling = false;
+    CU_OK(c, cudaSetDevice(c->device));
+    CU_OK(c, cudaDeviceSynchronize());
+    for (int i = 0; i < n_classes; ++i) { if (ms) ms[i] = 0; if (flops) flops[i] = 0; if (count) count[i] = 0; }
+    for (auto& r : c->prof) {
+        float t = 0.0f;
+        CU_OK(c, cudaEventElapsedTime(&t, r.a, r.b));
+        if (r.cls >= 0 && r.cls < n_classes) {
+            if (ms) ms[r.cls] += t;
+            if (flops) flops[r.cls] += r.flops;
+            if (count) count[r.cls] += 1;
+        }
+        c->ev_pool.push_back(r.a); c->ev_pool.push_back(r.b);
+    }
+    c->prof.clear();
     return TIM_OK;
 }
 

@@ -1,0 +1,44 @@
+"""Data-parallel plumbing: clips shard over ranks (one process per GPU). The forward needs NO data-path collective
+(clips are independent: no BatchNorm, and the mask makes even queries independent) — the only
+collectives here are the timing / result-gathering ones used by bench.py and the tests. Mirrors the reference's
+DistributedSampler split (datasets/loader.py:48-50) and utils/distributed.py:15-53 helpers."""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced (sizes differ by at most one) clip range of `rank`."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def max_over_ranks(value: float, device: str = "cpu") -> float:
+    """Device-timed durations are reported as the max over ranks."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def gather_rows(local: torch.Tensor, rows_per_clip: int, B: int) -> torch.Tensor:
+    """Concatenate per-rank [b_r * rows_per_clip, C] results in clip order (ragged shards allowed)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return local
+    world, rank = dist.get_world_size(), dist.get_rank()
+    C_ = local.shape[1]
+    maxb = max(shard_range(B, r, world)[1] - shard_range(B, r, world)[0] for r in range(world))
+    pad = torch.zeros((maxb * rows_per_clip, C_), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    bufs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(bufs, pad)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_range(B, r, world)
+        parts.append(bufs[r][:(hi - lo) * rows_per_clip])
+    return torch.cat(parts, 0)

@@ -171,6 +171,18 @@ class TIMEngine:
                                                  C.byref(up), C.byref(down)), self._ctx)
         return outs, int(up.value), int(down.value)
 
+    PROFILE_CLASSES = ("gemm", "attention", "layernorm", "assemble", "other")
+
+    def profile_begin(self) -> None:
+        _lib.check(self.lib.tim_profile_begin(self._ctx), self._ctx)
+
+    def profile_end(self) -> Dict[str, Dict[str, float]]:
+        """{class: {ms, flops, launches}} accumulated since profile_begin() (synchronises the device)."""
+        n = len(self.PROFILE_CLASSES)
+        ms, fl, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_uint64 * n)()
+        _lib.check(self.lib.tim_profile_end(self._ctx, ms, fl, cnt, n), self._ctx)
+        return {name: {"ms": ms[i], "flops": fl[i], "launches": int(cnt[i])} for i, name in enumerate(self.PROFILE_CLASSES)}
+
     @property
     def launch_count(self) -> int:
         return int(self.lib.tim_launch_count(self._ctx))
