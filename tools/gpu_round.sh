@@ -1,0 +1,31 @@
+#!/usr/bin/env bash
+# One GPU-box visit: parity tests, the bench line, the ncu launch list of the same command and one full capture of
+# the dominant kernel. Everything lands in gpurun_out/ (scratch); summaries are copied into profiles/ by hand.
+#   gpurun --timeout 1500 -- 'bash tools/gpu_round.sh [tag]'
+set -u
+TAG=${1:-r01}
+OUT=gpurun_out
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total,power.limit --format=csv > $OUT/smi_$TAG.txt 2>&1
+
+if [ "${SKIP_TESTS:-0}" != "1" ]; then
+  timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1
+  echo "pytest exit $?" | tee -a $OUT/pytest_gpu_$TAG.log
+  tail -n 5 $OUT/pytest_gpu_$TAG.log
+fi
+
+timeout 600 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err
+echo "bench exit $?"; cat $OUT/bench_$TAG.json
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_$TAG.json 2>> $OUT/bench_$TAG.err
+cat $OUT/bench_ref_$TAG.json
+
+if [ "${SKIP_NCU:-0}" != "1" ]; then
+  # launch list of the bench command (cold-cache, serialised: compare shares, not absolutes)
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 400 --csv \
+      --log-file $OUT/launches_$TAG.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/ncu_list_$TAG.log 2>&1
+  echo "ncu list exit $?"
+  # one full capture of the dominant kernel (3 launches from the middle of the run)
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:linear_umma -s 40 -c 3 \
+      -o $OUT/prof_gemm_$TAG -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_$TAG.log 2>&1
+  echo "ncu full exit $?"
+fi
