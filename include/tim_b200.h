@@ -117,6 +117,10 @@ int tim_profile_end(tim_ctx* ctx, double* ms, double* flops, uint64_t* count, in
  * computed through the selected compute path (the 16-bit paths cast A and W on device first). */
 int tim_test_linear(int compute_dtype, const float* A, const float* W, const float* bias, const float* resid, float* out,
                     int M, int N, int K, int act, void* stream);
+/* timing hook (tools/gemm_bench.py): `iters` back-to-back launches of one linear layer on 16-bit device operands
+ * A16 [M,K], W16 [N,K]; out is T [M,N] (out_fp32 = 0) or float [M,N]; version 1 = single-CTA kernel, 2 = CTA-pair kernel. */
+int tim_bench_linear(int compute_dtype, const void* A16, const void* W16, const float* bias, const float* resid, void* out,
+                     int M, int N, int K, int act, int out_fp32, int version, int iters, float* ms_per_iter);
 /* attention over a two-stream qkv buffer [(B*Ft + B*Qt), 3*H*hd] fp32 -> out [(B*Ft + B*Qt), H*hd] fp32.
  * The q columns must already carry the hd^-0.5 * log2(e) factor that tim_set_weight folds into in_proj. */
 int tim_test_attention(int compute_dtype, const float* qkv, float* out, int B, int Ft, int Qt, int H, int hd, void* stream);

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -22,7 +23,9 @@ struct LinearW {
     int N = 0, K = 0;
     void* w = nullptr;          // [N, K] in the compute dtype
     float* bias = nullptr;      // [N] fp32
-    CUtensorMap tmB;            // 16-bit modes only
+    CUtensorMap tmB;            // 16-bit modes only: box (64, block_n) for the single-CTA kernel
+    CUtensorMap tmB2;           // box (64, 128) for the CTA-pair kernel
+    bool has_tmB2 = false;
     int block_n = 0;
     int scale_rows = 0;         // leading rows (and bias entries) multiplied by `scale` when packed (q part of in_proj)
     float scale = 1.0f;
@@ -64,6 +67,7 @@ struct tim_ctx {
     std::string err;
     uint64_t launches = 0;
     EncodeTiledFn encode = nullptr;
+    int gemm_version = 2;       // 2: CTA-pair kernel where the shape allows, 1: single-CTA kernel only (TIM_B200_GEMM=1)
 
     // optional live profiling: CUDA-event pairs around every launch, accumulated per kernel class
     bool profiling = false;
@@ -175,6 +179,26 @@ int make_tmap(tim_ctx* c, CUtensorMap* tm, const void* base, int K, long long ro
     return TIM_OK;
 }
 
+// generic row-major 2-D map: `inner` elements per row, `rows` rows, row pitch `pitch_bytes`; 128-byte swizzle
+int make_tmap_2d(tim_ctx* c, CUtensorMap* tm, const void* base, CUtensorMapDataType dt, int esize, long long inner, long long rows,
+                 long long pitch_bytes, int box_inner, int box_rows) {
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (pitch_bytes & 15) != 0 || box_inner * esize != 128)
+        return c->fail(TIM_ERR_INVALID, "TMA map: base / pitch must be 16-byte aligned and the box 128 bytes wide");
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch_bytes)};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_inner), static_cast<cuuint32_t>(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = c->encode(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return c->fail(TIM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%lld rows=%lld pitch=%lld box=(%d,%d)", static_cast<int>(r),
+                       inner, rows, pitch_bytes, box_inner, box_rows);
+    return TIM_OK;
+}
+inline CUtensorMapDataType op_dtype(const tim_ctx* c) {
+    return c->cfg.compute_dtype == TIM_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+}
+
 int make_tmap_w(tim_ctx* c, LinearW& w) {
     const CUtensorMapDataType dt = c->cfg.compute_dtype == TIM_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     if (w.K % 8) return c->fail(TIM_ERR_INVALID, "tcgen05 path needs K %% 8 == 0 (weight K=%d)", w.K);
@@ -186,6 +210,11 @@ int make_tmap_w(tim_ctx* c, LinearW& w) {
     CUresult r = c->encode(&w.tmB, dt, 2, w.w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return c->fail(TIM_ERR_CUDA, "cuTensorMapEncodeTiled(weight %dx%d) failed (%d)", w.N, w.K, static_cast<int>(r));
+    w.has_tmB2 = false;
+    if (w.N >= 128) {
+        TIM_TRY(make_tmap_2d(c, &w.tmB2, w.w, dt, 2, w.K, w.N, static_cast<long long>(w.K) * 2, 64, 128));
+        w.has_tmB2 = true;
+    }
     return TIM_OK;
 }
 
@@ -315,6 +344,27 @@ int run_linear(tim_ctx* c, const void* A, int lda, const LinearW& w, RowMap rm, 
         LAUNCH_C(c, 0, 2.0 * rm.G * rm.R * w.N * w.K, s,
                  launch_linear_simt(static_cast<const float*>(A), lda, static_cast<const float*>(w.w), w.N, w.K, rm, ep, s));
     } else {
+        const bool plain = rm.G == 1 && rm.box_g == 1 && rm.a_row_off == 0 && rm.out_row_off == 0;
+        const int esz_out = ep.out_fp32 ? 4 : 2;
+        if (c->gemm_version >= 2 && plain && w.has_tmB2 && umma2_supported(rm.R, w.N, w.K) && (ep.out_fp32 || !ep.resid) &&
+            (static_cast<size_t>(ep.ldo) * esz_out) % 16 == 0 && (!ep.resid || (static_cast<size_t>(ep.ldr) * 4) % 16 == 0) &&
+            (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0 && (reinterpret_cast<uintptr_t>(ep.resid) & 15) == 0) {
+            Umma2Params q;
+            std::memset(&q, 0, sizeof(q));
+            const int M = rm.R;
+            TIM_TRY(make_tmap_2d(c, &q.tmA, A, op_dtype(c), 2, w.K, M, static_cast<long long>(lda) * 2, 64, 128));
+            q.tmB = w.tmB2;
+            if (ep.out_fp32)
+                TIM_TRY(make_tmap_2d(c, &q.tmOut, ep.out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, w.N, M, static_cast<long long>(ep.ldo) * 4, 32, 32));
+            else
+                TIM_TRY(make_tmap_2d(c, &q.tmOut, ep.out, op_dtype(c), 2, w.N, M, static_cast<long long>(ep.ldo) * 2, 64, 32));
+            if (ep.resid)
+                TIM_TRY(make_tmap_2d(c, &q.tmRes, ep.resid, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, w.N, M, static_cast<long long>(ep.ldr) * 4, 32, 32));
+            q.bias = ep.bias; q.M = M; q.N = w.N; q.K = w.K;
+            const int mode = ep.out_fp32 ? (ep.resid ? 2 : 1) : 0;
+            LAUNCH_C(c, 0, 2.0 * M * w.N * w.K, s, launch_linear_umma2<T>(q, mode, ep.act, c->num_sms, s));
+            return TIM_OK;
+        }
         UmmaParams p;
         std::memset(&p, 0, sizeof(p));
         TIM_TRY(make_tmap(c, &p.tmA, A, w.K, rm.a_group_rows, rm.G, rm.box_r, rm.box_g));
@@ -595,6 +645,7 @@ int tim_create(tim_ctx** out, const tim_config* cfg, int device) {
     c->aud_data = g.data_modality != TIM_VISUAL;
     c->vn_tokens = g.variant == TIM_RECOGNITION && g.include_verb_noun && c->vis_data;
     c->esize = g.compute_dtype == TIM_FP32 ? 4 : 2;
+    if (const char* gv = std::getenv("TIM_B200_GEMM")) c->gemm_version = std::atoi(gv) == 1 ? 1 : 2;
     if (c->d % 4) return bail(c->fail(TIM_ERR_INVALID, "d_model must be a multiple of 4"));
     if (c->vis_data && !g.n_action) return bail(c->fail(TIM_ERR_INVALID, "visual data modality needs n_action > 0"));
     if (c->aud_data && !g.n_audio) return bail(c->fail(TIM_ERR_INVALID, "audio data modality needs n_audio > 0"));
@@ -873,6 +924,7 @@ int tim_test_linear(int dtype, const float* A, const float* W, const float* bias
     c->num_sms = prop.multiProcessorCount; c->device = dev;
     c->cfg.compute_dtype = dtype;
     c->esize = dtype == TIM_FP32 ? 4 : 2;
+    if (const char* gv = std::getenv("TIM_B200_GEMM")) c->gemm_version = std::atoi(gv) == 1 ? 1 : 2;
     LinearW w;
     w.N = N; w.K = K; w.bias = const_cast<float*>(bias);
     Epilogue ep = epi(out, N, true, act, resid, N);
@@ -908,6 +960,47 @@ int tim_test_linear(int dtype, const float* A, const float* W, const float* bias
     if (r) return fin(r);
     cudaError_t e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return fin(c->fail(TIM_ERR_CUDA, "tim_test_linear: %s", cudaGetErrorString(e)));
+    return TIM_OK;
+}
+
+int tim_bench_linear(int dtype, const void* A16, const void* W16, const float* bias, const float* resid, void* out, int M, int N, int K,
+                     int act, int out_fp32, int version, int iters, float* ms_per_iter) {
+    TmpCtx t;
+    tim_ctx* c = &t.c;
+    auto fin = [&](int r) { g_create_error = c->err; return r; };
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
+        g_create_error = "tim_bench_linear: no sm_100 device";
+        return TIM_ERR_NO_DEVICE;
+    }
+    if (dtype != TIM_BF16 && dtype != TIM_FP16) return fin(c->fail(TIM_ERR_INVALID, "tim_bench_linear: 16-bit dtypes only"));
+    c->num_sms = prop.multiProcessorCount; c->device = dev;
+    c->cfg.compute_dtype = dtype;
+    c->esize = 2;
+    c->gemm_version = version == 1 ? 1 : 2;
+    int r = get_encode_fn(c);
+    if (r) return fin(r);
+    LinearW w;
+    w.N = N; w.K = K; w.bias = const_cast<float*>(bias); w.w = const_cast<void*>(W16);
+    r = make_tmap_w(c, w);
+    if (r) return fin(r);
+    Epilogue ep = epi(out, N, out_fp32 != 0, act, resid, N);
+    cudaStream_t s = nullptr;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < iters + 2 && r == TIM_OK; ++i) {
+        if (i == 2) cudaEventRecord(e0, s);
+        r = dtype == TIM_BF16 ? run_linear<__nv_bfloat16>(c, A16, K, w, plain_rows(M), ep, s) : run_linear<__half>(c, A16, K, w, plain_rows(M), ep, s);
+    }
+    cudaEventRecord(e1, s);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (r) return fin(r);
+    if (e != cudaSuccess) return fin(c->fail(TIM_ERR_CUDA, "tim_bench_linear: %s", cudaGetErrorString(e)));
+    if (ms_per_iter) *ms_per_iter = ms / (iters > 0 ? iters : 1);
     return TIM_OK;
 }
 

@@ -33,34 +33,35 @@ template <int HD> struct Swz {
     }
 };
 
+// One CTA per (clip, head[, tile range]): K_f / V_f are staged once and stay resident while the CTA walks over its 64-row
+// tiles (feature tiles first, then query tiles). Shared memory is sized to the padded key count so that two CTAs fit on
+// an SM (104 KB each at Ft = 100, hd = 128): one CTA's cp.async phase overlaps the other's MMA / softmax phase.
 template <typename T, int HD>
-__global__ void __launch_bounds__(AT_WARPS * 32) attention_mma_kernel(const T* __restrict__ qkv, T* __restrict__ out,
-                                                                      int B, int Ft, int Qt, int H, int tiles_f) {
+__global__ void __launch_bounds__(AT_WARPS * 32, 2) attention_mma_kernel(const T* __restrict__ qkv, T* __restrict__ out,
+                                                                         int B, int Ft, int Qt, int H, int tiles_f, int tiles_q,
+                                                                         int tiles_per_cta) {
     constexpr int CH = HD / 8;
     constexpr int KSTEPS = HD / 16;
     constexpr int NT_MAX = AT_MAXKEYS / 8;
     using SW = Swz<HD>;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* sK = smem;                                  // [128][HD]
-    uint8_t* sV = sK + AT_MAXKEYS * HD * 2;              // [128][HD]
-    uint8_t* sQ = sV + AT_MAXKEYS * HD * 2;              // [64][HD]  (reused as the output staging tile)
+    const int Fp = (Ft + 15) & ~15;                       // keys padded to the MMA k granularity
+    uint8_t* sK = smem;                                  // [Fp][HD]
+    uint8_t* sV = sK + Fp * HD * 2;                      // [Fp][HD]
+    uint8_t* sQ = sV + Fp * HD * 2;                      // [64][HD]  (reused as the output staging tile)
     uint8_t* sKq = sQ + AT_BM * HD * 2;                  // [64][HD]  own keys of a query tile
     uint8_t* sVq = sKq + AT_BM * HD * 2;                 // [64][HD]  own values of a query tile
 
-    const int b = blockIdx.z, h = blockIdx.y;
-    const bool qtile = static_cast<int>(blockIdx.x) >= tiles_f;
-    const int t = qtile ? blockIdx.x - tiles_f : blockIdx.x;
-    const int rows_in_stream = qtile ? Qt : Ft;
-    const int row0 = t * AT_BM;                           // first row of the tile inside its stream
-    const int nrows = min(AT_BM, rows_in_stream - row0);
+    const int item = blockIdx.x;                          // (clip, head)
+    const int b = item / H, h = item - b * H;
+    const int tile_lo = blockIdx.y * tiles_per_cta;
+    const int tile_hi = min(tile_lo + tiles_per_cta, tiles_f + tiles_q);
     const size_t E = static_cast<size_t>(H) * HD;
     const size_t ld = 3 * E;
     const size_t feat_base = static_cast<size_t>(b) * Ft;
-    const size_t tile_base = qtile ? static_cast<size_t>(B) * Ft + static_cast<size_t>(b) * Qt + row0 : feat_base + row0;
-    const int Fp = (Ft + 15) & ~15;                       // keys padded to the MMA k granularity
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    // ---- stage K_f, V_f (+ zero padding rows), Q tile and, for query tiles, the tile's own K / V rows ----
+    // ---- stage K_f, V_f (+ zero padding rows) once ----
     for (int i = tid; i < Fp * CH; i += AT_WARPS * 32) {
         const int r = i / CH, c = i - r * CH;
         if (r < Ft) {
@@ -72,140 +73,152 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attention_mma_kernel(const T* _
             *reinterpret_cast<uint4*>(sV + SW::off(r, c)) = make_uint4(0, 0, 0, 0);
         }
     }
-    for (int i = tid; i < AT_BM * CH; i += AT_WARPS * 32) {
-        const int r = i / CH, c = i - r * CH;
-        if (r < nrows) {
-            const T* src = qkv + (tile_base + r) * ld + h * HD + c * 8;
-            cp_async_16(smem_u32(sQ + SW::off(r, c)), src);
-            if (qtile) {
-                cp_async_16(smem_u32(sKq + SW::off(r, c)), src + E);
-                cp_async_16(smem_u32(sVq + SW::off(r, c)), src + 2 * E);
-            }
-        } else {
-            *reinterpret_cast<uint4*>(sQ + SW::off(r, c)) = make_uint4(0, 0, 0, 0);
-            if (qtile) {
-                *reinterpret_cast<uint4*>(sKq + SW::off(r, c)) = make_uint4(0, 0, 0, 0);
-                *reinterpret_cast<uint4*>(sVq + SW::off(r, c)) = make_uint4(0, 0, 0, 0);
-            }
-        }
-    }
-    cp_async_commit();
-    cp_async_wait_all();
-    __syncthreads();
 
-    const int wr0 = warp * 16;                            // this warp's rows inside the tile
-    if (wr0 < nrows) {                                    // warp-uniform
-        const int g = lane >> 2, tq = lane & 3;
-        const int nt = Fp / 8;                            // score n-tiles in use (even)
-        const int lm = lane >> 3, lr = lane & 7;          // ldmatrix: matrix index / row inside it
+    for (int tile = tile_lo; tile < tile_hi; ++tile) {
+        const bool qtile = tile >= tiles_f;
+        const int t = qtile ? tile - tiles_f : tile;
+        const int rows_in_stream = qtile ? Qt : Ft;
+        const int row0 = t * AT_BM;                       // first row of the tile inside its stream
+        const int nrows = min(AT_BM, rows_in_stream - row0);
+        const size_t tile_base = qtile ? static_cast<size_t>(B) * Ft + static_cast<size_t>(b) * Qt + row0 : feat_base + row0;
 
-        // ---- S = Q K_f^T  (and the self score q.k_self for query tiles) ----
-        float sc[NT_MAX][4];
-#pragma unroll
-        for (int j = 0; j < NT_MAX; ++j) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.0f; }
-        float self0 = 0.0f, self1 = 0.0f;                 // rows g and g+8
-#pragma unroll
-        for (int kk = 0; kk < KSTEPS; ++kk) {
-            uint32_t a[4];
-            const int arow = wr0 + (lm & 1) * 8 + lr, achunk = kk * 2 + (lm >> 1);
-            ldmatrix_x4(smem_u32(sQ + SW::off(arow, achunk)), a[0], a[1], a[2], a[3]);
-            if (qtile) {
-                uint32_t kq[4];
-                ldmatrix_x4(smem_u32(sKq + SW::off(arow, achunk)), kq[0], kq[1], kq[2], kq[3]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 qa = unpack2<T>(a[i]), ka = unpack2<T>(kq[i]);
-                    const float d = qa.x * ka.x + qa.y * ka.y;
-                    if (i & 1) self1 += d; else self0 += d;
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < NT_MAX; j += 2) {
-                if (j < nt) {
-                    uint32_t b0, b1, b2, b3;
-                    const int krow = 8 * (j + (lm >> 1)) + lr, kchunk = kk * 2 + (lm & 1);
-                    ldmatrix_x4(smem_u32(sK + SW::off(krow, kchunk)), b0, b1, b2, b3);
-                    MmaSync<T>::run(sc[j], a, b0, b1);
-                    MmaSync<T>::run(sc[j + 1], a, b2, b3);
-                }
-            }
-        }
-        // ---- softmax over (feature keys [+ self]) in the log2 domain ----
-        float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < NT_MAX; ++j) {
-            if (j < nt) {
-                const int key = 8 * j + 2 * tq;
-                if (key >= Ft) { sc[j][0] = -INFINITY; sc[j][2] = -INFINITY; }
-                if (key + 1 >= Ft) { sc[j][1] = -INFINITY; sc[j][3] = -INFINITY; }
-                m0 = fmaxf(m0, fmaxf(sc[j][0], sc[j][1]));
-                m1 = fmaxf(m1, fmaxf(sc[j][2], sc[j][3]));
-            }
-        }
-        if (qtile) {
-            self0 += __shfl_xor_sync(0xffffffffu, self0, 1); self0 += __shfl_xor_sync(0xffffffffu, self0, 2);
-            self1 += __shfl_xor_sync(0xffffffffu, self1, 1); self1 += __shfl_xor_sync(0xffffffffu, self1, 2);
-        } else {
-            self0 = self1 = -INFINITY;
-        }
-        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-        m0 = fmaxf(m0, self0); m1 = fmaxf(m1, self1);
-        float l0 = 0.0f, l1 = 0.0f;
-        uint32_t pa[NT_MAX / 2][4];                       // P as A fragments for the PV MMAs
-#pragma unroll
-        for (int j = 0; j < NT_MAX; ++j) {
-            if (j < nt) {
-                const float p0 = exp2f(sc[j][0] - m0), p1 = exp2f(sc[j][1] - m0);
-                const float p2 = exp2f(sc[j][2] - m1), p3 = exp2f(sc[j][3] - m1);
-                l0 += p0 + p1; l1 += p2 + p3;
-                pa[j >> 1][(j & 1) * 2 + 0] = pack2<T>(p0, p1);
-                pa[j >> 1][(j & 1) * 2 + 1] = pack2<T>(p2, p3);
-            }
-        }
-        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-        const float ps0 = qtile ? exp2f(self0 - m0) : 0.0f;
-        const float ps1 = qtile ? exp2f(self1 - m1) : 0.0f;
-        const float inv0 = 1.0f / (l0 + ps0), inv1 = 1.0f / (l1 + ps1);
-
-        // ---- O = P V_f (+ p_self * v_self), normalise, stage into this warp's rows of sQ ----
-        __syncwarp();                                     // all lanes of the warp are done reading their sQ rows
-#pragma unroll
-        for (int jn = 0; jn < HD / 8; jn += 2) {
-            float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int k2 = 0; k2 < NT_MAX / 2; ++k2) {
-                if (2 * k2 < nt) {
-                    uint32_t b0, b1, b2, b3;
-                    const int vrow = 16 * k2 + (lm & 1) * 8 + lr, vchunk = jn + (lm >> 1);
-                    ldmatrix_x4_trans(smem_u32(sV + SW::off(vrow, vchunk)), b0, b1, b2, b3);
-                    MmaSync<T>::run(o0, pa[k2], b0, b1);
-                    MmaSync<T>::run(o1, pa[k2], b2, b3);
-                }
-            }
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float* o = half ? o1 : o0;
-                const int chunk = jn + half;
-                const int r_lo = wr0 + g, r_hi = wr0 + g + 8;
-                if (qtile) {
-                    const float2 vlo = unpack2<T>(*reinterpret_cast<const uint32_t*>(sVq + SW::off(r_lo, chunk) + tq * 4));
-                    const float2 vhi = unpack2<T>(*reinterpret_cast<const uint32_t*>(sVq + SW::off(r_hi, chunk) + tq * 4));
-                    o[0] += ps0 * vlo.x; o[1] += ps0 * vlo.y;
-                    o[2] += ps1 * vhi.x; o[3] += ps1 * vhi.y;
-                }
-                *reinterpret_cast<uint32_t*>(sQ + SW::off(r_lo, chunk) + tq * 4) = pack2<T>(o[0] * inv0, o[1] * inv0);
-                *reinterpret_cast<uint32_t*>(sQ + SW::off(r_hi, chunk) + tq * 4) = pack2<T>(o[2] * inv1, o[3] * inv1);
-            }
-        }
-        __syncwarp();
-        // ---- coalesced 16-byte stores of this warp's 16 rows ----
-        for (int i = lane; i < 16 * CH; i += 32) {
-            const int r = wr0 + i / CH, c = i % CH;
+        if (tile != tile_lo) __syncthreads();             // everyone is done with the previous tile's sQ / sKq / sVq
+        // ---- stage the Q tile and, for query tiles, the tile's own K / V rows ----
+        for (int i = tid; i < AT_BM * CH; i += AT_WARPS * 32) {
+            const int r = i / CH, c = i - r * CH;
             if (r < nrows) {
-                const uint4 v = *reinterpret_cast<const uint4*>(sQ + SW::off(r, c));
-                *reinterpret_cast<uint4*>(out + (tile_base + r) * E + h * HD + c * 8) = v;
+                const T* src = qkv + (tile_base + r) * ld + h * HD + c * 8;
+                cp_async_16(smem_u32(sQ + SW::off(r, c)), src);
+                if (qtile) {
+                    cp_async_16(smem_u32(sKq + SW::off(r, c)), src + E);
+                    cp_async_16(smem_u32(sVq + SW::off(r, c)), src + 2 * E);
+                }
+            } else {
+                *reinterpret_cast<uint4*>(sQ + SW::off(r, c)) = make_uint4(0, 0, 0, 0);
+                if (qtile) {
+                    *reinterpret_cast<uint4*>(sKq + SW::off(r, c)) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4*>(sVq + SW::off(r, c)) = make_uint4(0, 0, 0, 0);
+                }
+            }
+        }
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncthreads();
+
+        const int wr0 = warp * 16;                        // this warp's rows inside the tile
+        if (wr0 < nrows) {                                // warp-uniform
+            const int g = lane >> 2, tq = lane & 3;
+            const int nt = Fp / 8;                        // score n-tiles in use (even)
+            const int lm = lane >> 3, lr = lane & 7;      // ldmatrix: matrix index / row inside it
+
+            // ---- S = Q K_f^T  (and the self score q.k_self for query tiles) ----
+            float sc[NT_MAX][4];
+#pragma unroll
+            for (int j = 0; j < NT_MAX; ++j) { sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.0f; }
+            float self0 = 0.0f, self1 = 0.0f;             // rows g and g+8
+#pragma unroll
+            for (int kk = 0; kk < KSTEPS; ++kk) {
+                uint32_t a[4];
+                const int arow = wr0 + (lm & 1) * 8 + lr, achunk = kk * 2 + (lm >> 1);
+                ldmatrix_x4(smem_u32(sQ + SW::off(arow, achunk)), a[0], a[1], a[2], a[3]);
+                if (qtile) {
+                    uint32_t kq[4];
+                    ldmatrix_x4(smem_u32(sKq + SW::off(arow, achunk)), kq[0], kq[1], kq[2], kq[3]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 qa = unpack2<T>(a[i]), ka = unpack2<T>(kq[i]);
+                        const float d = qa.x * ka.x + qa.y * ka.y;
+                        if (i & 1) self1 += d; else self0 += d;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < NT_MAX; j += 2) {
+                    if (j < nt) {
+                        uint32_t b0, b1, b2, b3;
+                        const int krow = 8 * (j + (lm >> 1)) + lr, kchunk = kk * 2 + (lm & 1);
+                        ldmatrix_x4(smem_u32(sK + SW::off(krow, kchunk)), b0, b1, b2, b3);
+                        MmaSync<T>::run(sc[j], a, b0, b1);
+                        MmaSync<T>::run(sc[j + 1], a, b2, b3);
+                    }
+                }
+            }
+            // ---- softmax over (feature keys [+ self]) in the log2 domain ----
+            float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < NT_MAX; ++j) {
+                if (j < nt) {
+                    const int key = 8 * j + 2 * tq;
+                    if (key >= Ft) { sc[j][0] = -INFINITY; sc[j][2] = -INFINITY; }
+                    if (key + 1 >= Ft) { sc[j][1] = -INFINITY; sc[j][3] = -INFINITY; }
+                    m0 = fmaxf(m0, fmaxf(sc[j][0], sc[j][1]));
+                    m1 = fmaxf(m1, fmaxf(sc[j][2], sc[j][3]));
+                }
+            }
+            if (qtile) {
+                self0 += __shfl_xor_sync(0xffffffffu, self0, 1); self0 += __shfl_xor_sync(0xffffffffu, self0, 2);
+                self1 += __shfl_xor_sync(0xffffffffu, self1, 1); self1 += __shfl_xor_sync(0xffffffffu, self1, 2);
+            } else {
+                self0 = self1 = -INFINITY;
+            }
+            m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+            m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+            m0 = fmaxf(m0, self0); m1 = fmaxf(m1, self1);
+            float l0 = 0.0f, l1 = 0.0f;
+            uint32_t pa[NT_MAX / 2][4];                   // P as A fragments for the PV MMAs
+#pragma unroll
+            for (int j = 0; j < NT_MAX; ++j) {
+                if (j < nt) {
+                    const float p0 = exp2f(sc[j][0] - m0), p1 = exp2f(sc[j][1] - m0);
+                    const float p2 = exp2f(sc[j][2] - m1), p3 = exp2f(sc[j][3] - m1);
+                    l0 += p0 + p1; l1 += p2 + p3;
+                    pa[j >> 1][(j & 1) * 2 + 0] = pack2<T>(p0, p1);
+                    pa[j >> 1][(j & 1) * 2 + 1] = pack2<T>(p2, p3);
+                }
+            }
+            l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+            l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+            const float ps0 = qtile ? exp2f(self0 - m0) : 0.0f;
+            const float ps1 = qtile ? exp2f(self1 - m1) : 0.0f;
+            const float inv0 = 1.0f / (l0 + ps0), inv1 = 1.0f / (l1 + ps1);
+
+            // ---- O = P V_f (+ p_self * v_self), normalise, stage into this warp's rows of sQ ----
+            __syncwarp();                                 // all lanes of the warp are done reading their sQ rows
+#pragma unroll
+            for (int jn = 0; jn < HD / 8; jn += 2) {
+                float o0[4] = {0.f, 0.f, 0.f, 0.f}, o1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k2 = 0; k2 < NT_MAX / 2; ++k2) {
+                    if (2 * k2 < nt) {
+                        uint32_t b0, b1, b2, b3;
+                        const int vrow = 16 * k2 + (lm & 1) * 8 + lr, vchunk = jn + (lm >> 1);
+                        ldmatrix_x4_trans(smem_u32(sV + SW::off(vrow, vchunk)), b0, b1, b2, b3);
+                        MmaSync<T>::run(o0, pa[k2], b0, b1);
+                        MmaSync<T>::run(o1, pa[k2], b2, b3);
+                    }
+                }
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float* o = half ? o1 : o0;
+                    const int chunk = jn + half;
+                    const int r_lo = wr0 + g, r_hi = wr0 + g + 8;
+                    if (qtile) {
+                        const float2 vlo = unpack2<T>(*reinterpret_cast<const uint32_t*>(sVq + SW::off(r_lo, chunk) + tq * 4));
+                        const float2 vhi = unpack2<T>(*reinterpret_cast<const uint32_t*>(sVq + SW::off(r_hi, chunk) + tq * 4));
+                        o[0] += ps0 * vlo.x; o[1] += ps0 * vlo.y;
+                        o[2] += ps1 * vhi.x; o[3] += ps1 * vhi.y;
+                    }
+                    *reinterpret_cast<uint32_t*>(sQ + SW::off(r_lo, chunk) + tq * 4) = pack2<T>(o[0] * inv0, o[1] * inv0);
+                    *reinterpret_cast<uint32_t*>(sQ + SW::off(r_hi, chunk) + tq * 4) = pack2<T>(o[2] * inv1, o[3] * inv1);
+                }
+            }
+            __syncwarp();
+            // ---- coalesced 16-byte stores of this warp's 16 rows ----
+            for (int i = lane; i < 16 * CH; i += 32) {
+                const int r = wr0 + i / CH, c = i % CH;
+                if (r < nrows) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(sQ + SW::off(r, c));
+                    *reinterpret_cast<uint4*>(out + (tile_base + r) * E + h * HD + c * 8) = v;
+                }
             }
         }
     }
@@ -213,17 +226,27 @@ __global__ void __launch_bounds__(AT_WARPS * 32) attention_mma_kernel(const T* _
 
 template <typename T, int HD>
 cudaError_t launch_attn_hd(const T* qkv, T* out, int B, int Ft, int Qt, int H, cudaStream_t s) {
-    const size_t smem = static_cast<size_t>(2 * AT_MAXKEYS + 3 * AT_BM) * HD * 2;
+    const int Fp = (Ft + 15) & ~15;
+    const size_t smem = static_cast<size_t>(2 * Fp + 3 * AT_BM) * HD * 2;
     auto kern = attention_mma_kernel<T, HD>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        smem_set = smem;
     }
     const int tiles_f = (Ft + AT_BM - 1) / AT_BM, tiles_q = (Qt + AT_BM - 1) / AT_BM;
-    dim3 grid(tiles_f + tiles_q, H, B);
-    kern<<<grid, AT_WARPS * 32, smem, s>>>(qkv, out, B, Ft, Qt, H, tiles_f);
+    const int tiles = tiles_f + tiles_q;
+    // split an item's tiles over several CTAs only when (clip, head) items alone cannot fill the machine
+    const long long items = 1LL * B * H;
+    if (items > 0x7fffffffLL) return cudaErrorInvalidValue;
+    int nsplit = static_cast<int>((148LL * 2 * 4 + items - 1) / items);
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > tiles) nsplit = tiles;
+    const int tiles_per_cta = (tiles + nsplit - 1) / nsplit;
+    nsplit = (tiles + tiles_per_cta - 1) / tiles_per_cta;
+    dim3 grid(static_cast<unsigned>(items), nsplit);
+    kern<<<grid, AT_WARPS * 32, smem, s>>>(qkv, out, B, Ft, Qt, H, tiles_f, tiles_q, tiles_per_cta);
     return cudaGetLastError();
 }
 

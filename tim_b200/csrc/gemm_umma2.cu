@@ -1,0 +1,303 @@
+// CTA-pair tcgen05 GEMM (cta_group::2) for the big dense contractions of the TIM encoder layers
+// (in_proj, out_proj, linear1, linear2; also the embedders / time-MLP / regression-head layers when N % 64 == 0):
+//     C[M, N] = A[M, K] * W[N, K]^T      16-bit operands, fp32 accumulate in TMEM
+// Replaces the torch addmm calls under */models/helpers/transformers.py:102-109 (no reference kernel exists).
+//
+// Why a second kernel: the single-CTA 128 x 256 tile of gemm_umma.cu pulls 48 KB from L2 per 64-wide k-step
+// (96 B/clk/SM), measured at 59 % tensor-pipe for in_proj and 26-45 % when the epilogue does uncoalesced fp32
+// traffic (profiles/r01a_*). Here two CTAs of a cluster share one 256 x 256 tile: each stages only its own 128 A rows
+// and 128 W rows (32 KB per k-step, 64 B/clk/SM), the leader issues tcgen05.mma.cta_group::2 for both, and the
+// epilogue goes through swizzled shared memory and TMA (bulk tensor stores, TMA loads for the fp32 residual) so that
+// global traffic is full 128-byte lines.
+//
+// Per CTA (320 threads):
+//   warp 0    : TMA producer (own A / W halves; completion bytes are signalled on the LEADER's full barrier)
+//   warp 1    : leader: MMA issuer (256 x 256 x 16 per instruction); both: TMEM allocation (512 columns = 2 accumulators)
+//   warps 2-9 : epilogue; warp w owns TMEM lanes 32*(w%4).. and every other column block of the tile
+// Pipelines: smem full/empty ring (5 stages), TMEM full/empty (2 accumulators), per-warp TMA store / residual-load
+// double buffers. Persistent: cluster c walks tiles c, c + #clusters, ... (N fastest, so A tiles are shared through L2).
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace tim {
+namespace {
+
+constexpr int BM = 128;                 // rows per CTA (256 per pair)
+constexpr int BN = 256;                 // columns per pair tile; each CTA stages BN/2 weight rows
+constexpr int BK = 64;                  // one 128-byte swizzle row of 16-bit elements
+constexpr int UK = 16;
+constexpr int STAGES = 5;
+constexpr int A_BYTES = BM * BK * 2;            // 16 KB
+constexpr int B_BYTES = (BN / 2) * BK * 2;      // 16 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 64 + EPI_WARPS * 32;
+constexpr int EPI_BUF = 32 * 128;               // 32 rows x 128 B
+constexpr int EPI_BUFS = 2;                     // per warp
+constexpr int BAR_BYTES = 512;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_BUFS * EPI_BUF + BAR_BYTES + 1024;
+constexpr int TMEM_COLS = 512;
+
+template <typename T> struct FmtOf2;
+template <> struct FmtOf2<__half> { static constexpr uint32_t v = 0; };
+template <> struct FmtOf2<__nv_bfloat16> { static constexpr uint32_t v = 1; };
+
+template <int ACT> __device__ __forceinline__ float apply_act(float v) {
+    if (ACT == ACT_RELU) return fmaxf(v, 0.0f);
+    if (ACT == ACT_GELU) return gelu_erf_fast(v);
+    return v;
+}
+
+// MODE 0: 16-bit output, 1: fp32 output, 2: fp32 output + fp32 residual (added after the activation)
+template <typename T, int MODE, int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_umma2_kernel(const __grid_constant__ Umma2Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t smem_a = smem_base;
+    const uint32_t smem_b = smem_base + STAGES * A_BYTES;
+    const uint32_t epi_base = smem_base + STAGES * STAGE_BYTES;
+    const uint32_t bar_base = epi_base + EPI_WARPS * EPI_BUFS * EPI_BUF;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    auto epild_bar = [&](int w, int b) { return bar_base + 8u * (2 * STAGES + 4 + w * EPI_BUFS + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4 + EPI_WARPS * EPI_BUFS);
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int num_kb = (p.K + BK - 1) / BK;
+    const int num_tiles = p.tiles_m * p.tiles_n;
+    const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA);
+        tma_prefetch_desc(&p.tmB);
+        tma_prefetch_desc(&p.tmOut);
+        if (MODE == 2) tma_prefetch_desc(&p.tmRes);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+            for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * EPI_WARPS); }
+            for (int w = 0; w < EPI_WARPS; ++w)
+                for (int b = 0; b < EPI_BUFS; ++b) mbar_init(epild_bar(w, b), 1);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc_cg2(tmem_slot, TMEM_COLS);
+        tmem_relinquish_cg2();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+                const int m0 = tm * (2 * BM) + static_cast<int>(rank) * BM;
+                const int n0 = tn * BN + static_cast<int>(rank) * (BN / 2);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    const uint32_t fb = mapa_shared(full_bar(stage), 0);     // the leader's barrier
+                    if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
+                    tma_load_2d_cg2(smem_a + stage * A_BYTES, &p.tmA, fb, kb * BK, m0);
+                    tma_load_2d_cg2(smem_b + stage * B_BYTES, &p.tmB, fb, kb * BK, n0);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(FmtOf2<T>::v, 2 * BM, BN);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint64_t adesc = umma_desc_sw128(smem_a + stage * A_BYTES);
+                    const uint64_t bdesc = umma_desc_sw128(smem_b + stage * B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UK; ++k)
+                        umma_f16_ss_cg2(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit_cg2(empty_bar(stage), 3);       // frees this stage in both CTAs
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit_cg2(tfull_bar(acc), 3);             // accumulator complete -> both epilogues
+                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue (warps 2..9, both CTAs) =====================
+        const int e = warp - 2;
+        const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
+        const int half = e >> 2;                          // which interleaved set of column blocks
+        const uint32_t buf0 = epi_base + static_cast<uint32_t>(e * EPI_BUFS) * EPI_BUF;
+        const uint32_t my_row = static_cast<uint32_t>(lane) * 128u;
+        const uint32_t swz = static_cast<uint32_t>(lane & 7);
+        const uint32_t tempty_leader0 = mapa_shared(tempty_bar(0), 0), tempty_leader1 = mapa_shared(tempty_bar(1), 0);
+        constexpr int COLS_PER_BLOCK = MODE == 0 ? 64 : 32;      // 128 B of output per row
+        constexpr int BLOCKS = BN / COLS_PER_BLOCK;
+        int acc = 0; uint32_t acc_phase = 0;
+        uint32_t nbuf = 0;                                // running buffer counter (selects buffer and its load parity)
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+            const int row0 = tm * (2 * BM) + static_cast<int>(rank) * BM + quarter * 32;
+            const int n0 = tn * BN;
+            const bool rows_live = row0 < p.M;            // warp-uniform: nothing to store for a fully out-of-range slice
+            // number of column blocks of this tile that exist (N % 64 == 0, so blocks are all-or-nothing)
+            int my_blocks = 0;
+            for (int cb = half; cb < BLOCKS; cb += 2) my_blocks += (n0 + cb * COLS_PER_BLOCK < p.N) ? 1 : 0;
+            if (!rows_live) my_blocks = 0;
+
+            if (MODE == 2 && my_blocks > 0) {             // prefetch the residual of the first block
+                const uint32_t b = nbuf & 1u;
+                if (lane == 0) {
+                    tma_store_wait_read<0>();             // that buffer's previous store has drained
+                    mbar_arrive_expect_tx(epild_bar(e, b), EPI_BUF);
+                    tma_load_2d(buf0 + b * EPI_BUF, &p.tmRes, epild_bar(e, b), n0 + half * COLS_PER_BLOCK, row0);
+                }
+                __syncwarp();
+            }
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
+
+            for (int i = 0; i < my_blocks; ++i) {
+                const int cb = half + 2 * i;
+                const int col0 = n0 + cb * COLS_PER_BLOCK;
+                const uint32_t b = nbuf & 1u;
+                const uint32_t buf = buf0 + b * EPI_BUF;
+                if (MODE == 2) {
+                    if (i + 1 < my_blocks) {              // prefetch the next block's residual into the other buffer
+                        if (lane == 0) {
+                            tma_store_wait_read<0>();
+                            mbar_arrive_expect_tx(epild_bar(e, b ^ 1u), EPI_BUF);
+                            tma_load_2d(buf0 + (b ^ 1u) * EPI_BUF, &p.tmRes, epild_bar(e, b ^ 1u), col0 + 2 * COLS_PER_BLOCK, row0);
+                        }
+                        __syncwarp();
+                    }
+                    mbar_wait(epild_bar(e, b), (nbuf >> 1) & 1u);
+                } else {
+                    if (lane == 0) tma_store_wait_read<EPI_BUFS - 1>();   // the store that last used this buffer has read it
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int part = 0; part < COLS_PER_BLOCK / 32; ++part) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_addr + static_cast<uint32_t>(cb * COLS_PER_BLOCK + part * 32), v);
+                    tmem_ld_wait();
+                    float f[32];
+                    const int n = col0 + part * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+                        f[j] = apply_act<ACT>(__uint_as_float(v[j]) + b4.x);
+                        f[j + 1] = apply_act<ACT>(__uint_as_float(v[j + 1]) + b4.y);
+                        f[j + 2] = apply_act<ACT>(__uint_as_float(v[j + 2]) + b4.z);
+                        f[j + 3] = apply_act<ACT>(__uint_as_float(v[j + 3]) + b4.w);
+                    }
+                    if (MODE == 0) {
+                        // 32 columns -> 64 B = logical 16-byte chunks part*4 .. part*4+3 of this row
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            uint4 q;
+                            q.x = pack2<T>(f[8 * c], f[8 * c + 1]); q.y = pack2<T>(f[8 * c + 2], f[8 * c + 3]);
+                            q.z = pack2<T>(f[8 * c + 4], f[8 * c + 5]); q.w = pack2<T>(f[8 * c + 6], f[8 * c + 7]);
+                            const uint32_t chunk = static_cast<uint32_t>(part * 4 + c);
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                                         ::"r"(buf + my_row + ((chunk ^ swz) << 4)), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const uint32_t addr = buf + my_row + ((static_cast<uint32_t>(c) ^ swz) << 4);
+                            float4 o = make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
+                            if (MODE == 2) {
+                                float4 r;
+                                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                                             : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+                                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                            }
+                            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
+                                         ::"r"(addr), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+                        }
+                    }
+                }
+                fence_proxy_async_smem();                 // generic-proxy smem writes -> visible to the TMA store
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&p.tmOut, buf, col0, row0);
+                    tma_store_commit();
+                }
+                ++nbuf;
+            }
+            // all of this warp's TMEM reads of the accumulator are done
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc ? tempty_leader1 : tempty_leader0);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+        }
+        if (lane == 0) tma_store_wait<0>();               // stores complete before the CTA (and its smem) goes away
+        __syncwarp();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_cg2(tmem_base, TMEM_COLS);
+    }
+}
+
+template <typename T, int MODE, int ACT>
+cudaError_t launch_mode(const Umma2Params& p, int num_sms, cudaStream_t s) {
+    auto kern = linear_umma2_kernel<T, MODE, ACT>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    const int tiles = p.tiles_m * p.tiles_n;
+    if (tiles <= 0) return cudaSuccess;
+    int clusters = num_sms / 2;
+    if (clusters > tiles) clusters = tiles;
+    kern<<<2 * clusters, THREADS, SMEM_BYTES, s>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool umma2_supported(int M, int N, int K) { return M > 0 && N >= 128 && (N % 64) == 0 && K >= 64 && (K % 8) == 0; }
+
+template <typename T>
+cudaError_t launch_linear_umma2(Umma2Params p, int mode, int act, int num_sms, cudaStream_t s) {
+    p.tiles_m = (p.M + 2 * BM - 1) / (2 * BM);
+    p.tiles_n = (p.N + BN - 1) / BN;
+#define TIM_U2(MODE_, ACT_) if (mode == MODE_ && act == ACT_) return launch_mode<T, MODE_, ACT_>(p, num_sms, s);
+    TIM_U2(0, ACT_NONE) TIM_U2(0, ACT_RELU) TIM_U2(0, ACT_GELU)
+    TIM_U2(1, ACT_NONE) TIM_U2(1, ACT_RELU) TIM_U2(1, ACT_GELU)
+    TIM_U2(2, ACT_NONE) TIM_U2(2, ACT_RELU) TIM_U2(2, ACT_GELU)
+#undef TIM_U2
+    return cudaErrorInvalidValue;
+}
+template cudaError_t launch_linear_umma2<__half>(Umma2Params, int, int, int, cudaStream_t);
+template cudaError_t launch_linear_umma2<__nv_bfloat16>(Umma2Params, int, int, int, cudaStream_t);
+
+}  // namespace tim

@@ -49,6 +49,21 @@ int umma_block_n(int N);   // tile width chosen for an N-column weight (64 / 128
 template <typename T>
 cudaError_t launch_linear_umma(UmmaParams p, int block_n, int num_sms, cudaStream_t s);
 
+// ---- CTA-pair tcgen05 GEMM (cta_group::2, 256 x 256 tiles, TMA-store epilogue): plain [M, K] x [N, K]^T only ----
+struct Umma2Params {
+    CUtensorMap tmA;      // 2-D (K, M), box (64, 128), SWIZZLE_128B
+    CUtensorMap tmB;      // 2-D (K, N), box (64, 128), SWIZZLE_128B
+    CUtensorMap tmOut;    // 2-D (N, M): 16-bit box (64, 32) / fp32 box (32, 32), SWIZZLE_128B
+    CUtensorMap tmRes;    // fp32 (N, M), box (32, 32), SWIZZLE_128B (mode 2 only)
+    const float* bias;    // [N]
+    int M, N, K;
+    int tiles_m, tiles_n;
+};
+bool umma2_supported(int M, int N, int K);
+// mode 0: out = T(act(acc + bias)); 1: out = float(act(acc + bias)); 2: out = float(act(acc + bias) + resid)
+template <typename T>
+cudaError_t launch_linear_umma2(Umma2Params p, int mode, int act, int num_sms, cudaStream_t s);
+
 // ---- fp32 SIMT GEMM with the same row mapping / epilogue (fp32 parity mode) ----
 cudaError_t launch_linear_simt(const float* A, int lda, const float* W, int N, int K, RowMap rm, Epilogue ep,
                                cudaStream_t s);
