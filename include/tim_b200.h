@@ -125,6 +125,11 @@ int tim_bench_linear(int compute_dtype, const void* A16, const void* W16, const 
  * The q columns must already carry the hd^-0.5 * log2(e) factor that tim_set_weight folds into in_proj. */
 int tim_test_attention(int compute_dtype, const float* qkv, float* out, int B, int Ft, int Qt, int H, int hd, void* stream);
 
+/* timing hook (tools/attn_bench.py): `iters` back-to-back attention launches on a 16-bit two-stream qkv buffer
+ * [(B*Ft + B*Qt), 3*H*hd] -> out16 [(B*Ft + B*Qt), H*hd]; version 1 = warp-MMA kernel, 2 = tcgen05 kernel (where supported). */
+int tim_bench_attention(int compute_dtype, const void* qkv16, void* out16, int B, int Ft, int Qt, int H, int hd, int version,
+                        int iters, float* ms_per_iter);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/tim_b200.h"
@@ -68,6 +69,7 @@ struct tim_ctx {
     uint64_t launches = 0;
     EncodeTiledFn encode = nullptr;
     int gemm_version = 2;       // 2: CTA-pair kernel where the shape allows, 1: single-CTA kernel only (TIM_B200_GEMM=1)
+    int attn_version = 2;       // 2: tcgen05 attention where the shape allows, 1: warp-MMA attention only (TIM_B200_ATTN=1)
 
     // optional live profiling: CUDA-event pairs around every launch, accumulated per kernel class
     bool profiling = false;
@@ -193,6 +195,26 @@ int make_tmap_2d(tim_ctx* c, CUtensorMap* tm, const void* base, CUtensorMapDataT
     if (r != CUDA_SUCCESS)
         return c->fail(TIM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%lld rows=%lld pitch=%lld box=(%d,%d)", static_cast<int>(r),
                        inner, rows, pitch_bytes, box_inner, box_rows);
+    return TIM_OK;
+}
+// 3-D map (inner elements, rows of a group, groups) with explicit pitches; 16-bit elements, box (64, box_rows, 1), 128-byte swizzle.
+// Rows / groups outside the tensor are zero-filled on load and skipped on store (the attention kernel relies on both).
+int make_tmap_3d16(tim_ctx* c, CUtensorMap* tm, const void* base, long long inner, long long rows, long long groups,
+                   long long row_pitch_bytes, long long group_pitch_bytes, int box_rows) {
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (row_pitch_bytes & 15) != 0 || (group_pitch_bytes & 15) != 0)
+        return c->fail(TIM_ERR_INVALID, "TMA map: base / pitches must be 16-byte aligned");
+    if (inner <= 0 || rows <= 0 || groups <= 0 || box_rows <= 0 || box_rows > 256)
+        return c->fail(TIM_ERR_INVALID, "TMA map: empty tensor or bad box");
+    const CUtensorMapDataType dt = c->cfg.compute_dtype == TIM_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    cuuint64_t dims[3] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(groups)};
+    cuuint64_t strides[2] = {static_cast<cuuint64_t>(row_pitch_bytes), static_cast<cuuint64_t>(group_pitch_bytes)};
+    cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = c->encode(tm, dt, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return c->fail(TIM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%lld rows=%lld groups=%lld box_rows=%d", static_cast<int>(r),
+                       inner, rows, groups, box_rows);
     return TIM_OK;
 }
 inline CUtensorMapDataType op_dtype(const tim_ctx* c) {
@@ -375,6 +397,28 @@ int run_linear(tim_ctx* c, const void* A, int lda, const LinearW& w, RowMap rm, 
     return TIM_OK;
 }
 
+// attention over the two-stream qkv buffer: tcgen05 kernel where it applies (head_dim 64 / 128 / 192, Ft <= 128), else the
+// warp-MMA kernel. `ap` caches the TMA maps for (qkv, out, B, Qt): they are identical for every layer of one forward.
+template <typename T>
+int prepare_attention(tim_ctx* c, AttnUmmaParams* ap, bool* use_umma, const T* qkv, T* out, int B, int Ft, int Qt) {
+    *use_umma = c->attn_version >= 2 && attention_umma_supported(Ft, c->hd);
+    if (!*use_umma) return TIM_OK;
+    std::memset(ap, 0, sizeof(*ap));
+    const long long E = c->E, ld = 3LL * c->E;
+    const int Fp = (Ft + 15) & ~15;
+    TIM_TRY(make_tmap_3d16(c, &ap->tmKV, qkv, ld, Ft, B, ld * 2, ld * 2 * Ft, Fp));
+    TIM_TRY(make_tmap_3d16(c, &ap->tmQf, qkv, ld, Ft, B, ld * 2, ld * 2 * Ft, 128));
+    TIM_TRY(make_tmap_3d16(c, &ap->tmOf, out, E, Ft, B, E * 2, E * 2 * Ft, 32));
+    if (Qt > 0) {
+        TIM_TRY(make_tmap_3d16(c, &ap->tmQq, qkv + static_cast<size_t>(B) * Ft * ld, ld, Qt, B, ld * 2, ld * 2 * Qt, 128));
+        TIM_TRY(make_tmap_3d16(c, &ap->tmOq, out + static_cast<size_t>(B) * Ft * E, E, Qt, B, E * 2, E * 2 * Qt, 32));
+    } else {
+        ap->tmQq = ap->tmQf; ap->tmOq = ap->tmOf;
+    }
+    ap->qkv = qkv; ap->B = B; ap->Ft = Ft; ap->Qt = Qt; ap->H = c->H;
+    return TIM_OK;
+}
+
 inline Epilogue epi(void* out, int ldo, bool out_fp32, int act = ACT_NONE, const float* resid = nullptr, int ldr = 0) {
     Epilogue e;
     e.bias = nullptr; e.resid = resid; e.ldr = ldr; e.out = out; e.ldo = ldo; e.out_fp32 = out_fp32 ? 1 : 0; e.act = act;
@@ -510,11 +554,16 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
     const double attn_flops = 4.0 * E * (static_cast<double>(Ft) * Ft + static_cast<double>(Qt) * (Ft + 1)) * B;
     const void* xin = f32 ? static_cast<const void*>(x32) : static_cast<const void*>(x16);
     T* x16o = f32 ? nullptr : x16;
+    AttnUmmaParams attn_p;
+    bool attn_umma = false;
+    if constexpr (!f32) TIM_TRY(prepare_attention<T>(c, &attn_p, &attn_umma, qkv, att, B, Ft, Qt));
     for (int l = 0; l < c->L; ++l) {
         Layer& ly = c->layers[l];
         TIM_TRY(run_linear<T>(c, xin, E, ly.in_proj, plain_rows(Mi), epi(qkv, 3 * E, f32), s));
         if constexpr (f32) {
             LAUNCH_C(c, 1, attn_flops, s, launch_attention_simt(reinterpret_cast<const float*>(qkv), reinterpret_cast<float*>(att), B, Ft, Qt, c->H, c->hd, s));
+        } else if (attn_umma) {
+            LAUNCH_C(c, 1, attn_flops, s, launch_attention_umma<T>(attn_p, c->hd, c->num_sms, s));
         } else {
             LAUNCH_C(c, 1, attn_flops, s, launch_attention_mma<T>(qkv, att, B, Ft, Qt, c->H, c->hd, s));
         }
@@ -646,6 +695,7 @@ int tim_create(tim_ctx** out, const tim_config* cfg, int device) {
     c->vn_tokens = g.variant == TIM_RECOGNITION && g.include_verb_noun && c->vis_data;
     c->esize = g.compute_dtype == TIM_FP32 ? 4 : 2;
     if (const char* gv = std::getenv("TIM_B200_GEMM")) c->gemm_version = std::atoi(gv) == 1 ? 1 : 2;
+    if (const char* av = std::getenv("TIM_B200_ATTN")) c->attn_version = std::atoi(av) == 1 ? 1 : 2;
     if (c->d % 4) return bail(c->fail(TIM_ERR_INVALID, "d_model must be a multiple of 4"));
     if (c->vis_data && !g.n_action) return bail(c->fail(TIM_ERR_INVALID, "visual data modality needs n_action > 0"));
     if (c->aud_data && !g.n_audio) return bail(c->fail(TIM_ERR_INVALID, "audio data modality needs n_audio > 0"));
@@ -1004,6 +1054,50 @@ int tim_bench_linear(int dtype, const void* A16, const void* W16, const float* b
     return TIM_OK;
 }
 
+int tim_bench_attention(int dtype, const void* qkv16, void* out16, int B, int Ft, int Qt, int H, int hd, int version, int iters,
+                        float* ms_per_iter) {
+    TmpCtx t;
+    tim_ctx* c = &t.c;
+    auto fin = [&](int r) { g_create_error = c->err; return r; };
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
+        g_create_error = "tim_bench_attention: no sm_100 device";
+        return TIM_ERR_NO_DEVICE;
+    }
+    if (dtype != TIM_BF16 && dtype != TIM_FP16) return fin(c->fail(TIM_ERR_INVALID, "tim_bench_attention: 16-bit dtypes only"));
+    c->num_sms = prop.multiProcessorCount; c->device = dev; c->cfg.compute_dtype = dtype; c->esize = 2;
+    c->H = H; c->hd = hd; c->E = H * hd; c->attn_version = version == 1 ? 1 : 2;
+    int r = get_encode_fn(c);
+    if (r) return fin(r);
+    cudaStream_t s = nullptr;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaError_t e = cudaSuccess;
+    auto run = [&](auto tag) -> int {
+        using TT = decltype(tag);
+        AttnUmmaParams ap;
+        bool use_umma = false;
+        TIM_TRY(prepare_attention<TT>(c, &ap, &use_umma, static_cast<const TT*>(qkv16), static_cast<TT*>(out16), B, Ft, Qt));
+        for (int i = 0; i < iters + 2 && e == cudaSuccess; ++i) {
+            if (i == 2) cudaEventRecord(e0, s);
+            e = use_umma ? launch_attention_umma<TT>(ap, hd, c->num_sms, s)
+                         : launch_attention_mma<TT>(static_cast<const TT*>(qkv16), static_cast<TT*>(out16), B, Ft, Qt, H, hd, s);
+        }
+        return TIM_OK;
+    };
+    r = dtype == TIM_BF16 ? run(__nv_bfloat16{}) : run(__half{});
+    cudaEventRecord(e1, s);
+    cudaError_t es = cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (r) return fin(r);
+    if (e != cudaSuccess || es != cudaSuccess) return fin(c->fail(TIM_ERR_CUDA, "tim_bench_attention: %s", cudaGetErrorString(e != cudaSuccess ? e : es)));
+    if (ms_per_iter) *ms_per_iter = ms / (iters > 0 ? iters : 1);
+    return TIM_OK;
+}
+
 int tim_test_attention(int dtype, const float* qkv, float* out, int B, int Ft, int Qt, int H, int hd, void* stream) {
     TmpCtx t;
     tim_ctx* c = &t.c;
@@ -1016,13 +1110,33 @@ int tim_test_attention(int dtype, const float* qkv, float* out, int B, int Ft, i
         e = launch_attention_simt(scaled, out, B, Ft, Qt, H, hd, s);
     } else {
         void *q16 = nullptr, *o16 = nullptr;
+        int dev = 0;
+        cudaDeviceProp prop;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
+            g_create_error = "tim_test_attention: no sm_100 device";
+            return TIM_ERR_NO_DEVICE;
+        }
+        c->num_sms = prop.multiProcessorCount; c->device = dev; c->cfg.compute_dtype = dtype; c->esize = 2;
+        c->H = H; c->hd = hd; c->E = static_cast<int>(E);
+        if (const char* av = std::getenv("TIM_B200_ATTN")) c->attn_version = std::atoi(av) == 1 ? 1 : 2;
+        int rc = get_encode_fn(c);
+        if (rc) return fin(rc);
+        // same dispatch as the forward: tcgen05 kernel where the shape allows, warp-MMA kernel otherwise
+        auto test_attn = [&](auto* qp, auto* op) -> cudaError_t {
+            using TT = std::remove_pointer_t<decltype(qp)>;
+            AttnUmmaParams ap;
+            bool use_umma = false;
+            if (prepare_attention<TT>(c, &ap, &use_umma, qp, op, B, Ft, Qt) != TIM_OK) return cudaErrorInvalidValue;
+            if (use_umma) return launch_attention_umma<TT>(ap, hd, c->num_sms, s);
+            return launch_attention_mma<TT>(qp, op, B, Ft, Qt, H, hd, s);
+        };
         if (t.alloc(&q16, M * 3 * E * 2) != cudaSuccess || t.alloc(&o16, M * E * 2) != cudaSuccess) return fin(c->fail(TIM_ERR_NOMEM, "alloc"));
         if (dtype == TIM_BF16) {
             launch_cast<__nv_bfloat16>(scaled, static_cast<__nv_bfloat16*>(q16), M, 3 * E, 0, 1.0f, s);
-            e = launch_attention_mma<__nv_bfloat16>(static_cast<__nv_bfloat16*>(q16), static_cast<__nv_bfloat16*>(o16), B, Ft, Qt, H, hd, s);
+            e = test_attn(static_cast<__nv_bfloat16*>(q16), static_cast<__nv_bfloat16*>(o16));
         } else {
             launch_cast<__half>(scaled, static_cast<__half*>(q16), M, 3 * E, 0, 1.0f, s);
-            e = launch_attention_mma<__half>(static_cast<__half*>(q16), static_cast<__half*>(o16), B, Ft, Qt, H, hd, s);
+            e = test_attn(static_cast<__half*>(q16), static_cast<__half*>(o16));
         }
         if (e == cudaSuccess) {
             // widen back to fp32 with a plain device loop (cast kernels only go fp32 -> T): use cudaMemcpy2D-free host path

@@ -74,6 +74,27 @@ cudaError_t launch_linear_simt(const float* A, int lda, const float* W, int N, i
 // Every row attends to the Ft feature keys of its clip; query rows additionally to their own key.
 template <typename T>
 cudaError_t launch_attention_mma(const T* qkv, T* out, int B, int Ft, int Qt, int H, int hd, cudaStream_t s);
+// tcgen05 version (head_dim 64 / 128 / 192, Ft <= 128): S = Q K_f^T and O = P V_f on the tensor cores, TMEM accumulators,
+// TMA loads / stores through 3-D maps over (columns, rows of a clip, clips). All maps use 128-byte swizzle.
+struct AttnUmmaParams {
+    CUtensorMap tmKV;     // qkv feature rows  (3E, Ft, B), box (64, Fp, 1)   - K_f / V_f of one (clip, head)
+    CUtensorMap tmQf;     // qkv feature rows  (3E, Ft, B), box (64, 128, 1)  - Q tile of the feature rows
+    CUtensorMap tmQq;     // qkv query rows    (3E, Qt, B), box (64, 128, 1)
+    CUtensorMap tmOf;     // out feature rows  (E, Ft, B),  box (64, 32, 1)
+    CUtensorMap tmOq;     // out query rows    (E, Qt, B),  box (64, 32, 1)
+    const void* qkv;      // raw pointer for the own-key / own-value rows of query tokens
+    int B, Ft, Qt, H;
+    int Fp;               // Ft rounded up to 16 (MMA N of S, MMA K of P.V)
+    int tiles_q;          // 128-row query tiles per clip
+    int tpu, chunks;      // row tiles per work unit, work units per (clip, head)
+    int num_units;
+};
+bool attention_umma_supported(int Ft, int hd);
+size_t attention_umma_smem(int Ft, int hd);
+// fills Fp / tiles_q / tpu / chunks / num_units from B, Ft, Qt, H (the maps and qkv must already be set)
+template <typename T>
+cudaError_t launch_attention_umma(AttnUmmaParams p, int hd, int num_sms, cudaStream_t s);
+
 cudaError_t launch_attention_simt(const float* qkv, float* out, int B, int Ft, int Qt, int H, int hd, cudaStream_t s);
 size_t attention_simt_smem(int Ft, int hd);
 
