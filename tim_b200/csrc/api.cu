@@ -362,6 +362,7 @@ int run_linear(tim_ctx* c, const void* A, int lda, const LinearW& w, RowMap rm, 
     if (rm.G <= 0 || rm.R <= 0) return TIM_OK;
     if (!ep.bias) ep.bias = w.bias;
     if constexpr (std::is_same<T, float>::value) {
+        if (ep.rstats) return c->fail(TIM_ERR_INVALID, "linear: LayerNorm-on-read residual is a 16-bit path feature");
         ep.out_fp32 = 1;
         LAUNCH_C(c, 0, 2.0 * rm.G * rm.R * w.N * w.K, s,
                  launch_linear_simt(static_cast<const float*>(A), lda, static_cast<const float*>(w.w), w.N, w.K, rm, ep, s));
@@ -383,7 +384,9 @@ int run_linear(tim_ctx* c, const void* A, int lda, const LinearW& w, RowMap rm, 
             if (ep.resid)
                 TIM_TRY(make_tmap_2d(c, &q.tmRes, ep.resid, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, w.N, M, static_cast<long long>(ep.ldr) * 4, 32, 32));
             q.bias = ep.bias; q.M = M; q.N = w.N; q.K = w.K;
-            const int mode = ep.out_fp32 ? (ep.resid ? 2 : 1) : 0;
+            q.rstats = ep.rstats; q.rgamma = ep.rgamma; q.rbeta = ep.rbeta;
+            const int mode = ep.out_fp32 ? (ep.resid ? (ep.rstats ? 3 : 2) : 1) : 0;
+            if (mode == 3 && ep.act != ACT_NONE) return c->fail(TIM_ERR_INVALID, "linear: LayerNorm-on-read residual supports no activation");
             LAUNCH_C(c, 0, 2.0 * M * w.N * w.K, s, launch_linear_umma2<T>(q, mode, ep.act, c->num_sms, s));
             return TIM_OK;
         }
@@ -422,6 +425,7 @@ int prepare_attention(tim_ctx* c, AttnUmmaParams* ap, bool* use_umma, const T* q
 inline Epilogue epi(void* out, int ldo, bool out_fp32, int act = ACT_NONE, const float* resid = nullptr, int ldr = 0) {
     Epilogue e;
     e.bias = nullptr; e.resid = resid; e.ldr = ldr; e.out = out; e.ldo = ldo; e.out_fp32 = out_fp32 ? 1 : 0; e.act = act;
+    e.rstats = nullptr; e.rgamma = nullptr; e.rbeta = nullptr;
     return e;
 }
 
@@ -519,6 +523,8 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
     const size_t regrows = static_cast<size_t>(B) * (qp.Qv > qp.Qa ? qp.Qv : qp.Qa);
     a.take(&r1, g.variant == TIM_DETECTION ? regrows * (E / 2) * sizeof(T) : 0);
     a.take(&r2, g.variant == TIM_DETECTION ? regrows * (E / 2) * sizeof(T) : 0);
+    float2* stats;
+    a.take(&stats, f32 ? 0 : M * sizeof(float2));
     if (ws_need) { *ws_need = a.off; return TIM_OK; }
 
     // ---- embedders: Linear -> GELU (epilogue) -> pre-LN rows; LN happens while assembling tokens ----
@@ -567,11 +573,36 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
         } else {
             LAUNCH_C(c, 1, attn_flops, s, launch_attention_mma<T>(qkv, att, B, Ft, Qt, c->H, c->hd, s));
         }
-        TIM_TRY(run_linear<T>(c, att, E, ly.out_proj, plain_rows(Mi), epi(z, E, true, ACT_NONE, x32, E), s));
-        LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(z, E, ly.n1g, ly.n1b, x32, E, x16o, E, Mi, E, s));
-        TIM_TRY(run_linear<T>(c, xin, E, ly.lin1, plain_rows(Mi), epi(hid, FF, f32, ACT_GELU), s));
-        TIM_TRY(run_linear<T>(c, hid, FF, ly.lin2, plain_rows(Mi), epi(z, E, true, ACT_NONE, x32, E), s));
-        LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(z, E, ly.n2g, ly.n2b, x32, E, x16o, E, Mi, E, s));
+        if constexpr (f32) {
+            TIM_TRY(run_linear<T>(c, att, E, ly.out_proj, plain_rows(Mi), epi(z, E, true, ACT_NONE, x32, E), s));
+            LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(z, E, ly.n1g, ly.n1b, x32, E, x16o, E, Mi, E, s));
+            TIM_TRY(run_linear<T>(c, xin, E, ly.lin1, plain_rows(Mi), epi(hid, FF, f32, ACT_GELU), s));
+            TIM_TRY(run_linear<T>(c, hid, FF, ly.lin2, plain_rows(Mi), epi(z, E, true, ACT_NONE, x32, E), s));
+            LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(z, E, ly.n2g, ly.n2b, x32, E, x16o, E, Mi, E, s));
+        } else {
+            // 16-bit path: the fp32 LayerNorm output is never materialised. x32 holds the tokens (layer 0) or the
+            // pre-norm2 rows z2 of the previous layer, z the pre-norm1 rows z1; LayerNorm writes only the 16-bit operand
+            // copy + (mean, rstd) per row, and the GEMM that needs LN(.) as its residual normalises the rows on read.
+            Epilogue e1 = epi(z, E, true, ACT_NONE, x32, E);
+            if (l > 0) { e1.rstats = stats; e1.rgamma = c->layers[l - 1].n2g; e1.rbeta = c->layers[l - 1].n2b; }
+            TIM_TRY(run_linear<T>(c, att, E, ly.out_proj, plain_rows(Mi), e1, s));
+            LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(z, E, ly.n1g, ly.n1b, nullptr, 0, x16o, E, Mi, E, s, stats));
+            TIM_TRY(run_linear<T>(c, xin, E, ly.lin1, plain_rows(Mi), epi(hid, FF, f32, ACT_GELU), s));
+            Epilogue e2 = epi(x32, E, true, ACT_NONE, z, E);
+            e2.rstats = stats; e2.rgamma = ly.n1g; e2.rbeta = ly.n1b;
+            TIM_TRY(run_linear<T>(c, hid, FF, ly.lin2, plain_rows(Mi), e2, s));
+            LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(x32, E, ly.n2g, ly.n2b, nullptr, 0, x16o, E, Mi, E, s, stats));
+        }
+    }
+    // fp32 features returned to the caller (tim.py:172, x[:, :num_feats]): LayerNorm of the last layer's z2 feature rows
+    const float* feats_src = x32;
+    bool feats_done = false;
+    if constexpr (!f32) {
+        if (c->L > 0 && o->feats && Mf) {
+            Layer& ly = c->layers[c->L - 1];
+            LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(x32, E, ly.n2g, ly.n2b, o->feats, E, static_cast<T*>(nullptr), 0, static_cast<int>(Mf), E, s));
+            feats_done = true;
+        }
     }
 
     // ---- heads read slices of the query stream ----
@@ -609,7 +640,7 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
             TIM_TRY(reg(c->reg_a, qp.off_audio, qp.Qa, o->reg_audio));
         }
     }
-    if (o->feats && Mf) CU_OK(c, cudaMemcpyAsync(o->feats, x32, Mf * E * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (o->feats && Mf && !feats_done) CU_OK(c, cudaMemcpyAsync(o->feats, feats_src, Mf * E * sizeof(float), cudaMemcpyDeviceToDevice, s));
     return TIM_OK;
 }
 

@@ -62,13 +62,14 @@ template <typename T>
 __global__ void __launch_bounds__(ROWS_PER_CTA * 32) layernorm_kernel(const float* __restrict__ in, int ldi,
                                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                       float* __restrict__ out32, int ld32, T* __restrict__ out16, int ld16,
-                                                                      int M, int n) {
+                                                                      int M, int n, float2* __restrict__ stats) {
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
     if (row >= M) return;
     const float* x = in + static_cast<size_t>(row) * ldi;
     float mean, rstd;
     row_stats(x, n, lane, mean, rstd);
+    if (stats && lane == 0) stats[row] = make_float2(mean, rstd);
     for (int c = lane * 4; c < n; c += 128) {
         const float4 v = *reinterpret_cast<const float4*>(x + c);
         const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
@@ -77,6 +78,50 @@ __global__ void __launch_bounds__(ROWS_PER_CTA * 32) layernorm_kernel(const floa
         const float y2 = (v.z - mean) * rstd * g.z + b.z, y3 = (v.w - mean) * rstd * g.w + b.w;
         if (out32) store4<float>(out32 + static_cast<size_t>(row) * ld32 + c, y0, y1, y2, y3);
         if (out16) store4<T>(out16 + static_cast<size_t>(row) * ld16 + c, y0, y1, y2, y3);
+    }
+}
+
+// Same, for rows of at most 128 * V floats: the row is read from memory ONCE and stays in registers for the two-pass
+// statistics and the normalisation (the generic kernel above re-reads it twice through L2, which is what bounds it).
+template <typename T, int V>
+__global__ void __launch_bounds__(ROWS_PER_CTA * 32) layernorm_reg_kernel(const float* __restrict__ in, int ldi,
+                                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                          float* __restrict__ out32, int ld32, T* __restrict__ out16, int ld16,
+                                                                          int M, int n, float2* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const float* x = in + static_cast<size_t>(row) * ldi;
+    float4 v[V];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const int c = lane * 4 + i * 128;
+        v[i] = c < n ? *reinterpret_cast<const float4*>(x + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) / static_cast<float>(n);
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        if (lane * 4 + i * 128 < n) {
+            const float a = v[i].x - mean, b2 = v[i].y - mean, c2 = v[i].z - mean, d2 = v[i].w - mean;
+            q += (a * a + b2 * b2) + (c2 * c2 + d2 * d2);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(n) + 1e-5f);
+    if (stats && lane == 0) stats[row] = make_float2(mean, rstd);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const int c = lane * 4 + i * 128;
+        if (c < n) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+            const float y0 = (v[i].x - mean) * rstd * g.x + b.x, y1 = (v[i].y - mean) * rstd * g.y + b.y;
+            const float y2 = (v[i].z - mean) * rstd * g.z + b.z, y3 = (v[i].w - mean) * rstd * g.w + b.w;
+            if (out32) store4<float>(out32 + static_cast<size_t>(row) * ld32 + c, y0, y1, y2, y3);
+            if (out16) store4<T>(out16 + static_cast<size_t>(row) * ld16 + c, y0, y1, y2, y3);
+        }
     }
 }
 
@@ -197,15 +242,19 @@ template cudaError_t launch_time_l1<__nv_bfloat16>(const float*, const float*, c
 
 template <typename T>
 cudaError_t launch_layernorm(const float* in, int ldi, const float* gamma, const float* beta, float* out32, int ld32, T* out16,
-                             int ld16, int M, int n, cudaStream_t s) {
+                             int ld16, int M, int n, cudaStream_t s, float2* stats) {
     if (M <= 0) return cudaSuccess;
     if ((n & 3) || (ldi & 3) || (out32 && (ld32 & 3)) || (out16 && (ld16 & 3))) return cudaErrorInvalidValue;
-    layernorm_kernel<T><<<(M + ROWS_PER_CTA - 1) / ROWS_PER_CTA, ROWS_PER_CTA * 32, 0, s>>>(in, ldi, gamma, beta, out32, ld32, out16, ld16, M, n);
+    const int grid = (M + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
+    if (n <= 512) layernorm_reg_kernel<T, 4><<<grid, ROWS_PER_CTA * 32, 0, s>>>(in, ldi, gamma, beta, out32, ld32, out16, ld16, M, n, stats);
+    else if (n <= 1024) layernorm_reg_kernel<T, 8><<<grid, ROWS_PER_CTA * 32, 0, s>>>(in, ldi, gamma, beta, out32, ld32, out16, ld16, M, n, stats);
+    else if (n <= 2048) layernorm_reg_kernel<T, 16><<<grid, ROWS_PER_CTA * 32, 0, s>>>(in, ldi, gamma, beta, out32, ld32, out16, ld16, M, n, stats);
+    else layernorm_kernel<T><<<grid, ROWS_PER_CTA * 32, 0, s>>>(in, ldi, gamma, beta, out32, ld32, out16, ld16, M, n, stats);
     return cudaGetLastError();
 }
-template cudaError_t launch_layernorm<float>(const float*, int, const float*, const float*, float*, int, float*, int, int, int, cudaStream_t);
-template cudaError_t launch_layernorm<__half>(const float*, int, const float*, const float*, float*, int, __half*, int, int, int, cudaStream_t);
-template cudaError_t launch_layernorm<__nv_bfloat16>(const float*, int, const float*, const float*, float*, int, __nv_bfloat16*, int, int, int, cudaStream_t);
+template cudaError_t launch_layernorm<float>(const float*, int, const float*, const float*, float*, int, float*, int, int, int, cudaStream_t, float2*);
+template cudaError_t launch_layernorm<__half>(const float*, int, const float*, const float*, float*, int, __half*, int, int, int, cudaStream_t, float2*);
+template cudaError_t launch_layernorm<__nv_bfloat16>(const float*, int, const float*, const float*, float*, int, __nv_bfloat16*, int, int, int, cudaStream_t, float2*);
 
 template <typename T>
 cudaError_t launch_assemble(const AssembleParams& p, cudaStream_t s) {

@@ -176,7 +176,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_umma_kernel(const __gri
                 }
                 if (ep.resid) {
                     const float* rp = ep.resid + orow * ep.ldr + n;
-                    if (full && (ep.ldr & 3) == 0) {
+                    if (ep.rstats) {                         // LayerNorm-on-read of the residual row
+                        const float2 st = ep.rstats[orow];
+                        const float nmr = -st.x * st.y;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (n + j < p.N) f[j] += fmaf(fmaf(rp[j], st.y, nmr), __ldg(ep.rgamma + n + j), __ldg(ep.rbeta + n + j));
+                    } else if (full && (ep.ldr & 3) == 0) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4) {
                             const float4 r4 = *reinterpret_cast<const float4*>(rp + j);

@@ -48,7 +48,8 @@ template <int ACT> __device__ __forceinline__ float apply_act(float v) {
     return v;
 }
 
-// MODE 0: 16-bit output, 1: fp32 output, 2: fp32 output + fp32 residual (added after the activation)
+// MODE 0: 16-bit output, 1: fp32 output, 2: fp32 output + fp32 residual (added after the activation),
+// 3: as 2 with LayerNorm applied to the residual rows on the fly (row statistics in p.rstats, affine in p.rgamma / p.rbeta)
 template <typename T, int MODE, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_umma2_kernel(const __grid_constant__ Umma2Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -78,7 +79,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
         tma_prefetch_desc(&p.tmOut);
-        if (MODE == 2) tma_prefetch_desc(&p.tmRes);
+        if (MODE >= 2) tma_prefetch_desc(&p.tmRes);
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -165,7 +166,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
             for (int cb = half; cb < BLOCKS; cb += 2) my_blocks += (n0 + cb * COLS_PER_BLOCK < p.N) ? 1 : 0;
             if (!rows_live) my_blocks = 0;
 
-            if (MODE == 2 && my_blocks > 0) {             // prefetch the residual of the first block
+            float ln_rstd = 1.0f, ln_nmr = 0.0f;          // MODE 3: residual row r -> (r * rstd - mean * rstd) * gamma + beta
+            if (MODE == 3 && row0 + lane < p.M) {
+                const float2 st = p.rstats[row0 + lane];
+                ln_rstd = st.y; ln_nmr = -st.x * st.y;
+            }
+            if (MODE >= 2 && my_blocks > 0) {             // prefetch the residual of the first block
                 const uint32_t b = nbuf & 1u;
                 if (lane == 0) {
                     tma_store_wait_read<0>();             // that buffer's previous store has drained
@@ -183,7 +189,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
                 const int col0 = n0 + cb * COLS_PER_BLOCK;
                 const uint32_t b = nbuf & 1u;
                 const uint32_t buf = buf0 + b * EPI_BUF;
-                if (MODE == 2) {
+                if (MODE >= 2) {
                     if (i + 1 < my_blocks) {              // prefetch the next block's residual into the other buffer
                         if (lane == 0) {
                             tma_store_wait_read<0>();
@@ -228,10 +234,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
                         for (int c = 0; c < 8; ++c) {
                             const uint32_t addr = buf + my_row + ((static_cast<uint32_t>(c) ^ swz) << 4);
                             float4 o = make_float4(f[4 * c], f[4 * c + 1], f[4 * c + 2], f[4 * c + 3]);
-                            if (MODE == 2) {
+                            if (MODE >= 2) {
                                 float4 r;
                                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                              : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+                                if (MODE == 3) {
+                                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.rgamma + n + 4 * c));
+                                    const float4 e4 = __ldg(reinterpret_cast<const float4*>(p.rbeta + n + 4 * c));
+                                    r.x = fmaf(fmaf(r.x, ln_rstd, ln_nmr), g4.x, e4.x); r.y = fmaf(fmaf(r.y, ln_rstd, ln_nmr), g4.y, e4.y);
+                                    r.z = fmaf(fmaf(r.z, ln_rstd, ln_nmr), g4.z, e4.z); r.w = fmaf(fmaf(r.w, ln_rstd, ln_nmr), g4.w, e4.w);
+                                }
                                 o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
                             }
                             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
@@ -294,6 +306,7 @@ cudaError_t launch_linear_umma2(Umma2Params p, int mode, int act, int num_sms, c
     TIM_U2(0, ACT_NONE) TIM_U2(0, ACT_RELU) TIM_U2(0, ACT_GELU)
     TIM_U2(1, ACT_NONE) TIM_U2(1, ACT_RELU) TIM_U2(1, ACT_GELU)
     TIM_U2(2, ACT_NONE) TIM_U2(2, ACT_RELU) TIM_U2(2, ACT_GELU)
+    TIM_U2(3, ACT_NONE)
 #undef TIM_U2
     return cudaErrorInvalidValue;
 }

@@ -30,6 +30,12 @@ struct Epilogue {
     const float* bias;    // [N] or nullptr
     const float* resid;   // fp32 [rows, ldr] or nullptr (added after the activation)
     int ldr;
+    // optional "LayerNorm on read" of the residual (16-bit tcgen05 kernels only): when rstats != nullptr the residual
+    // buffer holds the PRE-LayerNorm rows z and the value added is (z - mean) * rstd * rgamma[n] + rbeta[n], with
+    // (mean, rstd) of the row from rstats[row]. Saves materialising the fp32 LayerNorm output (transformers.py:105,109).
+    const float2* rstats;
+    const float* rgamma;
+    const float* rbeta;
     void* out;            // [rows, ldo]
     int ldo;
     int out_fp32;         // 1: float*, 0: T*
@@ -54,13 +60,17 @@ struct Umma2Params {
     CUtensorMap tmA;      // 2-D (K, M), box (64, 128), SWIZZLE_128B
     CUtensorMap tmB;      // 2-D (K, N), box (64, 128), SWIZZLE_128B
     CUtensorMap tmOut;    // 2-D (N, M): 16-bit box (64, 32) / fp32 box (32, 32), SWIZZLE_128B
-    CUtensorMap tmRes;    // fp32 (N, M), box (32, 32), SWIZZLE_128B (mode 2 only)
+    CUtensorMap tmRes;    // fp32 (N, M), box (32, 32), SWIZZLE_128B (modes 2 / 3 only)
     const float* bias;    // [N]
+    const float2* rstats; // mode 3: per-row (mean, rstd) of the residual rows; rgamma / rbeta [N]
+    const float* rgamma;
+    const float* rbeta;
     int M, N, K;
     int tiles_m, tiles_n;
 };
 bool umma2_supported(int M, int N, int K);
-// mode 0: out = T(act(acc + bias)); 1: out = float(act(acc + bias)); 2: out = float(act(acc + bias) + resid)
+// mode 0: out = T(act(acc + bias)); 1: out = float(act(acc + bias)); 2: out = float(act(acc + bias) + resid);
+// mode 3: out = float(act(acc + bias) + LayerNorm(resid)) with the row statistics given (Epilogue::rstats)
 template <typename T>
 cudaError_t launch_linear_umma2(Umma2Params p, int mode, int act, int num_sms, cudaStream_t s);
 
@@ -104,9 +114,10 @@ template <typename TO>
 cudaError_t launch_time_l1(const float* times, const float* W, const float* b, TO* out, int M, int d, cudaStream_t s);
 
 // LayerNorm over rows of `in` [M, n] (row stride ldi); writes fp32 (out32, stride ld32) and/or T (out16, stride ld16)
+// and/or the row statistics (mean, rstd) to stats[M]
 template <typename T>
 cudaError_t launch_layernorm(const float* in, int ldi, const float* gamma, const float* beta, float* out32, int ld32,
-                             T* out16, int ld16, int M, int n, cudaStream_t s);
+                             T* out16, int ld16, int M, int n, cudaStream_t s, float2* stats = nullptr);
 
 // Token assembly (encodings.py forward): see elementwise.cu for the row plan
 struct TokenGroup {          // a run of `count` query tokens per clip
