@@ -86,6 +86,19 @@ def test_host_path_equals_device_path(lib, name):
             assert np.array_equal(v, a[k]), k
 
 
+def test_host_path_tapered_chunks(lib):
+    """B >= 4 chunks: the host path tapers the first / last chunks (cpc/4, cpc/2, cpc ..., cpc/2, cpc/4) and leaves a ragged
+    middle chunk; every clip must still land in its own output rows, bit-identical to the device path."""
+    cfg, Qv, Qa = named_config("cfg1")
+    sd = synth_state_dict(cfg, 0, "trained")
+    inp = synth_inputs(cfg, 45, Qv, Qa, 99)
+    a = engine_run(cfg, sd, inp, Qv, Qa, "fp16")
+    b = engine_run(cfg, sd, inp, Qv, Qa, "fp16", host=True, chunks=8)
+    for k, v in b.items():
+        if v is not None:
+            assert np.array_equal(v, a[k]), k
+
+
 @pytest.mark.parametrize("dt", ["fp32", "fp16", "bf16"])
 @pytest.mark.parametrize("name,B", [("cfg2", 3), ("cfg3", 2), ("cfg4", 1)])
 def test_named_configs_vs_oracle(lib, name, B, dt):
@@ -179,7 +192,11 @@ def test_linear_kernel(lib, M, N, K, dt):
 
 @pytest.mark.parametrize("dt", ["fp32", "fp16", "bf16"])
 @pytest.mark.parametrize("B,Ft,Qt,H,hd", [(2, 12, 7, 2, 16), (3, 100, 100, 2, 128), (2, 128, 200, 1, 192), (2, 100, 0, 2, 64),
-                                           (1, 50, 300, 2, 32), (1, 1, 5, 1, 16)])
+                                           (1, 50, 300, 2, 32), (1, 1, 5, 1, 16),
+                                           # tcgen05 kernel: several work units per (clip, head), ragged last tiles, Ft = 1 / 16 / 128,
+                                           # more (clip, head) items than SMs
+                                           (1, 100, 1000, 2, 128), (5, 17, 130, 2, 64), (2, 1, 5, 1, 64), (2, 128, 129, 2, 128),
+                                           (3, 16, 128, 1, 192), (40, 100, 100, 8, 128)])
 def test_attention_kernel(lib, B, Ft, Qt, H, hd, dt):
     """mask-aware attention vs a dense masked softmax(QK^T)V in fp64 (the reference's formulation)."""
     g = torch.Generator().manual_seed(Ft * 3 + Qt)

@@ -881,7 +881,23 @@ int tim_forward_host(tim_ctx* c, const float* vis, const float* aud, const float
     TIM_TRY(encoder_ws(c, cpc, T_, Qv, Qa, &need_e));
     TIM_TRY(ensure_ws(c, need_t > need_e ? need_t : need_e));
 
-    const int nchunks = (B + cpc - 1) / cpc;
+    // chunk schedule: full chunks of cpc clips with tapered ends (cpc/4, cpc/2 ... cpc/2, cpc/4) so that the un-overlapped
+    // H2D of the first chunk and D2H of the last chunk are short
+    std::vector<int> chunk_b0, chunk_nb;
+    {
+        std::vector<int> head, tail;
+        int left = B;
+        if (B >= 4 * cpc && cpc >= 8) {
+            head = {cpc / 4, cpc / 2};
+            tail = {cpc / 2, cpc / 4};
+            left -= cpc / 4 * 2 + cpc / 2 * 2;
+        }
+        int b0 = 0;
+        for (int n : head) { chunk_b0.push_back(b0); chunk_nb.push_back(n); b0 += n; }
+        while (left > 0) { const int n = left < cpc ? left : cpc; chunk_b0.push_back(b0); chunk_nb.push_back(n); b0 += n; left -= n; }
+        for (int n : tail) { chunk_b0.push_back(b0); chunk_nb.push_back(n); b0 += n; }
+    }
+    const int nchunks = static_cast<int>(chunk_nb.size());
     std::vector<cudaEvent_t> ev_in(nchunks), ev_comp(nchunks), ev_out(nchunks);
     for (int i = 0; i < nchunks; ++i) {
         CU_OK(c, cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
@@ -901,7 +917,8 @@ int tim_forward_host(tim_ctx* c, const float* vis, const float* aud, const float
         return cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToHost, c->s_d2h);
     };
     for (int i = 0; i < nchunks && rc == TIM_OK; ++i) {
-        const int b0 = i * cpc, nb = (B - b0 < cpc) ? B - b0 : cpc;
+        const size_t b0 = static_cast<size_t>(chunk_b0[i]);
+        const int nb = chunk_nb[i];
         Set& s = st[i & 1];
         // inputs of chunk i may overwrite set (i&1) once chunk i-2 has been computed
         if (i >= 2) CU_OK(c, cudaStreamWaitEvent(c->s_h2d, ev_comp[i - 2], 0));

@@ -22,6 +22,9 @@
 //   warp 1    : MMA issuer; software-pipelined so that S(t+1) is issued before O(t) (two TMEM / smem stages, hd <= 128)
 //   warps 2-5 : softmax (TMEM lane quarter = warp % 4)
 //   warps 6-9 : epilogue (same quarters); softmax of tile t+1 overlaps the epilogue of tile t
+#include <cstdio>
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -31,6 +34,7 @@ namespace {
 constexpr int AU_THREADS = 320;
 constexpr int AU_BM = 128;
 constexpr int AU_P_BYTES = 32768;        // P tile (128 rows x up to 128 keys); reused as the epilogue's v_self scratch
+constexpr int AU_PF = 1;                 // tiles prefetched into L2 ahead of the smem loads (measured: 1 > 2 > 0 > 4)
 constexpr int AU_MIN_SMEM = 120 * 1024;  // keeps it at one CTA per SM (each CTA allocates all 512 TMEM columns)
 
 template <int HD> struct AUCfg {
@@ -112,6 +116,41 @@ __global__ void __launch_bounds__(AU_THREADS, 1) attention_umma_kernel(const __g
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
+            // L2 prefetch iterator running AU_PF tiles ahead of the loads: with two smem stages the loads in flight
+            // (<= 2 x 64 KB per SM) cannot cover the HBM latency-bandwidth product; the prefetches can.
+            int pf_u = blockIdx.x, pf_t = 0;
+            UnitInfo pf_ui = {0, 0, 0, 0};
+            bool pf_valid = pf_u < p.num_units;
+            if (pf_valid) { pf_ui = decode_unit(p, pf_u); pf_t = pf_ui.t_lo; }
+            auto prefetch_next = [&]() {
+                if (!pf_valid) return;
+                const int h0 = pf_ui.h * HD;
+                const bool tiles_too = p.pf_mode >= 2;
+                if (pf_t == pf_ui.t_lo) {
+#pragma unroll
+                    for (int j = 0; j < KBOX; ++j) {
+                        tma_prefetch_l2_3d(&p.tmKV, E + h0 + 64 * j, 0, pf_ui.b);
+                        tma_prefetch_l2_3d(&p.tmKV, 2 * E + h0 + 64 * j, 0, pf_ui.b);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < KBOX; ++j) {
+                    if (!tiles_too) break;
+                    if (pf_t == 0) {
+                        tma_prefetch_l2_3d(&p.tmQf, h0 + 64 * j, 0, pf_ui.b);
+                    } else {
+                        tma_prefetch_l2_3d(&p.tmQq, h0 + 64 * j, (pf_t - 1) * AU_BM, pf_ui.b);
+                        tma_prefetch_l2_3d(&p.tmQq, E + h0 + 64 * j, (pf_t - 1) * AU_BM, pf_ui.b);
+                        tma_prefetch_l2_3d(&p.tmQq, 2 * E + h0 + 64 * j, (pf_t - 1) * AU_BM, pf_ui.b);    // own-value rows (epilogue)
+                    }
+                }
+                if (++pf_t >= pf_ui.t_hi) {
+                    pf_u += gridDim.x;
+                    pf_valid = pf_u < p.num_units;
+                    if (pf_valid) { pf_ui = decode_unit(p, pf_u); pf_t = pf_ui.t_lo; }
+                }
+            };
+            if (p.pf_mode >= 1) for (int i = 0; i < p.pf_tiles; ++i) prefetch_next();
             uint32_t g = 0, un = 0;
             for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++un) {
                 const UnitInfo ui = decode_unit(p, u);
@@ -122,6 +161,7 @@ __global__ void __launch_bounds__(AU_THREADS, 1) attention_umma_kernel(const __g
                 for (int t = ui.t_lo; t < ui.t_hi; ++t, ++g) {
                     const int st = g % NST;
                     const uint32_t ph = (g / NST) & 1u;
+                    if (p.pf_mode >= 1) prefetch_next();
                     mbar_wait(q_empty(st), ph ^ 1u);
                     mbar_arrive_expect_tx(q_full(st), t == 0 ? C::Q_BYTES : 2 * C::Q_BYTES);
 #pragma unroll
@@ -445,6 +485,14 @@ cudaError_t launch_attention_umma(AttnUmmaParams p, int hd, int num_sms, cudaStr
     const long long units = items * p.chunks;
     if (units > 0x7fffffffLL) return cudaErrorInvalidValue;
     p.num_units = static_cast<int>(units);
+    // L2 prefetch policy (TIM_B200_ATTN_PF = "<mode>,<tiles>"): mode 0 off, 1 K_f / V_f of upcoming units only, 2 everything
+    p.pf_mode = 2; p.pf_tiles = AU_PF;
+    if (const char* e = std::getenv("TIM_B200_ATTN_PF")) {
+        int m = 0, t = AU_PF;
+        const int n = std::sscanf(e, "%d,%d", &m, &t);
+        if (n >= 1) p.pf_mode = m;
+        if (n >= 2 && t >= 0 && t <= 16) p.pf_tiles = t;
+    }
     switch (hd) {
         case 64: return launch_hd<T, 64>(p, num_sms, s);
         case 128: return launch_hd<T, 128>(p, num_sms, s);

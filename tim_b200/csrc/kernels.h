@@ -98,6 +98,7 @@ struct AttnUmmaParams {
     int tiles_q;          // 128-row query tiles per clip
     int tpu, chunks;      // row tiles per work unit, work units per (clip, head)
     int num_units;
+    int pf_mode, pf_tiles; // L2 prefetch policy of the TMA producer (see launch_attention_umma)
 };
 bool attention_umma_supported(int Ft, int hd);
 size_t attention_umma_smem(int Ft, int hd);
