@@ -94,6 +94,9 @@ struct tim_ctx {
     // workspace arena (grow-only)
     uint8_t* ws = nullptr;
     size_t ws_bytes = 0;
+    uint32_t* ln_flags = nullptr;   // per-256-row-block counters of the LayerNorm-prologue GEMM (grow-only)
+    size_t ln_flags_n = 0;
+    int ln_prologue = 0;            // 1: LayerNorm as a prologue of the consuming GEMM (TIM_B200_LNP=1; measured slower)
     // staging for tim_forward_host
     uint8_t* io = nullptr;
     size_t io_bytes = 0;
@@ -356,11 +359,35 @@ struct Arena {
 // ------------------------------------------------------------------------------------------------------------------
 // one linear layer through the selected compute path
 // ------------------------------------------------------------------------------------------------------------------
+// LayerNorm feeding a linear layer: A (16-bit, [rows, K]) = LayerNorm(in) (+ row statistics). Where the CTA-pair kernel
+// applies it runs as that kernel's prologue (mode 4); otherwise as a LayerNorm kernel of its own before the GEMM.
+struct LnPrologue {
+    const float* in;      // fp32 [rows, K]
+    const float* gamma;
+    const float* beta;
+    float2* stats;        // [rows]
+};
+
 template <typename T>
-int run_linear(tim_ctx* c, const void* A, int lda, const LinearW& w, RowMap rm, Epilogue ep, cudaStream_t s) {
+int run_linear(tim_ctx* c, const void* A, int lda, const LinearW& w, RowMap rm, Epilogue ep, cudaStream_t s,
+               const LnPrologue* ln = nullptr) {
     if (lda != w.K) return c->fail(TIM_ERR_INVALID, "linear: lda %d != K %d", lda, w.K);
     if (rm.G <= 0 || rm.R <= 0) return TIM_OK;
     if (!ep.bias) ep.bias = w.bias;
+    bool ln_fused = false;
+    if (ln) {
+        if constexpr (std::is_same<T, float>::value) {
+            return c->fail(TIM_ERR_INVALID, "linear: LayerNorm prologue is a 16-bit path feature");
+        } else {
+            const bool plain0 = rm.G == 1 && rm.box_g == 1 && rm.a_row_off == 0 && rm.out_row_off == 0;
+            ln_fused = c->ln_prologue && c->gemm_version >= 2 && plain0 && w.has_tmB2 && umma2_supported(rm.R, w.N, w.K) &&
+                       umma2_ln_supported(w.K) && !ep.out_fp32 && !ep.resid && (ep.act == ACT_NONE || ep.act == ACT_GELU) &&
+                       (static_cast<size_t>(ep.ldo) * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0;
+            if (!ln_fused)
+                LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(ln->in, w.K, ln->gamma, ln->beta, nullptr, 0, static_cast<T*>(const_cast<void*>(A)), w.K,
+                                                             rm.R, w.K, s, ln->stats));
+        }
+    }
     if constexpr (std::is_same<T, float>::value) {
         if (ep.rstats) return c->fail(TIM_ERR_INVALID, "linear: LayerNorm-on-read residual is a 16-bit path feature");
         ep.out_fp32 = 1;
@@ -385,7 +412,20 @@ int run_linear(tim_ctx* c, const void* A, int lda, const LinearW& w, RowMap rm, 
                 TIM_TRY(make_tmap_2d(c, &q.tmRes, ep.resid, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, w.N, M, static_cast<long long>(ep.ldr) * 4, 32, 32));
             q.bias = ep.bias; q.M = M; q.N = w.N; q.K = w.K;
             q.rstats = ep.rstats; q.rgamma = ep.rgamma; q.rbeta = ep.rbeta;
-            const int mode = ep.out_fp32 ? (ep.resid ? (ep.rstats ? 3 : 2) : 1) : 0;
+            int mode = ep.out_fp32 ? (ep.resid ? (ep.rstats ? 3 : 2) : 1) : 0;
+            if (ln_fused) {
+                const size_t blocks = (static_cast<size_t>(M) + 255) / 256 + 1;
+                if (blocks > c->ln_flags_n) {
+                    if (c->ln_flags) { cudaDeviceSynchronize(); cudaFree(c->ln_flags); c->ln_flags = nullptr; c->ln_flags_n = 0; }
+                    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->ln_flags), blocks * sizeof(uint32_t));
+                    if (e != cudaSuccess) return c->fail(TIM_ERR_NOMEM, "LayerNorm flag cudaMalloc failed: %s", cudaGetErrorString(e));
+                    c->ln_flags_n = blocks;
+                }
+                q.ln_in = ln->in; q.ln_gamma = ln->gamma; q.ln_beta = ln->beta; q.ln_out = const_cast<void*>(A);
+                q.ln_stats = ln->stats; q.ln_flags = c->ln_flags;
+                mode = 4;
+                c->launches++;      // the counter memset in front of the kernel
+            }
             if (mode == 3 && ep.act != ACT_NONE) return c->fail(TIM_ERR_INVALID, "linear: LayerNorm-on-read residual supports no activation");
             LAUNCH_C(c, 0, 2.0 * M * w.N * w.K, s, launch_linear_umma2<T>(q, mode, ep.act, c->num_sms, s));
             return TIM_OK;
@@ -565,7 +605,16 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
     if constexpr (!f32) TIM_TRY(prepare_attention<T>(c, &attn_p, &attn_umma, qkv, att, B, Ft, Qt));
     for (int l = 0; l < c->L; ++l) {
         Layer& ly = c->layers[l];
-        TIM_TRY(run_linear<T>(c, xin, E, ly.in_proj, plain_rows(Mi), epi(qkv, 3 * E, f32), s));
+        if constexpr (f32) {
+            TIM_TRY(run_linear<T>(c, xin, E, ly.in_proj, plain_rows(Mi), epi(qkv, 3 * E, f32), s));
+        } else {
+            // 16-bit path: the fp32 LayerNorm output is never materialised. x32 holds the tokens (layer 0) or the
+            // pre-norm2 rows z2 of the previous layer, z the pre-norm1 rows z1. LayerNorm writes only the 16-bit operand
+            // copy + (mean, rstd) per row - as the prologue of the GEMM that consumes it - and the GEMM that needs LN(.) as
+            // its residual normalises the rows on read.
+            LnPrologue lp{x32, l > 0 ? c->layers[l - 1].n2g : nullptr, l > 0 ? c->layers[l - 1].n2b : nullptr, stats};
+            TIM_TRY(run_linear<T>(c, xin, E, ly.in_proj, plain_rows(Mi), epi(qkv, 3 * E, f32), s, l > 0 ? &lp : nullptr));
+        }
         if constexpr (f32) {
             LAUNCH_C(c, 1, attn_flops, s, launch_attention_simt(reinterpret_cast<const float*>(qkv), reinterpret_cast<float*>(att), B, Ft, Qt, c->H, c->hd, s));
         } else if (attn_umma) {
@@ -580,18 +629,17 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
             TIM_TRY(run_linear<T>(c, hid, FF, ly.lin2, plain_rows(Mi), epi(z, E, true, ACT_NONE, x32, E), s));
             LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(z, E, ly.n2g, ly.n2b, x32, E, x16o, E, Mi, E, s));
         } else {
-            // 16-bit path: the fp32 LayerNorm output is never materialised. x32 holds the tokens (layer 0) or the
-            // pre-norm2 rows z2 of the previous layer, z the pre-norm1 rows z1; LayerNorm writes only the 16-bit operand
-            // copy + (mean, rstd) per row, and the GEMM that needs LN(.) as its residual normalises the rows on read.
             Epilogue e1 = epi(z, E, true, ACT_NONE, x32, E);
             if (l > 0) { e1.rstats = stats; e1.rgamma = c->layers[l - 1].n2g; e1.rbeta = c->layers[l - 1].n2b; }
             TIM_TRY(run_linear<T>(c, att, E, ly.out_proj, plain_rows(Mi), e1, s));
-            LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(z, E, ly.n1g, ly.n1b, nullptr, 0, x16o, E, Mi, E, s, stats));
-            TIM_TRY(run_linear<T>(c, xin, E, ly.lin1, plain_rows(Mi), epi(hid, FF, f32, ACT_GELU), s));
+            LnPrologue lp1{z, ly.n1g, ly.n1b, stats};
+            TIM_TRY(run_linear<T>(c, xin, E, ly.lin1, plain_rows(Mi), epi(hid, FF, f32, ACT_GELU), s, &lp1));
             Epilogue e2 = epi(x32, E, true, ACT_NONE, z, E);
             e2.rstats = stats; e2.rgamma = ly.n1g; e2.rbeta = ly.n1b;
             TIM_TRY(run_linear<T>(c, hid, FF, ly.lin2, plain_rows(Mi), e2, s));
-            LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(x32, E, ly.n2g, ly.n2b, nullptr, 0, x16o, E, Mi, E, s, stats));
+            // the last layer's norm2 feeds the heads: a kernel of its own
+            if (l == c->L - 1)
+                LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(x32, E, ly.n2g, ly.n2b, nullptr, 0, x16o, E, Mi, E, s, stats));
         }
     }
     // fp32 features returned to the caller (tim.py:172, x[:, :num_feats]): LayerNorm of the last layer's z2 feature rows
@@ -727,6 +775,7 @@ int tim_create(tim_ctx** out, const tim_config* cfg, int device) {
     c->esize = g.compute_dtype == TIM_FP32 ? 4 : 2;
     if (const char* gv = std::getenv("TIM_B200_GEMM")) c->gemm_version = std::atoi(gv) == 1 ? 1 : 2;
     if (const char* av = std::getenv("TIM_B200_ATTN")) c->attn_version = std::atoi(av) == 1 ? 1 : 2;
+    if (const char* lv = std::getenv("TIM_B200_LNP")) c->ln_prologue = std::atoi(lv) != 0;
     if (c->d % 4) return bail(c->fail(TIM_ERR_INVALID, "d_model must be a multiple of 4"));
     if (c->vis_data && !g.n_action) return bail(c->fail(TIM_ERR_INVALID, "visual data modality needs n_action > 0"));
     if (c->aud_data && !g.n_audio) return bail(c->fail(TIM_ERR_INVALID, "audio data modality needs n_audio > 0"));
@@ -755,6 +804,7 @@ void tim_destroy(tim_ctx* c) {
     cudaDeviceSynchronize();
     for (void* p : c->allocs) cudaFree(p);
     if (c->ws) cudaFree(c->ws);
+    if (c->ln_flags) cudaFree(c->ln_flags);
     if (c->io) cudaFree(c->io);
     for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
