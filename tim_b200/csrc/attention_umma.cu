@@ -286,7 +286,8 @@ __global__ void __launch_bounds__(AU_THREADS, 1) attention_umma_kernel(const __g
                     }
                 }
                 tmem_ld_wait();
-                float m = sself;
+                // four independent max / sum chains: one warp per scheduler runs this, so dependent-issue latency is what it costs
+                float mx[4] = {sself, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     if (c * 16 < Fp) {
@@ -296,10 +297,11 @@ __global__ void __launch_bounds__(AU_THREADS, 1) attention_umma_kernel(const __g
                                 if (c * 16 + j >= Ft) s[c * 16 + j] = -INFINITY;
                         }
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) m = fmaxf(m, s[c * 16 + j]);
+                        for (int j = 0; j < 16; ++j) mx[j & 3] = fmaxf(mx[j & 3], s[c * 16 + j]);
                     }
                 }
-                float l = 0.0f;
+                const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+                float ls[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     if (c * 16 < Fp) {
@@ -307,7 +309,7 @@ __global__ void __launch_bounds__(AU_THREADS, 1) attention_umma_kernel(const __g
                         for (int j = 0; j < 16; ++j) {
                             const float e = ex2_approx(s[c * 16 + j] - m);
                             s[c * 16 + j] = e;
-                            l += e;
+                            ls[j & 3] += e;
                         }
 #pragma unroll
                         for (int h8 = 0; h8 < 2; ++h8) {
@@ -319,6 +321,7 @@ __global__ void __launch_bounds__(AU_THREADS, 1) attention_umma_kernel(const __g
                         }
                     }
                 }
+                const float l = (ls[0] + ls[1]) + (ls[2] + ls[3]);
                 const float ps = qt ? ex2_approx(sself - m) : 0.0f;
                 const float inv = 1.0f / (l + ps);
                 sts_f32(stat(st, 0, row), inv);
@@ -380,16 +383,20 @@ __global__ void __launch_bounds__(AU_THREADS, 1) attention_umma_kernel(const __g
                         }
                         __syncwarp();
                     }
+                    // TMEM loads of one 64-column box at a time (one wait per box), then the arithmetic
 #pragma unroll
                     for (int cc = 0; cc < 4; ++cc) {
                         if (cc < nb * 2) {
                             const int c32 = jb * 2 + cc;
-                            uint32_t v[32];
-                            tmem_ld_32x32(taddr + c32 * 32, v);
-                            tmem_ld_wait();
+                            uint32_t v[2][32];
+                            if ((cc & 1) == 0) {
+                                tmem_ld_32x32(taddr + c32 * 32, v[0]);
+                                tmem_ld_32x32(taddr + c32 * 32 + 32, v[1]);
+                                tmem_ld_wait();
+                            }
                             float f[32];
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * inv;
+                            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[cc & 1][j]) * inv;
                             if (vterm) {
 #pragma unroll
                                 for (int c = 0; c < 4; ++c) {
