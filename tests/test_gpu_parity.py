@@ -225,6 +225,57 @@ def test_attention_kernel(lib, B, Ft, Qt, H, hd, dt):
     assert e <= {"fp32": 5e-6, "fp16": 6e-4, "bf16": 5e-3}[dt], e
 
 
+@pytest.mark.parametrize("name", ["recog_av_small", "det_visual"])
+def test_patch_model_dropin(lib, name):
+    """The drop-in itself: patch_model() on a module with the reference's attributes and parameter names must give the
+    reference's call signatures / return structure, track parameter updates (torch version counter, as optimizer.step()
+    and load_state_dict bump it) and refuse what is not built instead of falling back."""
+    from oracle.tim_oracle import TIMOracle
+    from tests._fake_tim import FakeTIM
+    from tim_b200.plugin import patch_model
+    cfg, sd, inp, gold, c = load_case(name)
+    Qv, Qa = c["Qv"], c["Qa"]
+    dev = torch.device("cuda", 0)
+    model = patch_model(FakeTIM(cfg, sd).to(dev).eval(), compute_dtype="fp32")
+    vis = torch.from_numpy(inp["vis"]).to(dev) if "vis" in inp else None
+    aud = torch.from_numpy(inp["aud"]).to(dev) if "aud" in inp else None
+    times = torch.from_numpy(inp["times"]).to(dev)
+
+    def run():
+        with torch.no_grad():
+            if cfg.variant == "recognition":
+                te = model(times, "time_mlp")
+                (verb, noun, action, audio), feats = model([vis, aud], "encoder", te, Qv, Qa)
+                return dict(verb=verb, noun=noun, action=action, audio=audio, feats=feats, time_encodings=te)
+            model.inference_queries = times[:1, cfg.F_tot:cfg.F_tot + Qv].clone()      # what synth's shared_queries encodes
+            (cls, reg, feats), offs, labels, queries, ious = model([vis, aud], "encoder", times[:, :cfg.F_tot], None, False)
+            assert queries[0].shape == (times.shape[0] * Qv, 2) and ious == (None, None)
+            return dict(verb=cls[0], noun=cls[1], action=cls[2], audio=cls[3], reg_v=reg[0], reg_a=reg[1], feats=feats)
+
+    def check(out, sd_now):
+        ref = TIMOracle(cfg, sd_now, np.float32).forward(inp.get("vis"), inp.get("aud"), inp["times"], Qv, Qa)
+        for k, v in out.items():
+            if ref.get(k) is None:
+                assert v is None, k
+            else:
+                assert rel_l2(v.cpu().numpy(), ref[k]) <= 1e-5, k
+
+    check(run(), sd)
+    # an in-place update of one parameter (what optimizer.step() does) must be picked up on the next call
+    key = f"{cfg.encoder_prefix}.layers.0.linear1.weight"
+    with torch.no_grad():
+        dict(model.named_parameters())[key].mul_(1.5)
+    sd2 = dict(sd)
+    sd2[key] = sd[key] * np.float32(1.5)
+    check(run(), sd2)
+    assert set(model.state_dict().keys()) >= set(sd.keys())                  # the module tree / checkpoint layout is untouched
+    model.train()
+    with pytest.raises(NotImplementedError):
+        model([vis, aud], "encoder", times, Qv, Qa) if cfg.variant == "recognition" else model([vis, aud], "encoder", times[:, :cfg.F_tot])
+    with pytest.raises(ValueError):
+        model.eval()(times, "no_such_forward_type")
+
+
 def test_errors_are_loud(lib):
     from tim_b200.plugin import TIMEngine
     from tim_b200._lib import TimError

@@ -90,3 +90,35 @@ def test_gloo_world2_sharded_forward_matches_single():
                        cwd=ROOT, env={**os.environ, "OMP_NUM_THREADS": "2"})
     assert r.returncode == 0, r.stdout + r.stderr
     assert "GLOO_SHARD_OK" in r.stdout
+
+
+@pytest.mark.parametrize("variant", ["recognition", "detection"])
+def test_config_from_real_reference_model(variant):
+    """Where the reference checkout exists (the build container, not the GPU box): instantiate the UNMODIFIED reference TIM on
+    CPU and check that the drop-in reads its constructor arguments back correctly (plugin.config_from_model) and that every
+    hot-path key exists in its state_dict with the expected shape. Own subprocess: recognition and detection share a package
+    name."""
+    import subprocess
+    import sys
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("reference checkout not present on this machine")
+    code = f"""
+import sys
+sys.path.insert(0, {ROOT!r})
+from tools.make_golden import build_reference
+from tim_b200.config import TIMConfig, hot_path_keys, state_dict_spec
+from tim_b200.plugin import config_from_model
+kw = dict(num_class=[[5, 7, 11], 3], visual_input_dim=48, audio_input_dim=40, d_model=64, nhead=4, num_layers=2, num_feats=6)
+if {variant!r} == "detection":
+    kw.update(num_class=[9, 4], include_verb_noun=False, data_modality="visual", variant="detection")
+cfg = TIMConfig(**kw)
+model = build_reference(cfg)
+got = config_from_model(model)
+assert got == cfg, (got, cfg)
+sd, spec = model.state_dict(), state_dict_spec(cfg)
+for k in hot_path_keys(cfg):
+    assert tuple(sd[k].shape) == tuple(spec[k]), k
+print("OK")
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
