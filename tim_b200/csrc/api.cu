@@ -94,9 +94,6 @@ struct tim_ctx {
     // workspace arena (grow-only)
     uint8_t* ws = nullptr;
     size_t ws_bytes = 0;
-    uint32_t* ln_flags = nullptr;   // per-256-row-block counters of the LayerNorm-prologue GEMM (grow-only)
-    size_t ln_flags_n = 0;
-    int ln_prologue = 0;            // 1: LayerNorm as a prologue of the consuming GEMM (TIM_B200_LNP=1; measured slower)
     // staging for tim_forward_host
     uint8_t* io = nullptr;
     size_t io_bytes = 0;
@@ -359,8 +356,8 @@ struct Arena {
 // ------------------------------------------------------------------------------------------------------------------
 // one linear layer through the selected compute path
 // ------------------------------------------------------------------------------------------------------------------
-// LayerNorm feeding a linear layer: A (16-bit, [rows, K]) = LayerNorm(in) (+ row statistics). Where the CTA-pair kernel
-// applies it runs as that kernel's prologue (mode 4); otherwise as a LayerNorm kernel of its own before the GEMM.
+// LayerNorm feeding a linear layer: A (16-bit, [rows, K]) = LayerNorm(in) (+ row statistics), a kernel of its own before the GEMM.
+// (Running it as a prologue inside the CTA-pair GEMM was built and measured slower - DESIGN.md §5, git d85dd9e, "mode 4".)
 struct LnPrologue {
     const float* in;      // fp32 [rows, K]
     const float* gamma;
@@ -374,17 +371,11 @@ int run_linear(tim_ctx* c, const void* A, int lda, const LinearW& w, RowMap rm, 
     if (lda != w.K) return c->fail(TIM_ERR_INVALID, "linear: lda %d != K %d", lda, w.K);
     if (rm.G <= 0 || rm.R <= 0) return TIM_OK;
     if (!ep.bias) ep.bias = w.bias;
-    bool ln_fused = false;
     if (ln) {
         if constexpr (std::is_same<T, float>::value) {
             return c->fail(TIM_ERR_INVALID, "linear: LayerNorm prologue is a 16-bit path feature");
         } else {
-            const bool plain0 = rm.G == 1 && rm.box_g == 1 && rm.a_row_off == 0 && rm.out_row_off == 0;
-            ln_fused = c->ln_prologue && c->gemm_version >= 2 && plain0 && w.has_tmB2 && umma2_supported(rm.R, w.N, w.K) &&
-                       umma2_ln_supported(w.K) && !ep.out_fp32 && !ep.resid && (ep.act == ACT_NONE || ep.act == ACT_GELU) &&
-                       (static_cast<size_t>(ep.ldo) * 2) % 16 == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15) == 0;
-            if (!ln_fused)
-                LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(ln->in, w.K, ln->gamma, ln->beta, nullptr, 0, static_cast<T*>(const_cast<void*>(A)), w.K,
+            LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(ln->in, w.K, ln->gamma, ln->beta, nullptr, 0, static_cast<T*>(const_cast<void*>(A)), w.K,
                                                              rm.R, w.K, s, ln->stats));
         }
     }
@@ -412,21 +403,7 @@ int run_linear(tim_ctx* c, const void* A, int lda, const LinearW& w, RowMap rm, 
                 TIM_TRY(make_tmap_2d(c, &q.tmRes, ep.resid, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, w.N, M, static_cast<long long>(ep.ldr) * 4, 32, 32));
             q.bias = ep.bias; q.M = M; q.N = w.N; q.K = w.K;
             q.rstats = ep.rstats; q.rgamma = ep.rgamma; q.rbeta = ep.rbeta;
-            int mode = ep.out_fp32 ? (ep.resid ? (ep.rstats ? 3 : 2) : 1) : 0;
-            if (ln_fused) {
-                const size_t blocks = (static_cast<size_t>(M) + 255) / 256 + 1;
-                if (blocks > c->ln_flags_n) {
-                    if (c->ln_flags) { cudaDeviceSynchronize(); cudaFree(c->ln_flags); c->ln_flags = nullptr; c->ln_flags_n = 0; }
-                    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->ln_flags), blocks * sizeof(uint32_t));
-                    if (e != cudaSuccess) return c->fail(TIM_ERR_NOMEM, "LayerNorm flag cudaMalloc failed: %s", cudaGetErrorString(e));
-                    c->ln_flags_n = blocks;
-                }
-                q.ln_in = ln->in; q.ln_gamma = ln->gamma; q.ln_beta = ln->beta; q.ln_out = const_cast<void*>(A);
-                q.ln_stats = ln->stats; q.ln_flags = c->ln_flags;
-                mode = 4;
-                c->launches++;      // the counter memset in front of the kernel
-            }
-            if (mode == 3 && ep.act != ACT_NONE) return c->fail(TIM_ERR_INVALID, "linear: LayerNorm-on-read residual supports no activation");
+            const int mode = ep.out_fp32 ? (ep.resid ? (ep.rstats ? 3 : 2) : 1) : 0;
             LAUNCH_C(c, 0, 2.0 * M * w.N * w.K, s, launch_linear_umma2<T>(q, mode, ep.act, c->num_sms, s));
             return TIM_OK;
         }
@@ -775,7 +752,6 @@ int tim_create(tim_ctx** out, const tim_config* cfg, int device) {
     c->esize = g.compute_dtype == TIM_FP32 ? 4 : 2;
     if (const char* gv = std::getenv("TIM_B200_GEMM")) c->gemm_version = std::atoi(gv) == 1 ? 1 : 2;
     if (const char* av = std::getenv("TIM_B200_ATTN")) c->attn_version = std::atoi(av) == 1 ? 1 : 2;
-    if (const char* lv = std::getenv("TIM_B200_LNP")) c->ln_prologue = std::atoi(lv) != 0;
     if (c->d % 4) return bail(c->fail(TIM_ERR_INVALID, "d_model must be a multiple of 4"));
     if (c->vis_data && !g.n_action) return bail(c->fail(TIM_ERR_INVALID, "visual data modality needs n_action > 0"));
     if (c->aud_data && !g.n_audio) return bail(c->fail(TIM_ERR_INVALID, "audio data modality needs n_audio > 0"));
@@ -804,7 +780,6 @@ void tim_destroy(tim_ctx* c) {
     cudaDeviceSynchronize();
     for (void* p : c->allocs) cudaFree(p);
     if (c->ws) cudaFree(c->ws);
-    if (c->ln_flags) cudaFree(c->ln_flags);
     if (c->io) cudaFree(c->io);
     for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);

@@ -32,14 +32,11 @@ constexpr int B_BYTES = (BN / 2) * BK * 2;      // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + EPI_WARPS * 32;
-constexpr int LN_WARPS = 4;                        // MODE 4 only: LayerNorm prologue warps
-constexpr int THREADS_LN = THREADS + LN_WARPS * 32;
 constexpr int EPI_BUF = 32 * 128;               // 32 rows x 128 B
 constexpr int EPI_BUFS = 2;                     // per warp
 constexpr int BAR_BYTES = 512;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_BUFS * EPI_BUF + BAR_BYTES + 1024;
 constexpr int TMEM_COLS = 512;
-constexpr int LN_MAX_K = 2048;                     // LayerNorm prologue: widest row held in registers (16 float4 per lane)
 
 template <typename T> struct FmtOf2;
 template <> struct FmtOf2<__half> { static constexpr uint32_t v = 0; };
@@ -51,80 +48,10 @@ template <int ACT> __device__ __forceinline__ float apply_act(float v) {
     return v;
 }
 
-// LayerNorm prologue work of one warp (MODE 4): rows of p.ln_in -> 16-bit rows of p.ln_out + (mean, rstd); R rows at a time,
-// each held in registers (V float4 per lane: rows of up to 128 * V floats), one pass over memory.
-template <typename T, int V, int R>
-__device__ __forceinline__ void ln_prologue_rows(const Umma2Params& p, int gw, int GW, int lane) {
-    const int n = p.K;
-    const float inv_n = 1.0f / static_cast<float>(n);
-    const int chunks = (p.M + 3) / 4;
-    T* out16 = static_cast<T*>(p.ln_out);
-    for (int ch = gw; ch < chunks; ch += GW) {
-        const int r0 = ch * 4;
-        const int nr = min(4, p.M - r0);
-        for (int i = 0; i < nr; i += R) {
-            float4 v[R][V];
-            float sum[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const float* x = p.ln_in + static_cast<size_t>(r0 + min(i + r, nr - 1)) * n;     // a missing row re-reads the last one
-                sum[r] = 0.0f;
-#pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    const int c = lane * 4 + j * 128;
-                    v[r][j] = c < n ? *reinterpret_cast<const float4*>(x + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    sum[r] += (v[r][j].x + v[r][j].y) + (v[r][j].z + v[r][j].w);
-                }
-            }
-            float mean[R], rstd[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                mean[r] = warp_sum(sum[r]) * inv_n;
-                float q = 0.0f;
-#pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    if (lane * 4 + j * 128 < n) {
-                        const float a = v[r][j].x - mean[r], b = v[r][j].y - mean[r], c2 = v[r][j].z - mean[r], d = v[r][j].w - mean[r];
-                        q += (a * a + b * b) + (c2 * c2 + d * d);
-                    }
-                }
-                rstd[r] = rsqrtf(warp_sum(q) * inv_n + 1e-5f);
-            }
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if (i + r < nr) {
-                    const size_t row = static_cast<size_t>(r0 + i + r);
-                    if (lane == 0) p.ln_stats[row] = make_float2(mean[r], rstd[r]);
-#pragma unroll
-                    for (int j = 0; j < V; ++j) {
-                        const int c = lane * 4 + j * 128;
-                        if (c < n) {
-                            const float4 g = __ldg(reinterpret_cast<const float4*>(p.ln_gamma + c));
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(p.ln_beta + c));
-                            uint2 o;
-                            o.x = pack2<T>((v[r][j].x - mean[r]) * rstd[r] * g.x + b.x, (v[r][j].y - mean[r]) * rstd[r] * g.y + b.y);
-                            o.y = pack2<T>((v[r][j].z - mean[r]) * rstd[r] * g.z + b.z, (v[r][j].w - mean[r]) * rstd[r] * g.w + b.w);
-                            *reinterpret_cast<uint2*>(out16 + row * n + c) = o;
-                        }
-                    }
-                }
-            }
-        }
-        __threadfence();                              // this lane's row pieces are visible device-wide ...
-        __syncwarp();
-        if (lane == 0) red_release_gpu_add_u32(p.ln_flags + (r0 >> 8), static_cast<uint32_t>(nr));   // ... before the count
-    }
-    if (lane == 0) red_release_gpu_add_u32(p.ln_flags + p.tiles_m, 1u);        // this warp has no rows left
-}
-
 // MODE 0: 16-bit output, 1: fp32 output, 2: fp32 output + fp32 residual (added after the activation),
 // 3: as 2 with LayerNorm applied to the residual rows on the fly (row statistics in p.rstats, affine in p.rgamma / p.rbeta),
-// 4: as 0 with a LayerNorm PROLOGUE: four extra warps per CTA normalise the fp32 rows p.ln_in [M, K] into the 16-bit A operand
-//    (p.ln_out, the tensor behind tmA) and publish per-256-row-block counters; the TMA producer acquires the counter of a
-//    row block before loading it. The HBM-bound LayerNorm then runs under the tensor-bound main loop instead of as a
-//    kernel of its own (transformers.py:105,109 feeding :102 / :107).
 template <typename T, int MODE, int ACT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == 4 ? THREADS_LN : THREADS, 1) linear_umma2_kernel(const __grid_constant__ Umma2Params p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_umma2_kernel(const __grid_constant__ Umma2Params p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smem_a = smem_base;
@@ -175,37 +102,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == 4 ? THREADS_
         // ===================== TMA producer (both CTAs) =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            // MODE 4: row-block readiness. The flag of the NEXT tile's row block and the "all LayerNorm warps finished" counter
-            // are loaded one tile ahead, so their L2 round trip hides behind this tile's loads; once everything is
-            // normalised the checks stop.
-            bool ln_all_done = false;
-            int ln_next_tm = -1;
-            uint32_t ln_next_cnt = 0, ln_done_warps = 0;
-            const uint32_t ln_total_warps = gridDim.x * LN_WARPS;
             for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
                 const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
                 const int m0 = tm * (2 * BM) + static_cast<int>(rank) * BM;
                 const int n0 = tn * BN + static_cast<int>(rank) * (BN / 2);
-                if (MODE == 4 && !ln_all_done) {
-                    // the A rows of this block exist only once the LayerNorm warps (of any CTA) have written them
-                    const uint32_t need = static_cast<uint32_t>(min(2 * BM, p.M - tm * (2 * BM)));
-                    if (ln_done_warps == ln_total_warps) {
-                        ln_all_done = true;
-                    } else if (!(tm == ln_next_tm && ln_next_cnt >= need)) {
-                        uint32_t spins = 0;
-                        while (ld_acquire_gpu_u32(p.ln_flags + tm) < need) {
-                            __nanosleep(64);
-                            if (++spins > (1u << 22)) __trap();
-                        }
-                    }
-                    fence_proxy_async_global();        // generic-proxy global writes (other CTAs) -> this thread's TMA loads
-                    const int nt = tile + num_clusters;
-                    if (nt < num_tiles) {
-                        ln_next_tm = nt / p.tiles_n;
-                        ln_next_cnt = ld_acquire_gpu_u32(p.ln_flags + ln_next_tm);
-                        ln_done_warps = ld_acquire_gpu_u32(p.ln_flags + p.tiles_m);
-                    }
-                }
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);
                     const uint32_t fb = mapa_shared(full_bar(stage), 0);     // the leader's barrier
@@ -252,7 +152,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == 4 ? THREADS_
         const uint32_t my_row = static_cast<uint32_t>(lane) * 128u;
         const uint32_t swz = static_cast<uint32_t>(lane & 7);
         const uint32_t tempty_leader0 = mapa_shared(tempty_bar(0), 0), tempty_leader1 = mapa_shared(tempty_bar(1), 0);
-        constexpr bool OUT16 = MODE == 0 || MODE == 4;
+        constexpr bool OUT16 = MODE == 0;
         constexpr bool RES = MODE == 2 || MODE == 3;
         constexpr int COLS_PER_BLOCK = OUT16 ? 64 : 32;          // 128 B of output per row
         constexpr int BLOCKS = BN / COLS_PER_BLOCK;
@@ -369,14 +269,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(MODE == 4 ? THREADS_
         }
         if (lane == 0) tma_store_wait<0>();               // stores complete before the CTA (and its smem) goes away
         __syncwarp();
-    } else if (MODE == 4) {
-        // ===================== LayerNorm prologue (warps 10..13) =====================
-        // Row chunks of 4 are dealt round-robin over all LN warps of the grid in increasing row order, so row blocks
-        // complete roughly in the order the tiles consume them. One pass: the row stays in registers.
-        const int gw = static_cast<int>(blockIdx.x) * LN_WARPS + (warp - 2 - EPI_WARPS);
-        const int GW = static_cast<int>(gridDim.x) * LN_WARPS;
-        if (p.K <= 1024) ln_prologue_rows<T, 8, 2>(p, gw, GW, lane);
-        else ln_prologue_rows<T, 16, 1>(p, gw, GW, lane);
     }
 
     tc_fence_before();
@@ -400,17 +292,11 @@ cudaError_t launch_mode(const Umma2Params& p, int num_sms, cudaStream_t s) {
     if (tiles <= 0) return cudaSuccess;
     int clusters = num_sms / 2;
     if (clusters > tiles) clusters = tiles;
-    if (MODE == 4) {
-        cudaError_t e = cudaMemsetAsync(p.ln_flags, 0, (static_cast<size_t>(p.tiles_m) + 1) * sizeof(uint32_t), s);
-        if (e != cudaSuccess) return e;
-    }
-    kern<<<2 * clusters, MODE == 4 ? THREADS_LN : THREADS, SMEM_BYTES, s>>>(p);
+    kern<<<2 * clusters, THREADS, SMEM_BYTES, s>>>(p);
     return cudaGetLastError();
 }
 
 }  // namespace
-
-bool umma2_ln_supported(int K) { return K % 4 == 0 && K <= LN_MAX_K; }
 
 bool umma2_supported(int M, int N, int K) { return M > 0 && N >= 128 && (N % 64) == 0 && K >= 64 && (K % 8) == 0; }
 
@@ -423,7 +309,6 @@ cudaError_t launch_linear_umma2(Umma2Params p, int mode, int act, int num_sms, c
     TIM_U2(1, ACT_NONE) TIM_U2(1, ACT_RELU) TIM_U2(1, ACT_GELU)
     TIM_U2(2, ACT_NONE) TIM_U2(2, ACT_RELU) TIM_U2(2, ACT_GELU)
     TIM_U2(3, ACT_NONE)
-    TIM_U2(4, ACT_NONE) TIM_U2(4, ACT_GELU)
 #undef TIM_U2
     return cudaErrorInvalidValue;
 }

@@ -65,21 +65,12 @@ struct Umma2Params {
     const float2* rstats; // mode 3: per-row (mean, rstd) of the residual rows; rgamma / rbeta [N]
     const float* rgamma;
     const float* rbeta;
-    // mode 4: LayerNorm prologue producing the A operand inside the kernel
-    const float* ln_in;   // fp32 [M, K] pre-LayerNorm rows
-    const float* ln_gamma;
-    const float* ln_beta;
-    void* ln_out;         // T [M, K]: the tensor tmA reads
-    float2* ln_stats;     // [M] (mean, rstd), for the later LayerNorm-on-read of the same rows
-    uint32_t* ln_flags;   // [tiles_m] rows normalised so far per 256-row block, [tiles_m]: LN warps finished (zeroed by the launcher)
     int M, N, K;
     int tiles_m, tiles_n;
 };
 bool umma2_supported(int M, int N, int K);
-bool umma2_ln_supported(int K);
 // mode 0: out = T(act(acc + bias)); 1: out = float(act(acc + bias)); 2: out = float(act(acc + bias) + resid);
 // mode 3: out = float(act(acc + bias) + LayerNorm(resid)) with the row statistics given (Epilogue::rstats)
-// mode 4: mode 0 whose A operand is LayerNorm(ln_in), normalised by extra warps of the same kernel
 template <typename T>
 cudaError_t launch_linear_umma2(Umma2Params p, int mode, int act, int num_sms, cudaStream_t s);
 
