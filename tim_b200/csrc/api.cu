@@ -30,6 +30,14 @@ struct LinearW {
     int block_n = 0;
     int scale_rows = 0;         // leading rows (and bias entries) multiplied by `scale` when packed (q part of in_proj)
     float scale = 1.0f;
+    // folded-LayerNorm variant (in_proj of layers >= 1, linear1): fp32 masters + gamma-folded 16-bit weight, see fold_ln_kernel
+    bool foldable = false;
+    float* w32 = nullptr;       // [N, K] fp32 master (unscaled)
+    float* b32 = nullptr;       // [N] fp32 master (unscaled)
+    void* wf = nullptr;         // [N, K] folded, compute dtype
+    float* cs = nullptr;        // [N]
+    float* bwf = nullptr;       // [N]
+    CUtensorMap tmB2f;          // CTA-pair map of wf
 };
 
 struct Slot {                   // one state_dict key
@@ -70,6 +78,8 @@ struct tim_ctx {
     EncodeTiledFn encode = nullptr;
     int gemm_version = 2;       // 2: CTA-pair kernel where the shape allows, 1: single-CTA kernel only (TIM_B200_GEMM=1)
     int attn_version = 2;       // 2: tcgen05 attention where the shape allows, 1: warp-MMA attention only (TIM_B200_ATTN=1)
+    bool fold_ln = false;       // encoder LayerNorms folded into the GEMMs around them (16-bit path, CTA-pair kernel shapes; TIM_B200_FOLD=0 disables)
+    bool fold_dirty = true;     // a weight changed since the folded copies were made
 
     // optional live profiling: CUDA-event pairs around every launch, accumulated per kernel class
     bool profiling = false;
@@ -333,6 +343,25 @@ int build_weights(tim_ctx* c) {
         TIM_TRY(add_vec(c, p + "norm2.weight", &ly.n2g, {E}));
         TIM_TRY(add_vec(c, p + "norm2.bias", &ly.n2b, {E}));
     }
+    // folded LayerNorm: needs every encoder GEMM on the CTA-pair kernel (shape conditions are independent of the batch)
+    c->fold_ln = g.compute_dtype != TIM_FP32 && c->gemm_version >= 2 && c->L > 0 && E <= 2048 && umma2_supported(1, 3 * E, E) &&
+                 umma2_supported(1, E, E) && umma2_supported(1, FF, E) && umma2_supported(1, E, FF);
+    if (const char* fv = std::getenv("TIM_B200_FOLD")) if (std::atoi(fv) == 0) c->fold_ln = false;
+    if (c->fold_ln) {
+        auto make_foldable = [&](LinearW& w) -> int {
+            w.foldable = true;
+            TIM_TRY(dev_alloc(c, reinterpret_cast<void**>(&w.w32), static_cast<size_t>(w.N) * w.K * sizeof(float)));
+            TIM_TRY(dev_alloc(c, reinterpret_cast<void**>(&w.b32), static_cast<size_t>(w.N) * sizeof(float)));
+            TIM_TRY(dev_alloc(c, &w.wf, static_cast<size_t>(w.N) * w.K * c->esize));
+            TIM_TRY(dev_alloc(c, reinterpret_cast<void**>(&w.cs), static_cast<size_t>(w.N) * sizeof(float)));
+            TIM_TRY(dev_alloc(c, reinterpret_cast<void**>(&w.bwf), static_cast<size_t>(w.N) * sizeof(float)));
+            return make_tmap_2d(c, &w.tmB2f, w.wf, op_dtype(c), 2, w.K, w.N, static_cast<long long>(w.K) * 2, 64, 128);
+        };
+        for (int l = 0; l < c->L; ++l) {
+            if (l > 0) TIM_TRY(make_foldable(c->layers[l].in_proj));
+            TIM_TRY(make_foldable(c->layers[l].lin1));
+        }
+    }
     return TIM_OK;
 }
 
@@ -457,6 +486,48 @@ inline RowMap group_rows(int B, int Qt, int off, int Q) {
     return rm;
 }
 
+// (re)build the gamma-folded weight copies after any parameter changed (12 small kernels for 6 layers)
+template <typename T>
+int refold_weights(tim_ctx* c, cudaStream_t s) {
+    for (int l = 0; l < c->L; ++l) {
+        Layer& ly = c->layers[l];
+        if (l > 0) {
+            LinearW& w = ly.in_proj;
+            LAUNCH(c, launch_fold_ln<T>(w.w32, w.b32, c->layers[l - 1].n2g, c->layers[l - 1].n2b, static_cast<T*>(w.wf), w.cs, w.bwf, w.N, w.K,
+                                        w.scale_rows, w.scale, s));
+        }
+        LinearW& w1 = ly.lin1;
+        LAUNCH(c, launch_fold_ln<T>(w1.w32, w1.b32, ly.n1g, ly.n1b, static_cast<T*>(w1.wf), w1.cs, w1.bwf, w1.N, w1.K, w1.scale_rows, w1.scale, s));
+    }
+    c->fold_dirty = false;
+    return TIM_OK;
+}
+
+// One launch of the CTA-pair kernel in one of the folded-LayerNorm modes (gemm_umma2.cu):
+//   mode 5 (producer): out32 [M,N] fp32 = A W^T + bias + R(resid), out16 = its 16-bit copy, opart = its partial row sums;
+//                      R = LayerNorm-on-read with (rstats, rgamma, rbeta) or the identity when rstats == nullptr
+//   mode 6 (consumer): out16 [M,N] = act(rstd * (A Wf^T - mean * cs) + bwf) with (mean, rstd) = rstats[row]
+template <typename T>
+int run_fold_gemm(tim_ctx* c, int mode, int act, const void* A, int M, int N, int K, const CUtensorMap& tmB, const float* bias,
+                  float* out32, void* out16, const float* resid, const float2* rstats, const float* rgamma, const float* rbeta,
+                  float2* opart, const float* cs, cudaStream_t s) {
+    Umma2Params q;
+    std::memset(&q, 0, sizeof(q));
+    TIM_TRY(make_tmap_2d(c, &q.tmA, A, op_dtype(c), 2, K, M, static_cast<long long>(K) * 2, 64, 128));
+    q.tmB = tmB;
+    if (mode == 5) {
+        TIM_TRY(make_tmap_2d(c, &q.tmOut, out32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, N, M, static_cast<long long>(N) * 4, 32, 32));
+        TIM_TRY(make_tmap_2d(c, &q.tmRes, resid, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, N, M, static_cast<long long>(N) * 4, 32, 32));
+        TIM_TRY(make_tmap_2d(c, &q.tmOut16, out16, op_dtype(c), 2, N, M, static_cast<long long>(N) * 2, 64, 32));
+    } else {
+        TIM_TRY(make_tmap_2d(c, &q.tmOut, out16, op_dtype(c), 2, N, M, static_cast<long long>(N) * 2, 64, 32));
+    }
+    q.bias = bias; q.M = M; q.N = N; q.K = K;
+    q.rstats = rstats; q.rgamma = rgamma; q.rbeta = rbeta; q.opart = opart; q.cs = cs;
+    LAUNCH_C(c, 0, 2.0 * M * N * K, s, launch_linear_umma2<T>(q, mode, act, c->num_sms, s));
+    return TIM_OK;
+}
+
 template <typename T>
 int time_mlp_impl(tim_ctx* c, const float* times, float* out, int B, int T_, cudaStream_t s, uint8_t* ws_base, size_t* ws_need) {
     const int M = B * T_, d = c->d;
@@ -540,8 +611,10 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
     const size_t regrows = static_cast<size_t>(B) * (qp.Qv > qp.Qa ? qp.Qv : qp.Qa);
     a.take(&r1, g.variant == TIM_DETECTION ? regrows * (E / 2) * sizeof(T) : 0);
     a.take(&r2, g.variant == TIM_DETECTION ? regrows * (E / 2) * sizeof(T) : 0);
-    float2* stats;
+    float2 *stats, *part;
     a.take(&stats, f32 ? 0 : M * sizeof(float2));
+    const size_t nparts = 2 * static_cast<size_t>((E + 255) / 256);       // per-tile partial row sums of the folded-LayerNorm GEMMs
+    a.take(&part, c->fold_ln ? nparts * M * sizeof(float2) : 0);
     if (ws_need) { *ws_need = a.off; return TIM_OK; }
 
     // ---- embedders: Linear -> GELU (epilogue) -> pre-LN rows; LN happens while assembling tokens ----
@@ -580,18 +653,30 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
     AttnUmmaParams attn_p;
     bool attn_umma = false;
     if constexpr (!f32) TIM_TRY(prepare_attention<T>(c, &attn_p, &attn_umma, qkv, att, B, Ft, Qt));
+    bool folded = false;
+    if constexpr (!f32) {
+        folded = c->fold_ln;
+        if (folded && c->fold_dirty) TIM_TRY(refold_weights<T>(c, s));
+    }
     for (int l = 0; l < c->L; ++l) {
         Layer& ly = c->layers[l];
+        // ---- in_proj ----
         if constexpr (f32) {
             TIM_TRY(run_linear<T>(c, xin, E, ly.in_proj, plain_rows(Mi), epi(qkv, 3 * E, f32), s));
+        } else if (folded) {
+            // x16 holds the tokens (layer 0) or the 16-bit copy of the previous layer's pre-norm2 rows z2, whose LayerNorm
+            // lives in this GEMM: gamma in the weight, (mean, rstd) and beta in the epilogue
+            if (l == 0) TIM_TRY(run_linear<T>(c, xin, E, ly.in_proj, plain_rows(Mi), epi(qkv, 3 * E, false), s));
+            else TIM_TRY(run_fold_gemm<T>(c, 6, ACT_NONE, x16, Mi, 3 * E, E, ly.in_proj.tmB2f, ly.in_proj.bwf, nullptr, qkv, nullptr, stats,
+                                          nullptr, nullptr, nullptr, ly.in_proj.cs, s));
         } else {
-            // 16-bit path: the fp32 LayerNorm output is never materialised. x32 holds the tokens (layer 0) or the
-            // pre-norm2 rows z2 of the previous layer, z the pre-norm1 rows z1. LayerNorm writes only the 16-bit operand
-            // copy + (mean, rstd) per row - as the prologue of the GEMM that consumes it - and the GEMM that needs LN(.) as
-            // its residual normalises the rows on read.
+            // un-folded 16-bit path: the fp32 LayerNorm output is never materialised either. x32 holds the tokens (layer 0)
+            // or the pre-norm2 rows z2 of the previous layer, z the pre-norm1 rows z1; a LayerNorm kernel writes only the
+            // 16-bit operand copy + (mean, rstd) per row, and the GEMM that needs LN(.) as its residual normalises on read.
             LnPrologue lp{x32, l > 0 ? c->layers[l - 1].n2g : nullptr, l > 0 ? c->layers[l - 1].n2b : nullptr, stats};
             TIM_TRY(run_linear<T>(c, xin, E, ly.in_proj, plain_rows(Mi), epi(qkv, 3 * E, f32), s, l > 0 ? &lp : nullptr));
         }
+        // ---- attention ----
         if constexpr (f32) {
             LAUNCH_C(c, 1, attn_flops, s, launch_attention_simt(reinterpret_cast<const float*>(qkv), reinterpret_cast<float*>(att), B, Ft, Qt, c->H, c->hd, s));
         } else if (attn_umma) {
@@ -599,12 +684,28 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
         } else {
             LAUNCH_C(c, 1, attn_flops, s, launch_attention_mma<T>(qkv, att, B, Ft, Qt, c->H, c->hd, s));
         }
+        // ---- out_proj + residual (+ norm1), FFN + residual (+ norm2) ----
         if constexpr (f32) {
             TIM_TRY(run_linear<T>(c, att, E, ly.out_proj, plain_rows(Mi), epi(z, E, true, ACT_NONE, x32, E), s));
             LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(z, E, ly.n1g, ly.n1b, x32, E, x16o, E, Mi, E, s));
             TIM_TRY(run_linear<T>(c, xin, E, ly.lin1, plain_rows(Mi), epi(hid, FF, f32, ACT_GELU), s));
             TIM_TRY(run_linear<T>(c, hid, FF, ly.lin2, plain_rows(Mi), epi(z, E, true, ACT_NONE, x32, E), s));
             LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(z, E, ly.n2g, ly.n2b, x32, E, x16o, E, Mi, E, s));
+        } else if (folded) {
+            // `stats` holds (mean, rstd) of the rows whose LayerNorm is pending: z2 of the previous layer here ...
+            // z1 = att Wo^T + bo + LN2_prev(z2_prev)   -> z (fp32), x16 (16-bit copy), partial sums
+            TIM_TRY(run_fold_gemm<T>(c, 5, ACT_NONE, att, Mi, E, E, ly.out_proj.tmB2, ly.out_proj.bias, z, x16, x32, l > 0 ? stats : nullptr,
+                                     l > 0 ? c->layers[l - 1].n2g : nullptr, l > 0 ? c->layers[l - 1].n2b : nullptr, part, nullptr, s));
+            LAUNCH_C(c, 2, 0.0, s, launch_row_stats_finalize(part, static_cast<int>(nparts), E, stats, Mi, s));      // ... z1 from here on
+            // hid = gelu(LN1(z1) W1^T + b1) with norm1 folded
+            TIM_TRY(run_fold_gemm<T>(c, 6, ACT_GELU, x16, Mi, FF, E, ly.lin1.tmB2f, ly.lin1.bwf, nullptr, hid, nullptr, stats, nullptr, nullptr,
+                                     nullptr, ly.lin1.cs, s));
+            // z2 = hid W2^T + b2 + LN1(z1)             -> x32 (fp32), x16 (16-bit copy), partial sums
+            TIM_TRY(run_fold_gemm<T>(c, 5, ACT_NONE, hid, Mi, E, FF, ly.lin2.tmB2, ly.lin2.bias, x32, x16, z, stats, ly.n1g, ly.n1b, part, nullptr, s));
+            if (l < c->L - 1) LAUNCH_C(c, 2, 0.0, s, launch_row_stats_finalize(part, static_cast<int>(nparts), E, stats, Mi, s));   // z2
+            // the last layer's norm2 feeds the heads: the only LayerNorm kernel of the stack
+            if (l == c->L - 1)
+                LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(x32, E, ly.n2g, ly.n2b, nullptr, 0, x16o, E, Mi, E, s, stats));
         } else {
             Epilogue e1 = epi(z, E, true, ACT_NONE, x32, E);
             if (l > 0) { e1.rstats = stats; e1.rgamma = c->layers[l - 1].n2g; e1.rbeta = c->layers[l - 1].n2b; }
@@ -809,6 +910,7 @@ int tim_set_weight(tim_ctx* c, const char* key, const float* data, const int64_t
         LinearW& w = *sl.lin;
         if (w.scale_rows % 4) return c->fail(TIM_ERR_INVALID, "q rows (%d) must be a multiple of 4", w.scale_rows);
         LAUNCH(c, launch_scale_copy(data, w.bias, w.N, 1, w.scale_rows, w.scale, s));
+        if (w.foldable) CU_OK(c, cudaMemcpyAsync(w.b32, data, static_cast<size_t>(w.N) * sizeof(float), cudaMemcpyDeviceToDevice, s));
     } else {
         LinearW& w = *sl.lin;
         if ((static_cast<size_t>(w.scale_rows) * w.K) % 4) return c->fail(TIM_ERR_INVALID, "scaled prefix not float4 aligned");
@@ -817,7 +919,9 @@ int tim_set_weight(tim_ctx* c, const char* key, const float* data, const int64_t
             case TIM_BF16: LAUNCH(c, launch_cast<__nv_bfloat16>(data, static_cast<__nv_bfloat16*>(w.w), w.N, w.K, w.scale_rows, w.scale, s)); break;
             case TIM_FP16: LAUNCH(c, launch_cast<__half>(data, static_cast<__half*>(w.w), w.N, w.K, w.scale_rows, w.scale, s)); break;
         }
+        if (w.foldable) CU_OK(c, cudaMemcpyAsync(w.w32, data, static_cast<size_t>(w.N) * w.K * sizeof(float), cudaMemcpyDeviceToDevice, s));
     }
+    c->fold_dirty = true;
     sl.set = true;
     return TIM_OK;
 }

@@ -202,6 +202,47 @@ __global__ void __launch_bounds__(256) cast_tail_kernel(const float* __restrict_
     if (i < n) out[i] = from_float<T>(i < scale_n ? in[i] * scale : in[i]);
 }
 
+// LayerNorm statistics of the rows a folded-LayerNorm producer GEMM wrote (gemm_umma2.cu, mode 5): the GEMM leaves per-tile
+// partial (sum, sum of squares); var = E[z^2] - mean^2 in fp32 (relative error ~ 6e-8 * (1 + mean^2 / var), fine for
+// residual-stream rows whose mean is far below their spread; clamped at 0).
+__global__ void __launch_bounds__(256) row_stats_finalize_kernel(const float2* __restrict__ part, int P, float inv_width,
+                                                                 float2* __restrict__ stats, int M) {
+    const int row = blockIdx.x * 256 + threadIdx.x;
+    if (row >= M) return;
+    float s = 0.0f, q = 0.0f;
+    for (int p = 0; p < P; ++p) {
+        const float2 v = part[static_cast<size_t>(p) * M + row];
+        s += v.x; q += v.y;
+    }
+    const float mean = s * inv_width;
+    const float var = fmaxf(q * inv_width - mean * mean, 0.0f);
+    stats[row] = make_float2(mean, rsqrtf(var + 1e-5f));
+}
+
+// Folding a LayerNorm's affine into the weight of the linear layer that follows it (one warp per output row n):
+//   Wf[n,k] = T(s_n * gamma[k] * W[n,k]),  cs[n] = sum_k float(Wf[n,k]),  bw[n] = s_n * (sum_k beta[k] * W[n,k] + bias[n])
+// so that  LN(z) W^T + bias = rstd * (z Wf^T - mean * cs) + bw   (s_n: optional row scale, the folded q scaling of in_proj)
+template <typename T>
+__global__ void __launch_bounds__(ROWS_PER_CTA * 32) fold_ln_kernel(const float* __restrict__ W, const float* __restrict__ bias,
+                                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                    T* __restrict__ Wf, float* __restrict__ cs, float* __restrict__ bw,
+                                                                    int N, int K, int scale_rows, float scale) {
+    const int lane = threadIdx.x & 31;
+    const int n = blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
+    if (n >= N) return;
+    const float sn = n < scale_rows ? scale : 1.0f;
+    const float* w = W + static_cast<size_t>(n) * K;
+    float c = 0.0f, b = 0.0f;
+    for (int k = lane; k < K; k += 32) {
+        const T q = from_float<T>(sn * gamma[k] * w[k]);
+        Wf[static_cast<size_t>(n) * K + k] = q;
+        c += to_float<T>(q);
+        b = fmaf(beta[k], w[k], b);
+    }
+    c = warp_sum(c); b = warp_sum(b);
+    if (lane == 0) { cs[n] = c; bw[n] = sn * (b + bias[n]); }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(ROWS_PER_CTA * 32) reg_final_kernel(const T* __restrict__ h, int ldh, const float* __restrict__ W,
                                                                       const float* __restrict__ b, float* __restrict__ out, int rows, int K) {
@@ -299,6 +340,22 @@ cudaError_t launch_scale_copy(const float* in, float* out, size_t rows, size_t c
     if (n % 4) cast_tail_kernel<float><<<1, 256, 0, s>>>(in, out, n4 * 4, n, scale_n, scale);
     return cudaGetLastError();
 }
+
+cudaError_t launch_row_stats_finalize(const float2* part, int P, int width, float2* stats, int M, cudaStream_t s) {
+    if (M <= 0) return cudaSuccess;
+    row_stats_finalize_kernel<<<(M + 255) / 256, 256, 0, s>>>(part, P, 1.0f / static_cast<float>(width), stats, M);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_fold_ln(const float* W, const float* bias, const float* gamma, const float* beta, T* Wf, float* cs, float* bw,
+                           int N, int K, int scale_rows, float scale, cudaStream_t s) {
+    if (N <= 0) return cudaSuccess;
+    fold_ln_kernel<T><<<(N + ROWS_PER_CTA - 1) / ROWS_PER_CTA, ROWS_PER_CTA * 32, 0, s>>>(W, bias, gamma, beta, Wf, cs, bw, N, K, scale_rows, scale);
+    return cudaGetLastError();
+}
+template cudaError_t launch_fold_ln<__half>(const float*, const float*, const float*, const float*, __half*, float*, float*, int, int, int, float, cudaStream_t);
+template cudaError_t launch_fold_ln<__nv_bfloat16>(const float*, const float*, const float*, const float*, __nv_bfloat16*, float*, float*, int, int, int, float, cudaStream_t);
 
 template <typename T>
 cudaError_t launch_reg_final(const T* h, int ldh, const float* W, const float* b, float* out, int rows, int K, cudaStream_t s) {

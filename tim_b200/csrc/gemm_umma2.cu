@@ -26,7 +26,7 @@ constexpr int BM = 128;                 // rows per CTA (256 per pair)
 constexpr int BN = 256;                 // columns per pair tile; each CTA stages BN/2 weight rows
 constexpr int BK = 64;                  // one 128-byte swizzle row of 16-bit elements
 constexpr int UK = 16;
-constexpr int STAGES = 5;
+constexpr int STAGES_MAX = 5;
 constexpr int A_BYTES = BM * BK * 2;            // 16 KB
 constexpr int B_BYTES = (BN / 2) * BK * 2;      // 16 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -35,7 +35,7 @@ constexpr int THREADS = 64 + EPI_WARPS * 32;
 constexpr int EPI_BUF = 32 * 128;               // 32 rows x 128 B
 constexpr int EPI_BUFS = 2;                     // per warp
 constexpr int BAR_BYTES = 512;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_WARPS * EPI_BUFS * EPI_BUF + BAR_BYTES + 1024;
+constexpr int SMEM_BYTES = STAGES_MAX * STAGE_BYTES + EPI_WARPS * EPI_BUFS * EPI_BUF + BAR_BYTES + 1024;
 constexpr int TMEM_COLS = 512;
 
 template <typename T> struct FmtOf2;
@@ -49,20 +49,30 @@ template <int ACT> __device__ __forceinline__ float apply_act(float v) {
 }
 
 // MODE 0: 16-bit output, 1: fp32 output, 2: fp32 output + fp32 residual (added after the activation),
-// 3: as 2 with LayerNorm applied to the residual rows on the fly (row statistics in p.rstats, affine in p.rgamma / p.rbeta),
+// 3: as 2 with LayerNorm applied to the residual rows on the fly (row statistics in p.rstats, affine in p.rgamma / p.rbeta)
+// Folded-LayerNorm pair (the LayerNorm between two GEMMs costs no kernel and no extra pass over memory):
+// 5: producer - z = acc + bias + resid (resid raw when p.rstats == nullptr, else LayerNorm-on-read as in mode 3), written as
+//    fp32 (tmOut) AND as the 16-bit operand copy (tmOut16), plus per-row partial sums (sum z, sum z^2) of the 128 columns this
+//    thread owns in the tile: p.opart[(2 tn + half) * M + row]  (row_stats_finalize_kernel turns them into (mean, rstd));
+// 6: consumer - A = the 16-bit copy of z, W pre-multiplied by gamma: out = T(act(rstd * (acc - mean * cs[n]) + bw[n])) with
+//    (mean, rstd) = p.rstats[row], cs[n] = sum_k W'[n,k], bw[n] = sum_k beta[k] W[n,k] + bias[n] (passed as p.bias),
 template <typename T, int MODE, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_umma2_kernel(const __grid_constant__ Umma2Params p) {
+    // MODE 5 trades one pipeline stage for a third epilogue buffer per warp (the 16-bit copy); same total
+    constexpr int STAGES = MODE == 5 ? STAGES_MAX - 1 : STAGES_MAX;
+    constexpr int EPI_BUFS_W = MODE == 5 ? 3 : 2;
+    static_assert(STAGES * STAGE_BYTES + EPI_WARPS * EPI_BUFS_W * EPI_BUF <= STAGES_MAX * STAGE_BYTES + EPI_WARPS * EPI_BUFS * EPI_BUF, "smem");
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t smem_a = smem_base;
     const uint32_t smem_b = smem_base + STAGES * A_BYTES;
     const uint32_t epi_base = smem_base + STAGES * STAGE_BYTES;
-    const uint32_t bar_base = epi_base + EPI_WARPS * EPI_BUFS * EPI_BUF;
+    const uint32_t bar_base = epi_base + EPI_WARPS * EPI_BUFS_W * EPI_BUF;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
-    auto epild_bar = [&](int w, int b) { return bar_base + 8u * (2 * STAGES + 4 + w * EPI_BUFS + b); };
+    auto epild_bar = [&](int w, int b) { return bar_base + 8u * (2 * STAGES + 4 + w * EPI_BUFS + b); };     // residual loads: 2 per warp
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4 + EPI_WARPS * EPI_BUFS);
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
@@ -79,7 +89,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
         tma_prefetch_desc(&p.tmOut);
-        if (MODE == 2 || MODE == 3) tma_prefetch_desc(&p.tmRes);
+        if (MODE == 2 || MODE == 3 || MODE == 5) tma_prefetch_desc(&p.tmRes);
+        if (MODE == 5) tma_prefetch_desc(&p.tmOut16);
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -148,14 +159,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
         const int e = warp - 2;
         const int quarter = warp & 3;                     // TMEM lane quarter this warp may access
         const int half = e >> 2;                          // which interleaved set of column blocks
-        const uint32_t buf0 = epi_base + static_cast<uint32_t>(e * EPI_BUFS) * EPI_BUF;
+        const uint32_t buf0 = epi_base + static_cast<uint32_t>(e * EPI_BUFS_W) * EPI_BUF;
+        const uint32_t buf16 = buf0 + 2 * EPI_BUF;       // MODE 5 only: 32 rows x 64 columns of the 16-bit copy
         const uint32_t my_row = static_cast<uint32_t>(lane) * 128u;
         const uint32_t swz = static_cast<uint32_t>(lane & 7);
         const uint32_t tempty_leader0 = mapa_shared(tempty_bar(0), 0), tempty_leader1 = mapa_shared(tempty_bar(1), 0);
-        constexpr bool OUT16 = MODE == 0;
-        constexpr bool RES = MODE == 2 || MODE == 3;
+        constexpr bool OUT16 = MODE == 0 || MODE == 6;
+        constexpr bool RES = MODE == 2 || MODE == 3 || MODE == 5;
+        constexpr bool DUAL = MODE == 5;
+        constexpr bool FOLD = MODE == 6;
         constexpr int COLS_PER_BLOCK = OUT16 ? 64 : 32;          // 128 B of output per row
         constexpr int BLOCKS = BN / COLS_PER_BLOCK;
+        // column block handled in this warp's i-th step: every other block; MODE 5 takes adjacent PAIRS of 32-column blocks
+        // (0,1),(4,5) / (2,3),(6,7) so that each pair is one 64-column group of the 16-bit copy
+        auto block_of = [&](int i) { return DUAL ? ((i >> 1) * 4 + 2 * half + (i & 1)) : (half + 2 * i); };
         int acc = 0; uint32_t acc_phase = 0;
         uint32_t nbuf = 0;                                // running buffer counter (selects buffer and its load parity)
         for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
@@ -163,22 +180,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
             const int row0 = tm * (2 * BM) + static_cast<int>(rank) * BM + quarter * 32;
             const int n0 = tn * BN;
             const bool rows_live = row0 < p.M;            // warp-uniform: nothing to store for a fully out-of-range slice
+            const bool row_ok = row0 + lane < p.M;
             // number of column blocks of this tile that exist (N % 64 == 0, so blocks are all-or-nothing)
             int my_blocks = 0;
-            for (int cb = half; cb < BLOCKS; cb += 2) my_blocks += (n0 + cb * COLS_PER_BLOCK < p.N) ? 1 : 0;
+            for (int i = 0; i < BLOCKS / 2; ++i) my_blocks += (n0 + block_of(i) * COLS_PER_BLOCK < p.N) ? 1 : 0;
             if (!rows_live) my_blocks = 0;
 
-            float ln_rstd = 1.0f, ln_nmr = 0.0f;          // MODE 3: residual row r -> (r * rstd - mean * rstd) * gamma + beta
-            if (MODE == 3 && row0 + lane < p.M) {
+            // LayerNorm of the residual row on read: r -> (r * rstd - mean * rstd) * gamma + beta   (MODE 3, MODE 5 with rstats)
+            float ln_rstd = 1.0f, ln_nmr = 0.0f;
+            const bool ln_res = MODE == 3 || (DUAL && p.rstats != nullptr);
+            if (ln_res && row_ok) {
                 const float2 st = p.rstats[row0 + lane];
                 ln_rstd = st.y; ln_nmr = -st.x * st.y;
             }
+            // folded LayerNorm of the A rows (MODE 6): out = act(fa * acc + fb * cs[n] + bw[n])
+            float fa = 1.0f, fb = 0.0f;
+            if (FOLD && row_ok) {
+                const float2 st = p.rstats[row0 + lane];
+                fa = st.y; fb = -st.x * st.y;
+            }
+            float st_sum = 0.0f, st_sq = 0.0f;            // MODE 5: sum / sum of squares of this thread's z columns in this tile
+
             if (RES && my_blocks > 0) {             // prefetch the residual of the first block
                 const uint32_t b = nbuf & 1u;
                 if (lane == 0) {
                     tma_store_wait_read<0>();             // that buffer's previous store has drained
                     mbar_arrive_expect_tx(epild_bar(e, b), EPI_BUF);
-                    tma_load_2d(buf0 + b * EPI_BUF, &p.tmRes, epild_bar(e, b), n0 + half * COLS_PER_BLOCK, row0);
+                    tma_load_2d(buf0 + b * EPI_BUF, &p.tmRes, epild_bar(e, b), n0 + block_of(0) * COLS_PER_BLOCK, row0);
                 }
                 __syncwarp();
             }
@@ -187,7 +215,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BN);
 
             for (int i = 0; i < my_blocks; ++i) {
-                const int cb = half + 2 * i;
+                const int cb = block_of(i);
                 const int col0 = n0 + cb * COLS_PER_BLOCK;
                 const uint32_t b = nbuf & 1u;
                 const uint32_t buf = buf0 + b * EPI_BUF;
@@ -196,7 +224,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
                         if (lane == 0) {
                             tma_store_wait_read<0>();
                             mbar_arrive_expect_tx(epild_bar(e, b ^ 1u), EPI_BUF);
-                            tma_load_2d(buf0 + (b ^ 1u) * EPI_BUF, &p.tmRes, epild_bar(e, b ^ 1u), col0 + 2 * COLS_PER_BLOCK, row0);
+                            tma_load_2d(buf0 + (b ^ 1u) * EPI_BUF, &p.tmRes, epild_bar(e, b ^ 1u), n0 + block_of(i + 1) * COLS_PER_BLOCK, row0);
                         }
                         __syncwarp();
                     }
@@ -215,10 +243,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-                        f[j] = apply_act<ACT>(__uint_as_float(v[j]) + b4.x);
-                        f[j + 1] = apply_act<ACT>(__uint_as_float(v[j + 1]) + b4.y);
-                        f[j + 2] = apply_act<ACT>(__uint_as_float(v[j + 2]) + b4.z);
-                        f[j + 3] = apply_act<ACT>(__uint_as_float(v[j + 3]) + b4.w);
+                        if (FOLD) {
+                            const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.cs + n + j));
+                            f[j] = apply_act<ACT>(fmaf(fa, __uint_as_float(v[j]), fmaf(fb, c4.x, b4.x)));
+                            f[j + 1] = apply_act<ACT>(fmaf(fa, __uint_as_float(v[j + 1]), fmaf(fb, c4.y, b4.y)));
+                            f[j + 2] = apply_act<ACT>(fmaf(fa, __uint_as_float(v[j + 2]), fmaf(fb, c4.z, b4.z)));
+                            f[j + 3] = apply_act<ACT>(fmaf(fa, __uint_as_float(v[j + 3]), fmaf(fb, c4.w, b4.w)));
+                        } else {
+                            f[j] = apply_act<ACT>(__uint_as_float(v[j]) + b4.x);
+                            f[j + 1] = apply_act<ACT>(__uint_as_float(v[j + 1]) + b4.y);
+                            f[j + 2] = apply_act<ACT>(__uint_as_float(v[j + 2]) + b4.z);
+                            f[j + 3] = apply_act<ACT>(__uint_as_float(v[j + 3]) + b4.w);
+                        }
                     }
                     if (OUT16) {
                         // 32 columns -> 64 B = logical 16-byte chunks part*4 .. part*4+3 of this row
@@ -240,7 +276,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
                                 float4 r;
                                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                              : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
-                                if (MODE == 3) {
+                                if (ln_res) {
                                     const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.rgamma + n + 4 * c));
                                     const float4 e4 = __ldg(reinterpret_cast<const float4*>(p.rbeta + n + 4 * c));
                                     r.x = fmaf(fmaf(r.x, ln_rstd, ln_nmr), g4.x, e4.x); r.y = fmaf(fmaf(r.y, ln_rstd, ln_nmr), g4.y, e4.y);
@@ -250,6 +286,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
                             }
                             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
                                          ::"r"(addr), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+                            if (DUAL) { f[4 * c] = o.x; f[4 * c + 1] = o.y; f[4 * c + 2] = o.z; f[4 * c + 3] = o.w; }
+                        }
+                        if (DUAL) {
+                            // 16-bit copy of the 32 z values: half of a 64-column (128-byte) row of buf16
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) {
+                                uint4 q;
+                                q.x = pack2<T>(f[8 * c], f[8 * c + 1]); q.y = pack2<T>(f[8 * c + 2], f[8 * c + 3]);
+                                q.z = pack2<T>(f[8 * c + 4], f[8 * c + 5]); q.w = pack2<T>(f[8 * c + 6], f[8 * c + 7]);
+                                const uint32_t chunk = static_cast<uint32_t>((i & 1) * 4 + c);
+                                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                                             ::"r"(buf16 + my_row + ((chunk ^ swz) << 4)), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) { st_sum += f[j]; st_sq = fmaf(f[j], f[j], st_sq); }
                         }
                     }
                 }
@@ -257,10 +308,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
                 __syncwarp();
                 if (lane == 0) {
                     tma_store_2d(&p.tmOut, buf, col0, row0);
+                    if (DUAL && (i & 1)) tma_store_2d(&p.tmOut16, buf16, col0 - 32, row0);
                     tma_store_commit();
                 }
                 ++nbuf;
             }
+            if (DUAL && row_ok)                          // also when this half owns no column of a ragged last tile: (0, 0)
+                p.opart[static_cast<size_t>(tn * 2 + half) * p.M + row0 + lane] = make_float2(st_sum, st_sq);
             // all of this warp's TMEM reads of the accumulator are done
             tc_fence_before();
             __syncwarp();
@@ -309,6 +363,8 @@ cudaError_t launch_linear_umma2(Umma2Params p, int mode, int act, int num_sms, c
     TIM_U2(1, ACT_NONE) TIM_U2(1, ACT_RELU) TIM_U2(1, ACT_GELU)
     TIM_U2(2, ACT_NONE) TIM_U2(2, ACT_RELU) TIM_U2(2, ACT_GELU)
     TIM_U2(3, ACT_NONE)
+    TIM_U2(5, ACT_NONE)
+    TIM_U2(6, ACT_NONE) TIM_U2(6, ACT_GELU)
 #undef TIM_U2
     return cudaErrorInvalidValue;
 }

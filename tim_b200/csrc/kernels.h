@@ -65,12 +65,17 @@ struct Umma2Params {
     const float2* rstats; // mode 3: per-row (mean, rstd) of the residual rows; rgamma / rbeta [N]
     const float* rgamma;
     const float* rbeta;
+    // folded-LayerNorm pair (modes 5 / 6); rstats doubles as the statistics of the residual rows (5) / of the A rows (6)
+    CUtensorMap tmOut16;  // mode 5: 16-bit copy of the output, (N, M), box (64, 32), SWIZZLE_128B
+    float2* opart;        // mode 5: [2 * tiles_n][M] partial (sum, sum of squares) of the rows written
+    const float* cs;      // mode 6: [N] row sums of the gamma-folded 16-bit weight
     int M, N, K;
     int tiles_m, tiles_n;
 };
 bool umma2_supported(int M, int N, int K);
 // mode 0: out = T(act(acc + bias)); 1: out = float(act(acc + bias)); 2: out = float(act(acc + bias) + resid);
 // mode 3: out = float(act(acc + bias) + LayerNorm(resid)) with the row statistics given (Epilogue::rstats)
+// modes 5 / 6: the folded-LayerNorm producer / consumer pair, see gemm_umma2.cu
 template <typename T>
 cudaError_t launch_linear_umma2(Umma2Params p, int mode, int act, int num_sms, cudaStream_t s);
 
@@ -150,6 +155,14 @@ template <typename T>
 cudaError_t launch_cast(const float* in, T* out, size_t rows, size_t cols, size_t scale_rows, float scale, cudaStream_t s);
 cudaError_t launch_scale_copy(const float* in, float* out, size_t rows, size_t cols, size_t scale_rows, float scale,
                               cudaStream_t s);
+
+// (mean, rstd) per row from the partial sums a mode-5 GEMM wrote: part [P][M] (sum, sum of squares), width columns in total
+cudaError_t launch_row_stats_finalize(const float2* part, int P, int width, float2* stats, int M, cudaStream_t s);
+
+// LayerNorm affine folded into the following linear layer's weight (see fold_ln_kernel); W, bias: fp32 masters
+template <typename T>
+cudaError_t launch_fold_ln(const float* W, const float* bias, const float* gamma, const float* beta, T* Wf, float* cs, float* bw,
+                           int N, int K, int scale_rows, float scale, cudaStream_t s);
 
 // last regression layer: sigmoid(h[rows, K] * W[2, K]^T + b) -> out[rows, 2] fp32
 template <typename T>
