@@ -225,8 +225,9 @@ def test_attention_kernel(lib, B, Ft, Qt, H, hd, dt):
     assert e <= {"fp32": 5e-6, "fp16": 6e-4, "bf16": 5e-3}[dt], e
 
 
+@pytest.mark.parametrize("dt", ["fp32", "fp16"])
 @pytest.mark.parametrize("name", ["recog_av_small", "det_visual"])
-def test_patch_model_dropin(lib, name):
+def test_patch_model_dropin(lib, name, dt):
     """The drop-in itself: patch_model() on a module with the reference's attributes and parameter names must give the
     reference's call signatures / return structure, track parameter updates (torch version counter, as optimizer.step()
     and load_state_dict bump it) and refuse what is not built instead of falling back."""
@@ -236,7 +237,8 @@ def test_patch_model_dropin(lib, name):
     cfg, sd, inp, gold, c = load_case(name)
     Qv, Qa = c["Qv"], c["Qa"]
     dev = torch.device("cuda", 0)
-    model = patch_model(FakeTIM(cfg, sd).to(dev).eval(), compute_dtype="fp32")
+    model = patch_model(FakeTIM(cfg, sd).to(dev).eval(), compute_dtype=dt)
+    tol = TOL_SMALL[dt]
     vis = torch.from_numpy(inp["vis"]).to(dev) if "vis" in inp else None
     aud = torch.from_numpy(inp["aud"]).to(dev) if "aud" in inp else None
     times = torch.from_numpy(inp["times"]).to(dev)
@@ -258,10 +260,11 @@ def test_patch_model_dropin(lib, name):
             if ref.get(k) is None:
                 assert v is None, k
             else:
-                assert rel_l2(v.cpu().numpy(), ref[k]) <= 1e-5, k
+                assert rel_l2(v.cpu().numpy(), ref[k]) <= tol, k
 
     check(run(), sd)
-    # an in-place update of one parameter (what optimizer.step() does) must be picked up on the next call
+    # an in-place update of one parameter (what optimizer.step() does) must be picked up on the next call - in the 16-bit
+    # path this is a weight whose packed copy carries a folded LayerNorm, so the folded copy must be rebuilt too
     key = f"{cfg.encoder_prefix}.layers.0.linear1.weight"
     with torch.no_grad():
         dict(model.named_parameters())[key].mul_(1.5)
