@@ -231,9 +231,15 @@ def main():
     gemm = prof["gemm"]
     gemm_tflops = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
     total_prof_ms = sum(c["ms"] for c in prof.values())
-    roofline = {"bound": "tensor", "kernel": "linear_umma_kernel (tcgen05 GEMM, all dense contractions)",
+    traffic, traffic_note = None, None
+    tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    if os.path.exists(tp):
+        tj = json.load(open(tp))
+        if tj.get("workload") == args.workload and tj.get("clips_per_step") == B:      # only for the configuration it was captured on
+            traffic, traffic_note = tj["dram_bytes_per_launch"], f"{tj['what']}; {tj['source']}; algorithmic {tj['algorithmic_bytes_per_launch']:.3e} B"
+    roofline = {"bound": "tensor", "kernel": "linear_umma2_kernel / linear_umma_kernel (tcgen05 GEMMs: every dense contraction of the step)",
                 "achieved": gemm_tflops, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": gemm_tflops / pk["tflops"],
-                "traffic": None, "peak_source": pk["source"],
+                "traffic": traffic, "traffic_note": traffic_note, "peak_source": pk["source"],
                 "launches_per_step": gemm["launches"] // args.steps, "avg_launch_ms": gemm["ms"] / max(1, gemm["launches"]),
                 "share_of_step": gemm["ms"] / total_prof_ms if total_prof_ms else None,
                 "class_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
