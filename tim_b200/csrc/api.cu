@@ -385,9 +385,9 @@ struct Arena {
 // ------------------------------------------------------------------------------------------------------------------
 // one linear layer through the selected compute path
 // ------------------------------------------------------------------------------------------------------------------
-// LayerNorm feeding a linear layer: A (16-bit, [rows, K]) = LayerNorm(in) (+ row statistics), a kernel of its own before the GEMM.
-// (Running it as a prologue inside the CTA-pair GEMM was built and measured slower - DESIGN.md §5, git d85dd9e, "mode 4".)
-struct LnPrologue {
+// LayerNorm feeding a linear layer in the un-folded flow: A (16-bit, [rows, K]) = LayerNorm(in) (+ row statistics), a kernel of
+// its own before the GEMM. (Running it as a prologue inside the CTA-pair GEMM was built and measured slower: DESIGN.md §5.)
+struct LnBefore {
     const float* in;      // fp32 [rows, K]
     const float* gamma;
     const float* beta;
@@ -396,7 +396,7 @@ struct LnPrologue {
 
 template <typename T>
 int run_linear(tim_ctx* c, const void* A, int lda, const LinearW& w, RowMap rm, Epilogue ep, cudaStream_t s,
-               const LnPrologue* ln = nullptr) {
+               const LnBefore* ln = nullptr) {
     if (lda != w.K) return c->fail(TIM_ERR_INVALID, "linear: lda %d != K %d", lda, w.K);
     if (rm.G <= 0 || rm.R <= 0) return TIM_OK;
     if (!ep.bias) ep.bias = w.bias;
@@ -673,7 +673,7 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
             // un-folded 16-bit path: the fp32 LayerNorm output is never materialised either. x32 holds the tokens (layer 0)
             // or the pre-norm2 rows z2 of the previous layer, z the pre-norm1 rows z1; a LayerNorm kernel writes only the
             // 16-bit operand copy + (mean, rstd) per row, and the GEMM that needs LN(.) as its residual normalises on read.
-            LnPrologue lp{x32, l > 0 ? c->layers[l - 1].n2g : nullptr, l > 0 ? c->layers[l - 1].n2b : nullptr, stats};
+            LnBefore lp{x32, l > 0 ? c->layers[l - 1].n2g : nullptr, l > 0 ? c->layers[l - 1].n2b : nullptr, stats};
             TIM_TRY(run_linear<T>(c, xin, E, ly.in_proj, plain_rows(Mi), epi(qkv, 3 * E, f32), s, l > 0 ? &lp : nullptr));
         }
         // ---- attention ----
@@ -710,7 +710,7 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
             Epilogue e1 = epi(z, E, true, ACT_NONE, x32, E);
             if (l > 0) { e1.rstats = stats; e1.rgamma = c->layers[l - 1].n2g; e1.rbeta = c->layers[l - 1].n2b; }
             TIM_TRY(run_linear<T>(c, att, E, ly.out_proj, plain_rows(Mi), e1, s));
-            LnPrologue lp1{z, ly.n1g, ly.n1b, stats};
+            LnBefore lp1{z, ly.n1g, ly.n1b, stats};
             TIM_TRY(run_linear<T>(c, xin, E, ly.lin1, plain_rows(Mi), epi(hid, FF, f32, ACT_GELU), s, &lp1));
             Epilogue e2 = epi(x32, E, true, ACT_NONE, z, E);
             e2.rstats = stats; e2.rgamma = ly.n1g; e2.rbeta = ly.n1b;

@@ -28,10 +28,6 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
-// Register reallocation between warpgroups of a warp-specialised kernel (all 4 warps of an aligned warpgroup execute it).
-template <int N> __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
-template <int N> __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
-
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -62,20 +58,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05 operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-
-// cross-CTA flags in global memory (LayerNorm prologue of the CTA-pair GEMM)
-__device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void red_release_gpu_add_u32(uint32_t* p, uint32_t v) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// generic-proxy global writes (made visible by an acquire) -> ordered before this thread's later async-proxy (TMA) reads
-__device__ __forceinline__ void fence_proxy_async_global() {
-    asm volatile("fence.proxy.async.global;" ::: "memory");
 }
 
 // ------------------------------------------------------------------ TMA
@@ -240,14 +222,6 @@ template <int N> __device__ __forceinline__ void tma_store_wait() {
 }
 
 // ------------------------------------------------------------------ shared-memory accesses by 32-bit shared address
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
 __device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
