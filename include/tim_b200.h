@@ -105,6 +105,10 @@ int tim_forward_host(tim_ctx* ctx, const float* vis, const float* aud, const flo
 size_t tim_workspace_bytes(const tim_ctx* ctx);         /* bytes currently held by the context's workspace */
 uint64_t tim_launch_count(const tim_ctx* ctx);          /* kernels launched by this context so far */
 int tim_seq_len(const tim_config* cfg, int Qv, int Qa); /* S = F_tot + query tokens (pure host arithmetic) */
+/* 1 while the encoder LayerNorms are folded into the GEMMs around them (16-bit path), 0 when the
+ * un-folded flow is in use: fp32 mode, shapes the CTA-pair GEMM does not cover, TIM_B200_FOLD=0, or after the precision
+ * guard saw residual-stream rows with |mean| > 8 std in an earlier forward of this context. */
+int tim_fold_active(const tim_ctx* ctx);
 
 /* Live per-kernel-class timing (bench.py's roofline object): between begin and end every launch is bracketed by a
  * CUDA-event pair on its own stream. Classes: 0 GEMM (tcgen05 / fp32 SIMT), 1 attention, 2 LayerNorm, 3 token

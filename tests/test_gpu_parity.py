@@ -279,6 +279,32 @@ def test_patch_model_dropin(lib, name, dt):
         model.eval()(times, "no_such_forward_type")
 
 
+def test_fold_precision_guard(lib):
+    """Folded LayerNorm rounds the pre-LayerNorm rows z to 16 bits; rows whose mean dwarfs their spread would lose precision.
+    A checkpoint that produces such rows (here: +40 on every out_proj bias of layer 0, i.e. |mean| ~ 40 std) must trip the
+    guard, after which the context runs the un-folded flow and is back inside the tolerance."""
+    from oracle.tim_oracle import TIMOracle
+    from tim_b200.plugin import TIMEngine
+    cfg, sd, inp, gold, c = load_case("recog_av_small")
+    Qv, Qa = c["Qv"], c["Qa"]
+    sd = dict(sd)
+    key = f"{cfg.encoder_prefix}.layers.0.self_attn.out_proj.bias"
+    sd[key] = sd[key] + np.float32(40.0)
+    ref = TIMOracle(cfg, sd, np.float32).forward(inp["vis"], inp["aud"], inp["times"], Qv, Qa)
+    dev = torch.device("cuda", 0)
+    eng = TIMEngine(cfg, 0, "fp16")
+    eng.load_state_dict(sd)
+    assert eng.fold_active
+    vis, aud, times = (torch.from_numpy(inp[k]).to(dev) for k in ("vis", "aud", "times"))
+    for it in range(3):
+        out = eng.encoder(vis, aud, eng.time_mlp(times), Qv, Qa)
+        torch.cuda.synchronize()
+    assert not eng.fold_active                       # tripped by the first forward, honoured from the second on
+    for k in ("verb", "noun", "action", "audio", "feats"):
+        assert rel_l2(out[k].cpu().numpy(), ref[k]) <= TOL_SMALL["fp16"], k
+    eng.close()
+
+
 def test_errors_are_loud(lib):
     from tim_b200.plugin import TIMEngine
     from tim_b200._lib import TimError

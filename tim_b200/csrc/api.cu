@@ -80,6 +80,12 @@ struct tim_ctx {
     int attn_version = 2;       // 2: tcgen05 attention where the shape allows, 1: warp-MMA attention only (TIM_B200_ATTN=1)
     bool fold_ln = false;       // encoder LayerNorms folded into the GEMMs around them (16-bit path, CTA-pair kernel shapes; TIM_B200_FOLD=0 disables)
     bool fold_dirty = true;     // a weight changed since the folded copies were made
+    // precision guard of the folded path: the finalize kernel flags rows with |mean| > 8 std (relative error of the folded
+    // operand x8); the flag is copied to pinned host memory at the end of every forward and read, without a synchronisation,
+    // at the start of the next one - from then on this context takes the un-folded flow.
+    int* fold_alarm_dev = nullptr;
+    volatile int* fold_alarm_host = nullptr;
+    bool fold_tripped = false;
 
     // optional live profiling: CUDA-event pairs around every launch, accumulated per kernel class
     bool profiling = false;
@@ -348,6 +354,11 @@ int build_weights(tim_ctx* c) {
                  umma2_supported(1, E, E) && umma2_supported(1, FF, E) && umma2_supported(1, E, FF);
     if (const char* fv = std::getenv("TIM_B200_FOLD")) if (std::atoi(fv) == 0) c->fold_ln = false;
     if (c->fold_ln) {
+        TIM_TRY(dev_alloc(c, reinterpret_cast<void**>(&c->fold_alarm_dev), sizeof(int)));
+        if (cudaMemset(c->fold_alarm_dev, 0, sizeof(int)) != cudaSuccess ||
+            cudaHostAlloc(reinterpret_cast<void**>(const_cast<int**>(&c->fold_alarm_host)), sizeof(int), cudaHostAllocDefault) != cudaSuccess)
+            return c->fail(TIM_ERR_NOMEM, "fold alarm allocation failed");
+        *c->fold_alarm_host = 0;
         auto make_foldable = [&](LinearW& w) -> int {
             w.foldable = true;
             TIM_TRY(dev_alloc(c, reinterpret_cast<void**>(&w.w32), static_cast<size_t>(w.N) * w.K * sizeof(float)));
@@ -655,7 +666,12 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
     if constexpr (!f32) TIM_TRY(prepare_attention<T>(c, &attn_p, &attn_umma, qkv, att, B, Ft, Qt));
     bool folded = false;
     if constexpr (!f32) {
-        folded = c->fold_ln;
+        if (c->fold_ln && !c->fold_tripped && *c->fold_alarm_host) {
+            c->fold_tripped = true;
+            std::fprintf(stderr, "[tim_b200] rows with |mean| > 8 std seen in the residual stream: LayerNorm folding is switched off "
+                                 "for this context (un-folded LayerNorm-on-read flow from now on)\n");
+        }
+        folded = c->fold_ln && !c->fold_tripped;
         if (folded && c->fold_dirty) TIM_TRY(refold_weights<T>(c, s));
     }
     for (int l = 0; l < c->L; ++l) {
@@ -696,13 +712,13 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
             // z1 = att Wo^T + bo + LN2_prev(z2_prev)   -> z (fp32), x16 (16-bit copy), partial sums
             TIM_TRY(run_fold_gemm<T>(c, 5, ACT_NONE, att, Mi, E, E, ly.out_proj.tmB2, ly.out_proj.bias, z, x16, x32, l > 0 ? stats : nullptr,
                                      l > 0 ? c->layers[l - 1].n2g : nullptr, l > 0 ? c->layers[l - 1].n2b : nullptr, part, nullptr, s));
-            LAUNCH_C(c, 2, 0.0, s, launch_row_stats_finalize(part, static_cast<int>(nparts), E, stats, Mi, s));      // ... z1 from here on
+            LAUNCH_C(c, 2, 0.0, s, launch_row_stats_finalize(part, static_cast<int>(nparts), E, stats, Mi, 64.0f, c->fold_alarm_dev, s));   // ... z1 from here on
             // hid = gelu(LN1(z1) W1^T + b1) with norm1 folded
             TIM_TRY(run_fold_gemm<T>(c, 6, ACT_GELU, x16, Mi, FF, E, ly.lin1.tmB2f, ly.lin1.bwf, nullptr, hid, nullptr, stats, nullptr, nullptr,
                                      nullptr, ly.lin1.cs, s));
             // z2 = hid W2^T + b2 + LN1(z1)             -> x32 (fp32), x16 (16-bit copy), partial sums
             TIM_TRY(run_fold_gemm<T>(c, 5, ACT_NONE, hid, Mi, E, FF, ly.lin2.tmB2, ly.lin2.bias, x32, x16, z, stats, ly.n1g, ly.n1b, part, nullptr, s));
-            if (l < c->L - 1) LAUNCH_C(c, 2, 0.0, s, launch_row_stats_finalize(part, static_cast<int>(nparts), E, stats, Mi, s));   // z2
+            if (l < c->L - 1) LAUNCH_C(c, 2, 0.0, s, launch_row_stats_finalize(part, static_cast<int>(nparts), E, stats, Mi, 64.0f, c->fold_alarm_dev, s));   // z2
             // the last layer's norm2 feeds the heads: the only LayerNorm kernel of the stack
             if (l == c->L - 1)
                 LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(x32, E, ly.n2g, ly.n2b, nullptr, 0, x16o, E, Mi, E, s, stats));
@@ -767,6 +783,7 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
         }
     }
     if (o->feats && Mf && !feats_done) CU_OK(c, cudaMemcpyAsync(o->feats, feats_src, Mf * E * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (folded) CU_OK(c, cudaMemcpyAsync(const_cast<int*>(c->fold_alarm_host), c->fold_alarm_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
     return TIM_OK;
 }
 
@@ -881,6 +898,7 @@ void tim_destroy(tim_ctx* c) {
     cudaDeviceSynchronize();
     for (void* p : c->allocs) cudaFree(p);
     if (c->ws) cudaFree(c->ws);
+    if (c->fold_alarm_host) cudaFreeHost(const_cast<int*>(c->fold_alarm_host));
     if (c->io) cudaFree(c->io);
     for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -1117,6 +1135,10 @@ int tim_profile_end(tim_ctx* c, double* ms, double* flops, uint64_t* count, int 
 
 size_t tim_workspace_bytes(const tim_ctx* c) { return c ? c->ws_bytes + c->io_bytes : 0; }
 uint64_t tim_launch_count(const tim_ctx* c) { return c ? c->launches : 0; }
+int tim_fold_active(const tim_ctx* c) {
+    if (!c || !c->fold_ln || c->fold_tripped) return 0;
+    return (c->fold_alarm_host && *c->fold_alarm_host) ? 0 : 1;
+}
 
 }  // extern "C"
 

@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(256) cast_tail_kernel(const float* __restrict_
 // partial (sum, sum of squares); var = E[z^2] - mean^2 in fp32 (relative error ~ 6e-8 * (1 + mean^2 / var), fine for
 // residual-stream rows whose mean is far below their spread; clamped at 0).
 __global__ void __launch_bounds__(256) row_stats_finalize_kernel(const float2* __restrict__ part, int P, float inv_width,
-                                                                 float2* __restrict__ stats, int M) {
+                                                                 float2* __restrict__ stats, int M, float alarm_ratio,
+                                                                 int* __restrict__ alarm) {
     const int row = blockIdx.x * 256 + threadIdx.x;
     if (row >= M) return;
     float s = 0.0f, q = 0.0f;
@@ -217,6 +218,9 @@ __global__ void __launch_bounds__(256) row_stats_finalize_kernel(const float2* _
     const float mean = s * inv_width;
     const float var = fmaxf(q * inv_width - mean * mean, 0.0f);
     stats[row] = make_float2(mean, rsqrtf(var + 1e-5f));
+    // the folded path rounds z, not LN(z), to 16 bits: its relative error grows with sqrt(1 + mean^2 / var). Rows whose mean
+    // dwarfs their spread raise a flag; the host side then takes the un-folded flow from the next call on (api.cu).
+    if (alarm && mean * mean > alarm_ratio * (var + 1e-5f)) *alarm = 1;
 }
 
 // Folding a LayerNorm's affine into the weight of the linear layer that follows it (one warp per output row n):
@@ -341,9 +345,10 @@ cudaError_t launch_scale_copy(const float* in, float* out, size_t rows, size_t c
     return cudaGetLastError();
 }
 
-cudaError_t launch_row_stats_finalize(const float2* part, int P, int width, float2* stats, int M, cudaStream_t s) {
+cudaError_t launch_row_stats_finalize(const float2* part, int P, int width, float2* stats, int M, float alarm_ratio, int* alarm,
+                                      cudaStream_t s) {
     if (M <= 0) return cudaSuccess;
-    row_stats_finalize_kernel<<<(M + 255) / 256, 256, 0, s>>>(part, P, 1.0f / static_cast<float>(width), stats, M);
+    row_stats_finalize_kernel<<<(M + 255) / 256, 256, 0, s>>>(part, P, 1.0f / static_cast<float>(width), stats, M, alarm_ratio, alarm);
     return cudaGetLastError();
 }
 

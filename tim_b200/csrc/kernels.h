@@ -156,8 +156,10 @@ cudaError_t launch_cast(const float* in, T* out, size_t rows, size_t cols, size_
 cudaError_t launch_scale_copy(const float* in, float* out, size_t rows, size_t cols, size_t scale_rows, float scale,
                               cudaStream_t s);
 
-// (mean, rstd) per row from the partial sums a mode-5 GEMM wrote: part [P][M] (sum, sum of squares), width columns in total
-cudaError_t launch_row_stats_finalize(const float2* part, int P, int width, float2* stats, int M, cudaStream_t s);
+// (mean, rstd) per row from the partial sums a mode-5 GEMM wrote: part [P][M] (sum, sum of squares), width columns in total;
+// *alarm (device int, optional) is set when some row has mean^2 > alarm_ratio * var
+cudaError_t launch_row_stats_finalize(const float2* part, int P, int width, float2* stats, int M, float alarm_ratio, int* alarm,
+                                      cudaStream_t s);
 
 // LayerNorm affine folded into the following linear layer's weight (see fold_ln_kernel); W, bias: fp32 masters
 template <typename T>

@@ -188,6 +188,11 @@ class TIMEngine:
         return int(self.lib.tim_launch_count(self._ctx))
 
     @property
+    def fold_active(self) -> bool:
+        """True while the encoder LayerNorms run folded into the GEMMs (see tim_fold_active in include/tim_b200.h)."""
+        return bool(self.lib.tim_fold_active(self._ctx))
+
+    @property
     def workspace_bytes(self) -> int:
         return int(self.lib.tim_workspace_bytes(self._ctx))
 
