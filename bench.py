@@ -147,6 +147,11 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the TIM forward has no CPU path (use --impl reference for the CPU arm)")
+    # stdout carries exactly ONE JSON line: anything a library prints there (NCCL's version banner does) goes to stderr
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    from tim_b200.dist import bind_to_gpu_numa_node
+    numa_node = bind_to_gpu_numa_node(local_rank)       # before any pinned allocation
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -265,7 +270,7 @@ def main():
     e2e_s = max_ranks((time.perf_counter() - t0) / e2e_steps)
     barrier()
     e2e = {"value": world * B * (Qv + Qa) / e2e_s, "unit": UNIT, "h2d_bytes_per_step": up, "d2h_bytes_per_step": down,
-           "ms_per_step": e2e_s * 1e3, "clips_per_chunk": chunk,
+           "ms_per_step": e2e_s * 1e3, "clips_per_chunk": chunk, "host_numa_node_of_rank0": numa_node,
            "d2h": "logits / regression outputs (what the reference eval loop reads, test.py:106-131); feature rows stay on device",
            "timing": "host wall clock around the blocking plugin call (outputs are in pinned host memory when it returns), "
                      "device synchronised on both sides, max over ranks"}
@@ -285,7 +290,7 @@ def main():
                            "weights": "synthetic trained-like (tim_b200.synth)"},
                 "clips_per_sec": world * B / (ms * 1e-3), "tokens_per_sec": world * B * cfg.seq_len(Qv, Qa) / (ms * 1e-3),
                 "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cb, "clocks": clocks, "parity": parity}
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     eng.close()
     if world > 1:
         dist.destroy_process_group()

@@ -4,10 +4,34 @@ collectives here are the timing / result-gathering ones used by bench.py and the
 DistributedSampler split (datasets/loader.py:48-50) and utils/distributed.py:15-53 helpers."""
 from __future__ import annotations
 
-from typing import Tuple
+import os
+from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist
+
+
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Pin this process (one per GPU) to the CPUs of the NUMA node its GPU hangs off, BEFORE it allocates pinned host
+    buffers: with 8 ranks streaming inputs / results over PCIe at once, buffers first-touched on the other socket push
+    every copy through the inter-socket link. Returns the node, or None when the topology cannot be read (no-op then)."""
+    try:
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
 
 
 def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
