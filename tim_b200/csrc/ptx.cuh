@@ -169,8 +169,12 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {   // arrive on a (possibly remote) barrier
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// Arrive on a (possibly remote) barrier. Default semantics (release at CTA scope), as CUTLASS' ClusterBarrier::arrive does:
+// the only thing published through these barriers is "my tcgen05.ld reads of the accumulator are done", which the preceding
+// tcgen05.fence::before_thread_sync orders; the cluster-scope release used before cost a MEMBAR + ERRBAR per tile and warp
+// (15-20 % of the epilogue warps' stall samples in profiles/r01e_ncu_full_linear_umma2).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // 2-CTA TMA load: data lands in this CTA's smem, the transaction bytes are signalled on `bar` (a shared::cluster
 // address, normally the leader CTA's full barrier)
