@@ -110,6 +110,19 @@ int tim_seq_len(const tim_config* cfg, int Qv, int Qa); /* S = F_tot + query tok
  * guard saw residual-stream rows with |mean| > 8 std in an earlier forward of this context. */
 int tim_fold_active(const tim_ctx* ctx);
 
+/* Detection query labelling (detection/time_interval_machine/models/tim.py:186-270 get_query_ious + label_queries): for every
+ * query [B, Nq, 2] the ground-truth segment [B, Na, 2] of maximal IoU (first maximum; computed after the reference's shift by
+ * |min(min_a start, 0)|, which is also applied to the returned segment), its labels gt_labels [B, Na, Nl] and the IoU. Queries
+ * with IoU < iou_threshold get targets = +inf and label ids = -1. All pointers are device pointers; results are bit-identical
+ * to the reference's fp32 arithmetic. Stateless: errors are reported through tim_last_error(NULL). */
+int tim_label_queries(const float* queries, const float* gt_segs, const int64_t* gt_labels, int B, int Nq, int Na, int Nl,
+                      float iou_threshold, float* targets /*[B*Nq,2]*/, int64_t* label_ids /*[B*Nq,Nl]*/, float* ious /*[B*Nq]*/,
+                      void* stream);
+/* assign_positive_labels (tim.py:158-185): out[row, c] = one_hot(id, C + 1)[c] * smoothing + (1 - smoothing) / (C + 1) for
+ * c < C = num_classes, id = label_ids[row * stride + col] with -1 mapped to the dropped class C. out is [rows, C] fp32. */
+int tim_smooth_labels(const int64_t* label_ids, int stride, int col, int64_t rows, int num_classes, double smoothing, float* out,
+                      void* stream);
+
 /* Live per-kernel-class timing (bench.py's roofline object): between begin and end every launch is bracketed by a
  * CUDA-event pair on its own stream. Classes: 0 GEMM (tcgen05 / fp32 SIMT), 1 attention, 2 LayerNorm, 3 token
  * assembly, 4 other row kernels. end() synchronises the device and fills ms / algorithmic FLOPs / launch counts. */

@@ -44,6 +44,7 @@ class FakeTIM(nn.Module):
         if cfg.variant == DETECTION:
             assert hasattr(self, "backbone")
             self.iou_threshold = 0.25
+            self.label_smoothing = 0.9
             self.inference_queries = torch.zeros(1, 0, 2)
 
     def label_queries(self, queries, target, modality, thr):           # target prep stays reference code; unused here

@@ -279,6 +279,78 @@ def test_patch_model_dropin(lib, name, dt):
         model.eval()(times, "no_such_forward_type")
 
 
+@pytest.mark.parametrize("name", ["vn", "act", "aud"])
+def test_label_queries_kernel(lib, name):
+    """tim_label_queries / tim_smooth_labels against the reference's own outputs (golden) - bit-exact (index and fp32 work in
+    the reference's operation order) - and against the oracle on a larger seeded case with NaN / tie / all-negative rows."""
+    from oracle.label_oracle import label_queries, smooth_labels
+    from tests.test_oracle_golden import GOLD, LABEL_CASES
+    from tim_b200.plugin import TIMEngine
+    import os
+    g = np.load(os.path.join(GOLD, "label_queries.npz"))
+    cfg, _, _ = named_config("cfg1")
+    eng = TIMEngine(cfg, 0, "fp32")
+    dev = torch.device("cuda", 0)
+    thr, sm = g[f"{name}_meta"]
+    t, ids, iou = eng.label_queries(torch.from_numpy(g[f"{name}_queries"]).to(dev), torch.from_numpy(g[f"{name}_gt"]).to(dev),
+                                    torch.from_numpy(g[f"{name}_labels"]).to(dev), float(thr))
+    assert np.array_equal(t.cpu().numpy(), g[f"{name}_targets"])
+    assert np.array_equal(iou.cpu().numpy(), g[f"{name}_ious"], equal_nan=True)
+    for k, C_ in enumerate(LABEL_CASES[name]):
+        if C_ is not None:
+            col = k if name != "aud" else 0
+            assert np.array_equal(eng.smooth_labels(ids, col, C_, float(sm)).cpu().numpy(), g[f"{name}_smooth{k}"])
+    # larger seeded case: 2048 queries (cfg4), zero-length queries against zero-length segments (0/0 = NaN), duplicates, far misses
+    rng = np.random.default_rng(11)
+    B, Nq, Na, Nl = 5, 2048, 23, 3
+    st = rng.uniform(-0.1, 0.9, (B, Nq)).astype(np.float32)
+    q = np.stack([st, st + rng.uniform(0.0, 0.3, (B, Nq)).astype(np.float32)], -1)
+    gs = rng.uniform(-0.3, 0.8, (B, Na)).astype(np.float32)
+    gt = np.stack([gs, gs + rng.uniform(0.0, 0.4, (B, Na)).astype(np.float32)], -1)
+    gt[:, -3:] = 0.0
+    q[:, :7] = 0.0
+    gt[2, 5] = gt[2, 4]
+    q[3, 100:110] = gt[3, 2]
+    lab = rng.integers(0, 97, (B, Na, Nl)).astype(np.int64)
+    t, ids, iou = eng.label_queries(torch.from_numpy(q).to(dev), torch.from_numpy(gt).to(dev), torch.from_numpy(lab).to(dev), 0.25)
+    rt, rids, riou = label_queries(q, gt, lab, 0.25)
+    assert np.array_equal(t.cpu().numpy(), rt) and np.array_equal(ids.cpu().numpy(), rids)
+    assert np.array_equal(iou.cpu().numpy(), riou, equal_nan=True)
+    assert np.array_equal(eng.smooth_labels(ids, 2, 97, 0.9).cpu().numpy(), smooth_labels(rids[:, 2], 97, 0.9))
+    eng.close()
+
+
+def test_patch_model_detection_labels(lib):
+    """detection forward with label_queries=True (detection/scripts/test.py:120-126): the patched forward labels the queries on
+    the device and returns the reference's structure ((offsets), (labels), (queries), (ious))."""
+    from oracle.label_oracle import label_queries, smooth_labels
+    from tests._fake_tim import FakeTIM
+    from tim_b200.plugin import patch_model
+    cfg, sd, inp, gold, c = load_case("det_visual")
+    Qv = c["Qv"]
+    dev = torch.device("cuda", 0)
+    model = patch_model(FakeTIM(cfg, sd).to(dev).eval(), compute_dtype="fp16")
+    times = torch.from_numpy(inp["times"]).to(dev)
+    B = times.shape[0]
+    model.inference_queries = times[:1, cfg.F_tot:cfg.F_tot + Qv].clone()
+    rng = np.random.default_rng(3)
+    Na = 4
+    gs = rng.uniform(0.0, 0.8, (B, Na)).astype(np.float32)
+    gt = np.stack([gs, gs + rng.uniform(0.05, 0.3, (B, Na)).astype(np.float32)], -1)
+    lab = rng.integers(0, 9, (B, Na, 3)).astype(np.int64)
+    target = {"v_gt_segments": torch.from_numpy(gt).to(dev), "verb": torch.from_numpy(lab[..., 0]).to(dev),
+              "noun": torch.from_numpy(lab[..., 1]).to(dev), "action": torch.from_numpy(lab[..., 2]).to(dev)}
+    with torch.no_grad():
+        outs, offs, labels, queries, ious = model([torch.from_numpy(inp["vis"]).to(dev), torch.from_numpy(inp["aud"]).to(dev)],
+                                                  "encoder", times[:, :cfg.F_tot], target, True)
+    q = model.inference_queries.repeat(B, 1, 1).cpu().numpy()
+    rt, rids, riou = label_queries(q, gt, lab, model.iou_threshold)
+    assert np.array_equal(offs[0].cpu().numpy(), rt) and np.array_equal(ious[0].cpu().numpy(), riou, equal_nan=True)
+    assert labels[0][0].numel() == 0 and labels[0][1].numel() == 0               # include_verb_noun=False: empty verb / noun labels
+    assert np.array_equal(labels[0][2].cpu().numpy(), smooth_labels(rids[:, 2], cfg.num_class[0], model.label_smoothing))
+    assert outs[0][2].shape == (B * Qv, cfg.num_class[0]) and queries[0].shape == (B * Qv, 2)
+
+
 def test_fold_precision_guard(lib):
     """Folded LayerNorm rounds the pre-LayerNorm rows z to 16 bits; rows whose mean dwarfs their spread would lose precision.
     A checkpoint that produces such rows (here: +40 on every out_proj bias of layer 0, i.e. |mean| ~ 40 std) must trip the

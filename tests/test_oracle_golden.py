@@ -99,3 +99,25 @@ def test_flop_formula_matches_survey():
     assert abs(cfg3.flops_fwd_per_clip(Qv, Qa) / 1e9 - 123.7) < 0.5
     cfg4, Qv, Qa = named_config("cfg4")
     assert abs(cfg4.flops_fwd_per_clip(Qv, Qa) / 1e9 - 227.7) < 0.5
+
+
+# ---------------------------------------------------------------- detection query labelling
+LABEL_CASES = {"vn": [5, 7, 11], "act": [None, None, 9], "aud": [4]}
+
+
+@pytest.mark.parametrize("name", sorted(LABEL_CASES))
+def test_label_oracle_matches_reference_golden(name):
+    """oracle/label_oracle.py against the outputs of the reference's label_queries / assign_positive_labels
+    (tests/golden/label_queries.npz, minted by tools/make_golden_labels.py): bit-exact, NaN-aware."""
+    from oracle.label_oracle import label_queries, smooth_labels
+    g = np.load(os.path.join(GOLD, "label_queries.npz"))
+    thr, sm = g[f"{name}_meta"]
+    t, ids, iou = label_queries(g[f"{name}_queries"], g[f"{name}_gt"], g[f"{name}_labels"], thr)
+    assert np.array_equal(t, g[f"{name}_targets"])
+    assert np.array_equal(iou, g[f"{name}_ious"], equal_nan=True)
+    for k, C_ in enumerate(LABEL_CASES[name]):
+        ref = g[f"{name}_smooth{k}"]
+        if C_ is None:
+            assert ref.size == 0
+            continue
+        assert np.array_equal(smooth_labels(ids[:, k if name != "aud" else 0], C_, sm), ref)

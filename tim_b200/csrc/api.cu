@@ -20,6 +20,12 @@ namespace {
 
 thread_local std::string g_create_error;
 
+}  // namespace
+namespace tim {
+void set_global_error(const char* msg) { g_create_error = msg ? msg : ""; }
+}  // namespace tim
+namespace {
+
 struct LinearW {
     int N = 0, K = 0;
     void* w = nullptr;          // [N, K] in the compute dtype

@@ -9,6 +9,9 @@
 
 namespace tim {
 
+// message returned by tim_last_error(NULL) (entry points without a context; defined in api.cu)
+void set_global_error(const char* msg);
+
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 
 // How the rows of a linear layer's A operand / output are laid out.

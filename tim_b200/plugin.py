@@ -171,6 +171,33 @@ class TIMEngine:
                                                  C.byref(up), C.byref(down)), self._ctx)
         return outs, int(up.value), int(down.value)
 
+    # ------------------------------------------------------------------ detection query labelling
+    def label_queries(self, queries: torch.Tensor, gt_segs: torch.Tensor, gt_labels: torch.Tensor, iou_threshold: float):
+        """detection/.../models/tim.py:186-270 on the device: (targets [B*Nq,2], label ids [B*Nq,Nl] (-1 = negative), ious [B*Nq])."""
+        q = queries.to(device=self.device, dtype=torch.float32).contiguous()
+        g = gt_segs.to(device=self.device, dtype=torch.float32).contiguous()
+        lab = gt_labels.to(device=self.device, dtype=torch.int64).contiguous()
+        B, Nq, Na, Nl = int(q.shape[0]), int(q.shape[1]), int(g.shape[1]), int(lab.shape[2])
+        if q.shape != (B, Nq, 2) or g.shape != (B, Na, 2) or lab.shape != (B, Na, Nl):
+            raise ValueError("label_queries: queries [B,Nq,2], gt_segs [B,Na,2], gt_labels [B,Na,Nl] expected")
+        with torch.cuda.device(self.device):
+            targets = torch.empty((B * Nq, 2), dtype=torch.float32, device=self.device)
+            ids = torch.empty((B * Nq, Nl), dtype=torch.int64, device=self.device)
+            ious = torch.empty((B * Nq,), dtype=torch.float32, device=self.device)
+            _lib.check(self.lib.tim_label_queries(_ptr(q), _ptr(g), _ptr(lab), B, Nq, Na, Nl, float(iou_threshold), _ptr(targets),
+                                                  _ptr(ids), _ptr(ious), self._stream()), None)
+        return targets, ids, ious
+
+    def smooth_labels(self, ids: torch.Tensor, col: int, num_classes: int, smoothing: float) -> torch.Tensor:
+        """assign_positive_labels (tim.py:158-185) for one label column: [rows, num_classes] fp32."""
+        rows, stride = int(ids.shape[0]), int(ids.shape[1])
+        with torch.cuda.device(self.device):
+            out = torch.empty((rows, num_classes), dtype=torch.float32, device=self.device)
+            if rows:
+                _lib.check(self.lib.tim_smooth_labels(_ptr(ids), stride, int(col), rows, int(num_classes), float(smoothing), _ptr(out),
+                                                      self._stream()), None)
+        return out
+
     PROFILE_CLASSES = ("gemm", "attention", "layernorm", "assemble", "other")
 
     def profile_begin(self) -> None:
@@ -250,6 +277,30 @@ def _forward_recognition(self, inputs, forward_type, time_encodings=None, num_v_
     raise ValueError(f"unknown forward_type {forward_type!r}")
 
 
+def _label_queries_device(model, engine: "TIMEngine", queries, target, modality):
+    """label_queries + assign_positive_labels of the reference (detection/.../models/tim.py:158-270) through the library: same
+    inputs (the target dict of the data loader), same return structure."""
+    dev = queries.device
+    if modality == "visual":
+        segs = target["v_gt_segments"]
+        labels = torch.stack([target["verb"], target["noun"], target["action"]], dim=-1)
+    else:
+        segs = target["a_gt_segments"]
+        labels = target["class_id"].unsqueeze(-1)
+    targets, ids, ious = engine.label_queries(queries, segs, labels, model.iou_threshold)
+    s = model.label_smoothing
+    if modality == "visual":
+        verb = noun = torch.empty(size=(0,), device=dev)
+        n_act = model.num_class[0]
+        if model.include_verb_noun:
+            n_verb, n_noun, n_act = model.num_class[0][0], model.num_class[0][1], model.num_class[0][2]
+            verb, noun = engine.smooth_labels(ids, 0, n_verb, s), engine.smooth_labels(ids, 1, n_noun, s)
+        query_labels = [verb, noun, engine.smooth_labels(ids, 2, n_act, s)]
+    else:
+        query_labels = engine.smooth_labels(ids, ids.shape[1] - 1, model.num_class[1], s)
+    return targets, query_labels, ious
+
+
 def _forward_detection(self, inputs, forward_type, feature_times=None, target=None, label_queries=False):
     """Same signature / returns as detection/.../models/tim.py:415-430 (inference branch :339-400)."""
     b: _Binding = self._tim_b200
@@ -271,15 +322,15 @@ def _forward_detection(self, inputs, forward_type, feature_times=None, target=No
     if "visual" in cfg.data_modality:
         v_queries = self.inference_queries.repeat(B, 1, 1).to(device=dev)
         nv = v_queries.shape[1]
-        if label_queries:                                  # target prep stays in the reference's own PyTorch code
-            v_offsets, v_labels, v_ious = self.label_queries(v_queries, target, "visual", self.iou_threshold)
+        if label_queries:                                  # IoU / arg-max / smoothed labels on the device (labels.cu)
+            v_offsets, v_labels, v_ious = _label_queries_device(self, b.engine, v_queries, target, "visual")
         all_times = torch.cat([all_times, v_queries], dim=1)
         v_queries = torch.flatten(v_queries, 0, 1)
     if "audio" in cfg.data_modality:
         a_queries = self.inference_queries.repeat(B, 1, 1).to(device=dev)
         na = a_queries.shape[1]
         if label_queries:
-            a_offsets, a_labels, a_ious = self.label_queries(a_queries, target, "audio", self.iou_threshold)
+            a_offsets, a_labels, a_ious = _label_queries_device(self, b.engine, a_queries, target, "audio")
         all_times = torch.cat([all_times, a_queries], dim=1)
         a_queries = torch.flatten(a_queries, 0, 1)
     te = b.engine.time_mlp(all_times)
