@@ -351,6 +351,27 @@ def test_patch_model_detection_labels(lib):
     assert outs[0][2].shape == (B * Qv, cfg.num_class[0]) and queries[0].shape == (B * Qv, 2)
 
 
+def test_two_devices_in_one_process(lib):
+    """The usual deployment is one process per GPU, but nothing may break when one process owns contexts on two devices
+    (kernel attributes such as the dynamic shared-memory limit are per device)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cfg, sd, inp, gold, c = load_case("recog_av_small")
+    from tim_b200.plugin import TIMEngine
+    outs = []
+    for d in (1, 0):                                      # device 1 first: its attributes must not rely on device 0's
+        dev = torch.device("cuda", d)
+        eng = TIMEngine(cfg, d, "fp16")
+        eng.load_state_dict(sd)
+        te = eng.time_mlp(torch.from_numpy(inp["times"]).to(dev))
+        o = eng.encoder(torch.from_numpy(inp["vis"]).to(dev), torch.from_numpy(inp["aud"]).to(dev), te, c["Qv"], c["Qa"])
+        torch.cuda.synchronize(dev)
+        outs.append({k: v.cpu() for k, v in o.items() if v is not None})
+        eng.close()
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
+
+
 def test_fold_precision_guard(lib):
     """Folded LayerNorm rounds the pre-LayerNorm rows z to 16 bits; rows whose mean dwarfs their spread would lose precision.
     A checkpoint that produces such rows (here: +40 on every out_proj bias of layer 0, i.e. |mean| ~ 40 std) must trip the

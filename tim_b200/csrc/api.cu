@@ -1051,12 +1051,15 @@ int tim_forward_host(tim_ctx* c, const float* vis, const float* aud, const float
         for (int n : tail) { chunk_b0.push_back(b0); chunk_nb.push_back(n); b0 += n; }
     }
     const int nchunks = static_cast<int>(chunk_nb.size());
-    std::vector<cudaEvent_t> ev_in(nchunks), ev_comp(nchunks), ev_out(nchunks);
-    for (int i = 0; i < nchunks; ++i) {
-        CU_OK(c, cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
-        CU_OK(c, cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming));
-        CU_OK(c, cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
-    }
+    struct EventSet {                                   // destroyed on every exit path
+        std::vector<cudaEvent_t> ev;
+        ~EventSet() { for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e); }
+    } events;
+    events.ev.assign(3 * static_cast<size_t>(nchunks), nullptr);
+    cudaEvent_t* ev_in = events.ev.data();
+    cudaEvent_t* ev_comp = ev_in + nchunks;
+    cudaEvent_t* ev_out = ev_comp + nchunks;
+    for (int i = 0; i < 3 * nchunks; ++i) CU_OK(c, cudaEventCreateWithFlags(&events.ev[i], cudaEventDisableTiming));
     uint64_t up = 0, down = 0;
     int rc = TIM_OK;
     auto h2d = [&](float* dst, const float* src, size_t n) -> cudaError_t {
@@ -1102,7 +1105,6 @@ int tim_forward_host(tim_ctx* c, const float* vis, const float* aud, const float
         CU_OK(c, cudaEventRecord(ev_out[i], c->s_d2h));
     }
     cudaError_t e1 = cudaStreamSynchronize(c->s_h2d), e2 = cudaStreamSynchronize(c->s_comp), e3 = cudaStreamSynchronize(c->s_d2h);
-    for (int i = 0; i < nchunks; ++i) { cudaEventDestroy(ev_in[i]); cudaEventDestroy(ev_comp[i]); cudaEventDestroy(ev_out[i]); }
     if (rc != TIM_OK) return rc;
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
         return c->fail(TIM_ERR_CUDA, "tim_forward_host: stream sync failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));

@@ -229,12 +229,8 @@ cudaError_t launch_attn_hd(const T* qkv, T* out, int B, int Ft, int Qt, int H, c
     const int Fp = (Ft + 15) & ~15;
     const size_t smem = static_cast<size_t>(2 * Fp + 3 * AT_BM) * HD * 2;
     auto kern = attention_mma_kernel<T, HD>;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) return e;
-        smem_set = smem;
-    }
+    static SmemAttrCache cache;
+    if (cudaError_t e = ensure_dynamic_smem(kern, smem, cache); e != cudaSuccess) return e;
     const int tiles_f = (Ft + AT_BM - 1) / AT_BM, tiles_q = (Qt + AT_BM - 1) / AT_BM;
     const int tiles = tiles_f + tiles_q;
     // split an item's tiles over several CTAs only when (clip, head) items alone cannot fill the machine
@@ -345,12 +341,8 @@ size_t attention_simt_smem(int Ft, int hd) {
 cudaError_t launch_attention_simt(const float* qkv, float* out, int B, int Ft, int Qt, int H, int hd, cudaStream_t s) {
     const size_t smem = attention_simt_smem(Ft, hd);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(attention_simt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) return e;
-        smem_set = smem;
-    }
+    static SmemAttrCache cache;
+    if (cudaError_t e = ensure_dynamic_smem(attention_simt_kernel, smem, cache); e != cudaSuccess) return e;
     const int tiles_f = (Ft + AS_ROWS - 1) / AS_ROWS, tiles_q = (Qt + AS_ROWS - 1) / AS_ROWS;
     dim3 grid(tiles_f + tiles_q, H, B);
     attention_simt_kernel<<<grid, AS_WARPS * 32, smem, s>>>(qkv, out, B, Ft, Qt, H, hd, tiles_f);

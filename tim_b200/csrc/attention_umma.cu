@@ -456,12 +456,8 @@ template <typename T, int HD>
 cudaError_t launch_hd(const AttnUmmaParams& p, int num_sms, cudaStream_t s) {
     const size_t smem = smem_for<HD>(p.Fp);
     auto kern = attention_umma_kernel<T, HD>;
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        if (e != cudaSuccess) return e;
-        smem_set = smem;
-    }
+    static SmemAttrCache cache;
+    if (cudaError_t e = ensure_dynamic_smem(kern, smem, cache); e != cudaSuccess) return e;
     const int grid = p.num_units < num_sms ? p.num_units : num_sms;
     kern<<<grid, AU_THREADS, smem, s>>>(p);
     return cudaGetLastError();

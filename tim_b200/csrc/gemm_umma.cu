@@ -238,12 +238,8 @@ template <typename T, int BLOCK_N>
 cudaError_t launch_one(const UmmaParams& p, int num_sms, cudaStream_t s) {
     using C = Cfg<BLOCK_N>;
     auto kern = linear_umma_kernel<T, BLOCK_N>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static SmemAttrCache cache;
+    if (cudaError_t e = ensure_dynamic_smem(kern, C::SMEM_BYTES, cache); e != cudaSuccess) return e;
     const int tiles = p.tiles_m * p.tiles_n;
     if (tiles <= 0) return cudaSuccess;
     const int grid = tiles < num_sms ? tiles : num_sms;

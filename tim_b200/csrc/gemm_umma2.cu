@@ -336,12 +336,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
 template <typename T, int MODE, int ACT>
 cudaError_t launch_mode(const Umma2Params& p, int num_sms, cudaStream_t s) {
     auto kern = linear_umma2_kernel<T, MODE, ACT>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    static SmemAttrCache cache;
+    if (cudaError_t e = ensure_dynamic_smem(kern, SMEM_BYTES, cache); e != cudaSuccess) return e;
     const int tiles = p.tiles_m * p.tiles_n;
     if (tiles <= 0) return cudaSuccess;
     int clusters = num_sms / 2;

@@ -14,6 +14,23 @@ void set_global_error(const char* msg);
 
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: remember the largest size requested per device, so a
+// process that drives several GPUs (several contexts) sets it on each of them.
+struct SmemAttrCache { size_t set[64] = {}; };
+template <typename K>
+inline cudaError_t ensure_dynamic_smem(K kern, size_t bytes, SmemAttrCache& cache) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+    if (bytes > cache.set[dev]) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+        if (e != cudaSuccess) return e;
+        cache.set[dev] = bytes;
+    }
+    return cudaSuccess;
+}
+
 // How the rows of a linear layer's A operand / output are laid out.
 // Logical rows are (group g, row r), g < G, r < R. One tile covers box_g groups x box_r rows (<= 128 rows).
 //   A row in memory   : g * a_group_rows + a_row_off + r      (SIMT path; the UMMA path bakes this into a 3-D tensor map
