@@ -235,7 +235,11 @@ def main():
     pk = peaks()
     gemm = prof["gemm"]
     gemm_tflops = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] > 0 else 0.0
-    total_prof_ms = sum(c["ms"] for c in prof.values())
+    kinds = ("gemm_in_proj_linear1", "gemm_out_proj_linear2", "gemm_other")
+    total_prof_ms = sum(c["ms"] for k, c in prof.items() if k != "gemm")
+    by_kind = {k: {"tflops": prof[k]["flops"] / (prof[k]["ms"] * 1e-3) / 1e12 if prof[k]["ms"] > 0 else 0.0,
+                   "frac": prof[k]["flops"] / (prof[k]["ms"] * 1e-3) / 1e12 / pk["tflops"] if prof[k]["ms"] > 0 else 0.0,
+                   "ms_per_step": prof[k]["ms"] / args.steps, "launches_per_step": prof[k]["launches"] // args.steps} for k in kinds}
     traffic, traffic_note = None, None
     tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     if os.path.exists(tp):
@@ -247,7 +251,8 @@ def main():
                 "traffic": traffic, "traffic_note": traffic_note, "peak_source": pk["source"],
                 "launches_per_step": gemm["launches"] // args.steps, "avg_launch_ms": gemm["ms"] / max(1, gemm["launches"]),
                 "share_of_step": gemm["ms"] / total_prof_ms if total_prof_ms else None,
-                "class_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items()},
+                "class_ms_per_step": {k: v["ms"] / args.steps for k, v in prof.items() if k not in kinds},
+                "by_gemm_kind": by_kind,
                 "path_tflops": cfg.flops_fwd_per_clip(Qv, Qa) * B / (ms * 1e-3) / 1e12,
                 "path_frac": cfg.flops_fwd_per_clip(Qv, Qa) * B / (ms * 1e-3) / 1e12 / pk["tflops"]}
 

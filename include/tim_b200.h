@@ -124,9 +124,11 @@ int tim_smooth_labels(const int64_t* label_ids, int stride, int col, int64_t row
                       void* stream);
 
 /* Live per-kernel-class timing (bench.py's roofline object): between begin and end every launch is bracketed by a
- * CUDA-event pair on its own stream. Classes: 0 GEMM (tcgen05 / fp32 SIMT), 1 attention, 2 LayerNorm, 3 token
- * assembly, 4 other row kernels. end() synchronises the device and fills ms / algorithmic FLOPs / launch counts. */
-#define TIM_PROFILE_CLASSES 5
+ * CUDA-event pair on its own stream. Classes: 0 GEMM (tcgen05 / fp32 SIMT) other than 5 and 6, 1 attention, 2 LayerNorm /
+ * row statistics, 3 token assembly, 4 other row kernels, 5 encoder GEMMs with a folded LayerNorm in front (in_proj, linear1:
+ * tensor-bound), 6 encoder GEMMs that also write the residual stream (out_proj, linear2: 12 - 14 KB of HBM traffic per row).
+ * end() synchronises the device and fills ms / algorithmic FLOPs / launch counts. */
+#define TIM_PROFILE_CLASSES 7
 int tim_profile_begin(tim_ctx* ctx);
 int tim_profile_end(tim_ctx* ctx, double* ms, double* flops, uint64_t* count, int n_classes);
 

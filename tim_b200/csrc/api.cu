@@ -148,7 +148,8 @@ cudaEvent_t prof_event(tim_ctx* c) {
             return (ctx)->fail(TIM_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
     } while (0)
 
-// kernel classes for tim_profile_*: 0 tcgen05/SIMT GEMM, 1 attention, 2 LayerNorm, 3 token assembly, 4 other row kernels
+// kernel classes for tim_profile_*: 0 tcgen05/SIMT GEMM, 1 attention, 2 LayerNorm, 3 token assembly, 4 other row kernels,
+// 5 folded-LayerNorm consumer GEMMs (in_proj, linear1), 6 producer GEMMs (out_proj, linear2)
 #define LAUNCH_C(ctx, cls_, flops_, stream_, expr)                                                         \
     do {                                                                                                   \
         tim_ctx::ProfRec _pr;                                                                              \
@@ -541,7 +542,7 @@ int run_fold_gemm(tim_ctx* c, int mode, int act, const void* A, int M, int N, in
     }
     q.bias = bias; q.M = M; q.N = N; q.K = K;
     q.rstats = rstats; q.rgamma = rgamma; q.rbeta = rbeta; q.opart = opart; q.cs = cs;
-    LAUNCH_C(c, 0, 2.0 * M * N * K, s, launch_linear_umma2<T>(q, mode, act, c->num_sms, s));
+    LAUNCH_C(c, mode == 6 ? 5 : 6, 2.0 * M * N * K, s, launch_linear_umma2<T>(q, mode, act, c->num_sms, s));
     return TIM_OK;
 }
 

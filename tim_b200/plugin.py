@@ -198,7 +198,7 @@ class TIMEngine:
                                                       self._stream()), None)
         return out
 
-    PROFILE_CLASSES = ("gemm", "attention", "layernorm", "assemble", "other")
+    PROFILE_CLASSES = ("gemm_other", "attention", "layernorm", "assemble", "other", "gemm_in_proj_linear1", "gemm_out_proj_linear2")
 
     def profile_begin(self) -> None:
         _lib.check(self.lib.tim_profile_begin(self._ctx), self._ctx)
@@ -208,7 +208,11 @@ class TIMEngine:
         n = len(self.PROFILE_CLASSES)
         ms, fl, cnt = (C.c_double * n)(), (C.c_double * n)(), (C.c_uint64 * n)()
         _lib.check(self.lib.tim_profile_end(self._ctx, ms, fl, cnt, n), self._ctx)
-        return {name: {"ms": ms[i], "flops": fl[i], "launches": int(cnt[i])} for i, name in enumerate(self.PROFILE_CLASSES)}
+        out = {name: {"ms": ms[i], "flops": fl[i], "launches": int(cnt[i])} for i, name in enumerate(self.PROFILE_CLASSES)}
+        # "gemm" = every dense contraction of the step (the three GEMM classes together)
+        parts = [out[k] for k in ("gemm_other", "gemm_in_proj_linear1", "gemm_out_proj_linear2")]
+        out["gemm"] = {k: sum(p[k] for p in parts) for k in ("ms", "flops", "launches")}
+        return out
 
     @property
     def launch_count(self) -> int:
