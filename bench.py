@@ -280,6 +280,52 @@ def main():
            "timing": "host wall clock around the blocking plugin call (outputs are in pinned host memory when it returns), "
                      "device synchronised on both sides, max over ranks"}
 
+    # ---- the same end-to-end metric with the feature bank resident in HBM: the reference caches every
+    # feature of the dataset in host RAM and gathers each clip's window on the host; with the bank on the device only the row
+    # indices and interval times of a step cross PCIe (H2D), the logits still come back (D2H). Reported NEXT TO `e2e`, not as it.
+    e2e_bank = None
+    if cfg.has_visual_input and cfg.has_audio_input:
+        vbank, abank = vis.reshape(B * F, -1), aud.reshape(B * F, -1)
+        perm = torch.stack([torch.randperm(B * F, generator=torch.Generator().manual_seed(7 + i)) for i in range(2)])
+        hvr = perm[0].view(B, F).contiguous().pin_memory()
+        har = perm[1].view(B, F).contiguous().pin_memory()
+        s_comp, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        hres = {k: v for k, v in hout[0].items() if v is not None}
+
+        def bank_step():
+            moved = 0
+            for b0 in range(0, B, chunk):
+                b1 = min(B, b0 + chunk)
+                with torch.cuda.stream(s_comp):
+                    vr = hvr[b0:b1].to(dev, non_blocking=True)
+                    ar = har[b0:b1].to(dev, non_blocking=True)
+                    tt = ht[b0:b1].to(dev, non_blocking=True)
+                    o = eng.encoder_indexed(vbank, vr, abank, ar, eng.time_mlp(tt), Qv, Qa, want_feats=False)
+                    done = torch.cuda.Event()
+                    done.record(s_comp)
+                moved += (vr.numel() + ar.numel()) * 8 + tt.numel() * 4
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(done)
+                    for k, hbuf in hres.items():
+                        rows = hbuf.shape[0] // B
+                        hbuf[b0 * rows:b1 * rows].copy_(o[k], non_blocking=True)
+                        o[k].record_stream(s_out)
+            s_comp.synchronize(); s_out.synchronize()
+            return moved
+
+        for _ in range(2):
+            up_bank = bank_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            bank_step()
+        torch.cuda.synchronize()
+        bank_s = max_ranks((time.perf_counter() - t0) / e2e_steps)
+        barrier()
+        e2e_bank = {"value": world * B * (Qv + Qa) / bank_s, "unit": UNIT, "ms_per_step": bank_s * 1e3, "h2d_bytes_per_step": up_bank,
+                    "d2h_bytes_per_step": down, "bank": f"fp32 [{B * F}, {cfg.visual_input_dim}] + [{B * F}, {cfg.audio_input_dim}] resident in HBM, "
+                    "windows gathered on the device (tim_encoder_fwd_indexed); random row permutation per modality"}
+
     if rank == 0:
         cb = None
         if not args.no_cpu_baseline:
@@ -294,7 +340,7 @@ def main():
                            "l2": f"per-step inputs {in_bytes / 1e6:.0f} MB + activations exceed the 126 MB L2 (no flush needed)",
                            "weights": "synthetic trained-like (tim_b200.synth)"},
                 "clips_per_sec": world * B / (ms * 1e-3), "tokens_per_sec": world * B * cfg.seq_len(Qv, Qa) / (ms * 1e-3),
-                "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline, "cpu_baseline": cb, "clocks": clocks, "parity": parity}
+                "gpu_launches": int(launches), "e2e": e2e, "e2e_resident_bank": e2e_bank, "roofline": roofline, "cpu_baseline": cb, "clocks": clocks, "parity": parity}
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     eng.close()
     if world > 1:

@@ -94,6 +94,21 @@ int tim_time_mlp_fwd(tim_ctx* ctx, const float* times, float* out, int B, int T,
 int tim_encoder_fwd(tim_ctx* ctx, const float* vis, const float* aud, const float* time_enc, int B, int T, int Qv, int Qa,
                     const tim_outputs* outs, void* stream);
 
+/* The same forward with the input windows gathered ON THE DEVICE from feature banks resident in HBM (SURVEY.md section 8f row 4;
+ * the reference's loader gathers feats[video][feat_indices, aug_indices] on the host, datasets/sliding_window.py:356-375, and
+ * ships [B, F, D] fp32 over PCIe every step). vis_rows / aud_rows [B * num_feats] (device, int64) give the bank row of every
+ * feature token, clip-major; a row outside the bank reads as zeros. Banks may be fp32 or 16-bit. */
+typedef struct {
+    const void* vis_bank;           /* [vis_bank_rows, vis_dim], device; NULL if the modality is absent */
+    const void* aud_bank;           /* [aud_bank_rows, aud_dim] */
+    const int64_t* vis_rows;
+    const int64_t* aud_rows;
+    int64_t vis_bank_rows, aud_bank_rows;
+    int32_t bank_dtype;             /* TIM_FP32 | TIM_BF16 | TIM_FP16 */
+} tim_feature_bank;
+int tim_encoder_fwd_indexed(tim_ctx* ctx, const tim_feature_bank* bank, const float* time_enc, int B, int T, int Qv, int Qa,
+                            const tim_outputs* outs, void* stream);
+
 /* End-to-end call on HOST buffers (pinned or pageable): time_mlp + encoder with the H2D input copies and D2H
  * result copies inside the call, chunked over clips and overlapped on three internal streams. Blocks until the
  * outputs are in host memory. `times` is [B, T, 2]; outputs as in tim_outputs but host pointers.

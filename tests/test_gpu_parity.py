@@ -351,6 +351,39 @@ def test_patch_model_detection_labels(lib):
     assert outs[0][2].shape == (B * Qv, cfg.num_class[0]) and queries[0].shape == (B * Qv, 2)
 
 
+@pytest.mark.parametrize("dt,bank_dt", [("fp32", "fp32"), ("fp16", "fp32"), ("fp16", "fp16"), ("bf16", "bf16")])
+def test_indexed_encoder_equals_dense(lib, dt, bank_dt):
+    """tim_encoder_fwd_indexed (window gather from an HBM-resident feature bank) must give exactly what the dense entry point
+    gives on the gathered rows - including repeated rows, and zeros for a row index outside the bank."""
+    from tim_b200.plugin import TIMEngine
+    cfg, sd, inp, gold, c = load_case("recog_av_small")
+    Qv, Qa = c["Qv"], c["Qa"]
+    dev = torch.device("cuda", 0)
+    tdt = {"fp32": torch.float32, "fp16": torch.float16, "bf16": torch.bfloat16}[bank_dt]
+    g = torch.Generator().manual_seed(5)
+    B, F = 4, cfg.num_feats
+    vbank = torch.randn(37, cfg.visual_input_dim, generator=g).to(tdt).to(dev)
+    abank = torch.randn(29, cfg.audio_input_dim, generator=g).to(tdt).to(dev)
+    vrows = torch.randint(0, 37, (B, F), generator=g).to(dev)
+    arows = torch.randint(0, 29, (B, F), generator=g).to(dev)
+    vrows[0, 0] = vrows[0, 1]                  # a repeated row
+    arows[1, 2] = 29                           # one past the end: reads as zeros
+    vis = vbank.float()[vrows]
+    aud = torch.cat([abank.float(), torch.zeros(1, cfg.audio_input_dim, device=dev)])[arows]
+    times = torch.from_numpy(synth_inputs(cfg, B, Qv, Qa, 8)["times"]).to(dev)
+    eng = TIMEngine(cfg, 0, dt)
+    eng.load_state_dict(sd)
+    te = eng.time_mlp(times)
+    dense = eng.encoder(vis.contiguous(), aud.contiguous(), te, Qv, Qa)
+    idx = eng.encoder_indexed(vbank, vrows, abank, arows, te, Qv, Qa)
+    torch.cuda.synchronize()
+    for k, v in dense.items():
+        assert (v is None) == (idx[k] is None)
+        if v is not None:
+            assert torch.equal(v, idx[k]), k
+    eng.close()
+
+
 def test_two_devices_in_one_process(lib):
     """The usual deployment is one process per GPU, but nothing may break when one process owns contexts on two devices
     (kernel attributes such as the dynamic shared-memory limit are per device)."""

@@ -54,6 +54,8 @@ SYMBOLS = {
     "tim_bench_linear": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "tim_fold_active": (C.c_int, [C.c_void_p]),
+    "tim_encoder_fwd_indexed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                          C.c_void_p]),
     "tim_label_queries": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float,
                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tim_smooth_labels": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_double, C.c_void_p, C.c_void_p]),
@@ -64,6 +66,11 @@ SYMBOLS = {
 }
 
 _lib = None
+
+
+class tim_feature_bank(C.Structure):
+    _fields_ = [("vis_bank", C.c_void_p), ("aud_bank", C.c_void_p), ("vis_rows", C.c_void_p), ("aud_rows", C.c_void_p),
+                ("vis_bank_rows", C.c_int64), ("aud_bank_rows", C.c_int64), ("bank_dtype", C.c_int32)]
 
 
 class TimError(RuntimeError):

@@ -604,7 +604,8 @@ int plan_queries(tim_ctx* c, int T_, int Qv, int Qa, QueryPlan* qp) {
 
 template <typename T>
 int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te, int B, int T_, int Qv, int Qa,
-                 const tim_outputs* o, cudaStream_t s, uint8_t* ws_base, size_t* ws_need) {
+                 const tim_outputs* o, cudaStream_t s, uint8_t* ws_base, size_t* ws_need, const tim_feature_bank* fb = nullptr,
+                 bool ws_indexed = false) {
     constexpr bool f32 = std::is_same<T, float>::value;
     const tim_config& g = c->cfg;
     const int d = c->d, E = c->E, FF = c->FF;
@@ -624,8 +625,10 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
     a.take(&hid, M * FF * sizeof(T));
     a.take(&embv, static_cast<size_t>(B) * c->Fv * d * sizeof(float));
     a.take(&emba, static_cast<size_t>(B) * c->Fa * d * sizeof(float));
-    a.take(&vis16, f32 ? 0 : static_cast<size_t>(B) * c->Fv * g.vis_dim * sizeof(T));
-    a.take(&aud16, f32 ? 0 : static_cast<size_t>(B) * c->Fa * g.aud_dim * sizeof(T));
+    // dense copies of the inputs in the compute dtype: the 16-bit cast of vis / aud, or (any dtype) the rows gathered from a bank
+    const bool indexed = fb != nullptr || ws_indexed;
+    a.take(&vis16, (f32 && !indexed) ? 0 : static_cast<size_t>(B) * c->Fv * g.vis_dim * sizeof(T));
+    a.take(&aud16, (f32 && !indexed) ? 0 : static_cast<size_t>(B) * c->Fa * g.aud_dim * sizeof(T));
     const size_t regrows = static_cast<size_t>(B) * (qp.Qv > qp.Qa ? qp.Qv : qp.Qa);
     a.take(&r1, g.variant == TIM_DETECTION ? regrows * (E / 2) * sizeof(T) : 0);
     a.take(&r2, g.variant == TIM_DETECTION ? regrows * (E / 2) * sizeof(T) : 0);
@@ -638,15 +641,29 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
     // ---- embedders: Linear -> GELU (epilogue) -> pre-LN rows; LN happens while assembling tokens ----
     const int Mv = B * c->Fv, Ma = B * c->Fa;
     if (c->Fv) {
-        if (!vis) return c->fail(TIM_ERR_INVALID, "visual input is NULL");
         const void* A = vis;
-        if constexpr (!f32) { LAUNCH(c, launch_cast<T>(vis, vis16, Mv, g.vis_dim, 0, 1.0f, s)); A = vis16; }
+        if (fb) {
+            if (!fb->vis_bank || !fb->vis_rows) return c->fail(TIM_ERR_INVALID, "visual feature bank / row indices are NULL");
+            LAUNCH(c, launch_gather_rows<T>(fb->vis_bank, fb->bank_dtype, fb->vis_bank_rows, reinterpret_cast<const long long*>(fb->vis_rows), vis16, Mv,
+                                            g.vis_dim, s));
+            A = vis16;
+        } else {
+            if (!vis) return c->fail(TIM_ERR_INVALID, "visual input is NULL");
+            if constexpr (!f32) { LAUNCH(c, launch_cast<T>(vis, vis16, Mv, g.vis_dim, 0, 1.0f, s)); A = vis16; }
+        }
         TIM_TRY(run_linear<T>(c, A, g.vis_dim, c->emb_v, plain_rows(Mv), epi(embv, d, true, ACT_GELU), s));
     }
     if (c->Fa) {
-        if (!aud) return c->fail(TIM_ERR_INVALID, "audio input is NULL");
         const void* A = aud;
-        if constexpr (!f32) { LAUNCH(c, launch_cast<T>(aud, aud16, Ma, g.aud_dim, 0, 1.0f, s)); A = aud16; }
+        if (fb) {
+            if (!fb->aud_bank || !fb->aud_rows) return c->fail(TIM_ERR_INVALID, "audio feature bank / row indices are NULL");
+            LAUNCH(c, launch_gather_rows<T>(fb->aud_bank, fb->bank_dtype, fb->aud_bank_rows, reinterpret_cast<const long long*>(fb->aud_rows), aud16, Ma,
+                                            g.aud_dim, s));
+            A = aud16;
+        } else {
+            if (!aud) return c->fail(TIM_ERR_INVALID, "audio input is NULL");
+            if constexpr (!f32) { LAUNCH(c, launch_cast<T>(aud, aud16, Ma, g.aud_dim, 0, 1.0f, s)); A = aud16; }
+        }
         TIM_TRY(run_linear<T>(c, A, g.aud_dim, c->emb_a, plain_rows(Ma), epi(emba, d, true, ACT_GELU), s));
     }
     // ---- token assembly into the two-stream buffer ----
@@ -813,9 +830,11 @@ int dispatch_dtype(tim_ctx* c, F&& f) {
 int time_mlp_ws(tim_ctx* c, int B, int T_, size_t* need) {
     return dispatch_dtype(c, [&](auto tag) { return time_mlp_impl<decltype(tag)>(c, nullptr, nullptr, B, T_, nullptr, nullptr, need); });
 }
-int encoder_ws(tim_ctx* c, int B, int T_, int Qv, int Qa, size_t* need) {
+int encoder_ws(tim_ctx* c, int B, int T_, int Qv, int Qa, size_t* need, bool indexed = false) {
     tim_outputs o; std::memset(&o, 0, sizeof(o));
-    return dispatch_dtype(c, [&](auto tag) { return encoder_impl<decltype(tag)>(c, nullptr, nullptr, nullptr, B, T_, Qv, Qa, &o, nullptr, nullptr, need); });
+    return dispatch_dtype(c, [&](auto tag) {
+        return encoder_impl<decltype(tag)>(c, nullptr, nullptr, nullptr, B, T_, Qv, Qa, &o, nullptr, nullptr, need, nullptr, indexed);
+    });
 }
 
 }  // namespace
@@ -984,6 +1003,22 @@ int tim_encoder_fwd(tim_ctx* c, const float* vis, const float* aud, const float*
     TIM_TRY(ensure_ws(c, need));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     return dispatch_dtype(c, [&](auto tag) { return encoder_impl<decltype(tag)>(c, vis, aud, te, B, T_, Qv, Qa, outs, s, c->ws, nullptr); });
+}
+
+int tim_encoder_fwd_indexed(tim_ctx* c, const tim_feature_bank* fb, const float* te, int B, int T_, int Qv, int Qa,
+                            const tim_outputs* outs, void* stream) {
+    if (!c) return TIM_ERR_INVALID;
+    if (!fb || !te || !outs || B <= 0 || T_ <= 0) return c->fail(TIM_ERR_INVALID, "tim_encoder_fwd_indexed: bad arguments");
+    if (fb->bank_dtype < TIM_FP32 || fb->bank_dtype > TIM_FP16) return c->fail(TIM_ERR_INVALID, "tim_encoder_fwd_indexed: bad bank_dtype");
+    TIM_TRY(check_ready(c));
+    CU_OK(c, cudaSetDevice(c->device));
+    size_t need = 0;
+    TIM_TRY(encoder_ws(c, B, T_, Qv, Qa, &need, true));
+    TIM_TRY(ensure_ws(c, need));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return dispatch_dtype(c, [&](auto tag) {
+        return encoder_impl<decltype(tag)>(c, nullptr, nullptr, te, B, T_, Qv, Qa, outs, s, c->ws, nullptr, fb, true);
+    });
 }
 
 int tim_forward_host(tim_ctx* c, const float* vis, const float* aud, const float* times, int B, int T_, int Qv, int Qa,

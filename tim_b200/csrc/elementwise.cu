@@ -247,6 +247,36 @@ __global__ void __launch_bounds__(ROWS_PER_CTA * 32) fold_ln_kernel(const float*
     if (lane == 0) { cs[n] = c; bw[n] = sn * (b + bias[n]); }
 }
 
+// Window gather on the device (the reference gathers `feats[video][feat_indices, aug_indices]` on the host,
+// recognition/.../datasets/sliding_window.py:356-375, and ships the result over PCIe): out[m, :] = TO(bank[rows[m], :]) for a
+// feature bank resident in HBM (fp32 or 16-bit). One warp per row, 16-byte loads; a row index outside the bank yields zeros.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(ROWS_PER_CTA * 32) gather_rows_kernel(const TI* __restrict__ bank, long long bank_rows,
+                                                                        const long long* __restrict__ rows, TO* __restrict__ out,
+                                                                        long long M, int D) {
+    const int lane = threadIdx.x & 31;
+    const long long m = static_cast<long long>(blockIdx.x) * ROWS_PER_CTA + (threadIdx.x >> 5);
+    if (m >= M) return;
+    const long long r = rows[m];
+    const bool ok = r >= 0 && r < bank_rows;
+    const TI* src = bank + (ok ? r : 0) * D;
+    TO* dst = out + m * D;
+    for (int c = lane * 4; c < D; c += 128) {
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f, v3 = 0.f;
+        if (ok) {
+            if constexpr (sizeof(TI) == 4) {
+                const float4 v = *reinterpret_cast<const float4*>(src + c);
+                v0 = v.x; v1 = v.y; v2 = v.z; v3 = v.w;
+            } else {
+                const uint2 u = *reinterpret_cast<const uint2*>(src + c);
+                const float2 a = unpack2<TI>(u.x), b = unpack2<TI>(u.y);
+                v0 = a.x; v1 = a.y; v2 = b.x; v3 = b.y;
+            }
+        }
+        store4<TO>(dst + c, v0, v1, v2, v3);
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(ROWS_PER_CTA * 32) reg_final_kernel(const T* __restrict__ h, int ldh, const float* __restrict__ W,
                                                                       const float* __restrict__ b, float* __restrict__ out, int rows, int K) {
@@ -344,6 +374,24 @@ cudaError_t launch_scale_copy(const float* in, float* out, size_t rows, size_t c
     if (n % 4) cast_tail_kernel<float><<<1, 256, 0, s>>>(in, out, n4 * 4, n, scale_n, scale);
     return cudaGetLastError();
 }
+
+template <typename TO>
+cudaError_t launch_gather_rows(const void* bank, int bank_dtype, long long bank_rows, const long long* rows, TO* out, long long M, int D,
+                               cudaStream_t s) {
+    if (M <= 0) return cudaSuccess;
+    if (D % 4 || bank_rows <= 0) return cudaErrorInvalidValue;
+    const unsigned grid = static_cast<unsigned>((M + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
+    switch (bank_dtype) {      // TIM_FP32 = 0, TIM_BF16 = 1, TIM_FP16 = 2
+        case 0: gather_rows_kernel<float, TO><<<grid, ROWS_PER_CTA * 32, 0, s>>>(static_cast<const float*>(bank), bank_rows, rows, out, M, D); break;
+        case 1: gather_rows_kernel<__nv_bfloat16, TO><<<grid, ROWS_PER_CTA * 32, 0, s>>>(static_cast<const __nv_bfloat16*>(bank), bank_rows, rows, out, M, D); break;
+        case 2: gather_rows_kernel<__half, TO><<<grid, ROWS_PER_CTA * 32, 0, s>>>(static_cast<const __half*>(bank), bank_rows, rows, out, M, D); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+template cudaError_t launch_gather_rows<float>(const void*, int, long long, const long long*, float*, long long, int, cudaStream_t);
+template cudaError_t launch_gather_rows<__half>(const void*, int, long long, const long long*, __half*, long long, int, cudaStream_t);
+template cudaError_t launch_gather_rows<__nv_bfloat16>(const void*, int, long long, const long long*, __nv_bfloat16*, long long, int, cudaStream_t);
 
 cudaError_t launch_row_stats_finalize(const float2* part, int P, int width, float2* stats, int M, float alarm_ratio, int* alarm,
                                       cudaStream_t s) {

@@ -176,6 +176,11 @@ cudaError_t launch_cast(const float* in, T* out, size_t rows, size_t cols, size_
 cudaError_t launch_scale_copy(const float* in, float* out, size_t rows, size_t cols, size_t scale_rows, float scale,
                               cudaStream_t s);
 
+// out[m, :] = TO(bank[rows[m], :]); bank_dtype 0 fp32 / 1 bf16 / 2 fp16; rows outside [0, bank_rows) give zeros
+template <typename TO>
+cudaError_t launch_gather_rows(const void* bank, int bank_dtype, long long bank_rows, const long long* rows, TO* out, long long M, int D,
+                               cudaStream_t s);
+
 // (mean, rstd) per row from the partial sums a mode-5 GEMM wrote: part [P][M] (sum, sum of squares), width columns in total;
 // *alarm (device int, optional) is set when some row has mean^2 > alarm_ratio * var
 cudaError_t launch_row_stats_finalize(const float2* part, int P, int width, float2* stats, int M, float alarm_ratio, int* alarm,

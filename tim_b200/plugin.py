@@ -150,6 +150,40 @@ class TIMEngine:
                                                 B, T, Qv, Qa, C.byref(co), self._stream()), self._ctx)
         return out
 
+    def encoder_indexed(self, vis_bank: Optional[torch.Tensor], vis_rows: Optional[torch.Tensor], aud_bank: Optional[torch.Tensor],
+                        aud_rows: Optional[torch.Tensor], time_enc: torch.Tensor, Qv: int, Qa: int,
+                        want_feats: bool = True) -> Dict[str, Optional[torch.Tensor]]:
+        """encoder() with the input windows gathered on the device from feature banks resident in HBM: *_bank [rows, dim] (fp32,
+        fp16 or bf16, same dtype for both), *_rows [B, num_feats] int64 = bank row of every feature token (what the reference's
+        loader indexes on the host: datasets/sliding_window.py:356-375)."""
+        cfg = self.cfg
+        B, T = int(time_enc.shape[0]), int(time_enc.shape[1])
+        time_enc = self._check_in(time_enc, "time_encodings", (B, T, cfg.d_model))
+        codes = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+        fb = _lib.tim_feature_bank()
+        dt = None
+        for name, bank, rows, dim, present in (("vis", vis_bank, vis_rows, cfg.visual_input_dim, cfg.has_visual_input),
+                                               ("aud", aud_bank, aud_rows, cfg.audio_input_dim, cfg.has_audio_input)):
+            if not present:
+                continue
+            if bank is None or rows is None or bank.device != self.device or rows.device != self.device:
+                raise ValueError(f"{name}: bank and row indices must be tensors on {self.device}")
+            if bank.dim() != 2 or bank.shape[1] != dim or not bank.is_contiguous() or bank.dtype not in codes:
+                raise ValueError(f"{name}_bank must be contiguous [rows, {dim}] fp32 / fp16 / bf16")
+            if rows.dtype != torch.int64 or tuple(rows.shape) != (B, cfg.num_feats) or not rows.is_contiguous():
+                raise ValueError(f"{name}_rows must be contiguous int64 [{B}, {cfg.num_feats}]")
+            if dt is not None and bank.dtype != dt:
+                raise ValueError("both banks must have the same dtype")
+            dt = bank.dtype
+            setattr(fb, f"{name}_bank", bank.data_ptr()); setattr(fb, f"{name}_rows", rows.data_ptr())
+            setattr(fb, f"{name}_bank_rows", int(bank.shape[0]))
+        fb.bank_dtype = codes[dt]
+        with torch.cuda.device(self.device):
+            out, co = self._alloc_outputs(B, int(Qv or 0), int(Qa or 0), pinned=False, want_feats=want_feats)
+            _lib.check(self.lib.tim_encoder_fwd_indexed(self._ctx, C.byref(fb), _ptr(time_enc), B, T, int(Qv or 0), int(Qa or 0),
+                                                        C.byref(co), self._stream()), self._ctx)
+        return out
+
     # ------------------------------------------------------------------ forward (host tensors, end to end)
     def forward_host(self, vis, aud, times: torch.Tensor, Qv: int, Qa: int, clips_per_chunk: int = 0,
                      want_feats: bool = True, out=None):
