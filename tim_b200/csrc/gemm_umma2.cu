@@ -14,8 +14,12 @@
 //   warp 0    : TMA producer (own A / W halves; completion bytes are signalled on the LEADER's full barrier)
 //   warp 1    : leader: MMA issuer (256 x 256 x 16 per instruction); both: TMEM allocation (512 columns = 2 accumulators)
 //   warps 2-9 : epilogue; warp w owns TMEM lanes 32*(w%4).. and every other column block of the tile
-// Pipelines: smem full/empty ring (5 stages), TMEM full/empty (2 accumulators), per-warp TMA store / residual-load
+// Pipelines: smem full/empty ring (5 stages; 4 in mode 5), TMEM full/empty (2 accumulators), per-warp TMA store / residual-load
 // double buffers. Persistent: cluster c walks tiles c, c + #clusters, ... (N fastest, so A tiles are shared through L2).
+//
+// Epilogue modes (template MODE): 0 16-bit out; 1 fp32 out; 2 fp32 out + fp32 residual; 3 as 2 with LayerNorm applied to the
+// residual rows on read; 5 / 6 the folded-LayerNorm producer / consumer pair that removes the LayerNorm kernels of the encoder
+// stack (transformers.py:105,109) - described in front of the kernel. Measured per-launch numbers: profiles/README.md.
 #include "kernels.h"
 #include "ptx.cuh"
 
