@@ -743,9 +743,10 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
             // z2 = hid W2^T + b2 + LN1(z1)             -> x32 (fp32), x16 (16-bit copy), partial sums
             TIM_TRY(run_fold_gemm<T>(c, 5, ACT_NONE, hid, Mi, E, FF, ly.lin2.tmB2, ly.lin2.bias, x32, x16, z, stats, ly.n1g, ly.n1b, part, nullptr, s));
             if (l < c->L - 1) LAUNCH_C(c, 2, 0.0, s, launch_row_stats_finalize(part, static_cast<int>(nparts), E, stats, Mi, 64.0f, c->fold_alarm_dev, s));   // z2
-            // the last layer's norm2 feeds the heads: the only LayerNorm kernel of the stack
-            if (l == c->L - 1)
-                LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(x32, E, ly.n2g, ly.n2b, nullptr, 0, x16o, E, Mi, E, s, stats));
+            // the last layer's norm2 feeds the heads: the only LayerNorm kernel of the stack, and only over the query rows
+            // (the heads read nothing else; the feature rows' fp32 LayerNorm goes straight to `feats` below)
+            if (l == c->L - 1 && Mq)
+                LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(x32 + Mf * E, E, ly.n2g, ly.n2b, nullptr, 0, x16o + Mf * E, E, static_cast<int>(Mq), E, s));
         } else {
             Epilogue e1 = epi(z, E, true, ACT_NONE, x32, E);
             if (l > 0) { e1.rstats = stats; e1.rgamma = c->layers[l - 1].n2g; e1.rbeta = c->layers[l - 1].n2b; }
@@ -755,9 +756,9 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
             Epilogue e2 = epi(x32, E, true, ACT_NONE, z, E);
             e2.rstats = stats; e2.rgamma = ly.n1g; e2.rbeta = ly.n1b;
             TIM_TRY(run_linear<T>(c, hid, FF, ly.lin2, plain_rows(Mi), e2, s));
-            // the last layer's norm2 feeds the heads: a kernel of its own
-            if (l == c->L - 1)
-                LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(x32, E, ly.n2g, ly.n2b, nullptr, 0, x16o, E, Mi, E, s, stats));
+            // the last layer's norm2 feeds the heads: a kernel of its own, over the query rows only
+            if (l == c->L - 1 && Mq)
+                LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(x32 + Mf * E, E, ly.n2g, ly.n2b, nullptr, 0, x16o + Mf * E, E, static_cast<int>(Mq), E, s));
         }
     }
     // fp32 features returned to the caller (tim.py:172, x[:, :num_feats]): LayerNorm of the last layer's z2 feature rows

@@ -14,19 +14,25 @@ namespace {
 
 constexpr int ROWS_PER_CTA = 8;      // 8 warps, one row each
 
+template <typename T> __device__ __forceinline__ void store4(T* p, float a, float b, float c, float d);
+
+// One warp per time row: lane l writes columns 4l, 4l + 128, ... (8- or 16-byte stores), the two inputs of the row are loaded once.
 template <typename TO>
-__global__ void __launch_bounds__(256) time_l1_kernel(const float* __restrict__ times, const float* __restrict__ W,
-                                                      const float* __restrict__ b, TO* __restrict__ out, int M, int d) {
-    const size_t total = static_cast<size_t>(M) * d;
-    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < total;
-         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
-        const size_t m = i / d;
-        const int c = static_cast<int>(i - m * d);
-        const float2 t = *reinterpret_cast<const float2*>(times + 2 * m);
-        const float2 w = *reinterpret_cast<const float2*>(W + 2 * c);
+__global__ void __launch_bounds__(ROWS_PER_CTA * 32) time_l1_kernel(const float* __restrict__ times, const float* __restrict__ W,
+                                                                    const float* __restrict__ b, TO* __restrict__ out, int M, int d) {
+    const int lane = threadIdx.x & 31;
+    const int m = blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
+    if (m >= M) return;
+    const float2 t = *reinterpret_cast<const float2*>(times + 2 * static_cast<size_t>(m));
+    TO* o = out + static_cast<size_t>(m) * d;
+    for (int c = lane * 4; c < d; c += 128) {
+        const float4 w01 = __ldg(reinterpret_cast<const float4*>(W + 2 * c));          // (w[c][0], w[c][1], w[c+1][0], w[c+1][1])
+        const float4 w23 = __ldg(reinterpret_cast<const float4*>(W + 2 * c + 4));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(b + c));
         // same association as x @ W.T + b: (t0*w0 + t1*w1) + b
-        const float v = fmaf(t.y, w.y, t.x * w.x) + b[c];
-        out[i] = from_float<TO>(fmaxf(v, 0.0f));
+        const float v0 = fmaf(t.y, w01.y, t.x * w01.x) + bb.x, v1 = fmaf(t.y, w01.w, t.x * w01.z) + bb.y;
+        const float v2 = fmaf(t.y, w23.y, t.x * w23.x) + bb.z, v3 = fmaf(t.y, w23.w, t.x * w23.z) + bb.w;
+        store4<TO>(o + c, fmaxf(v0, 0.0f), fmaxf(v1, 0.0f), fmaxf(v2, 0.0f), fmaxf(v3, 0.0f));
     }
 }
 
@@ -47,7 +53,6 @@ __device__ __forceinline__ void row_stats(const float* __restrict__ row, int n, 
     rstd = rsqrtf(warp_sum(q) / static_cast<float>(n) + 1e-5f);
 }
 
-template <typename T> __device__ __forceinline__ void store4(T* p, float a, float b, float c, float d);
 template <> __device__ __forceinline__ void store4<float>(float* p, float a, float b, float c, float d) {
     *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
 }
@@ -308,7 +313,8 @@ inline int grid_for(size_t n, int block, int cap = 148 * 16) {
 template <typename TO>
 cudaError_t launch_time_l1(const float* times, const float* W, const float* b, TO* out, int M, int d, cudaStream_t s) {
     if (M <= 0) return cudaSuccess;
-    time_l1_kernel<TO><<<grid_for(static_cast<size_t>(M) * d, 256), 256, 0, s>>>(times, W, b, out, M, d);
+    if (d % 4) return cudaErrorInvalidValue;
+    time_l1_kernel<TO><<<(M + ROWS_PER_CTA - 1) / ROWS_PER_CTA, ROWS_PER_CTA * 32, 0, s>>>(times, W, b, out, M, d);
     return cudaGetLastError();
 }
 template cudaError_t launch_time_l1<float>(const float*, const float*, const float*, float*, int, int, cudaStream_t);
