@@ -30,7 +30,8 @@ template <int BLOCK_N> struct Cfg {
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;
     static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;   // two accumulator stages (power of two)
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int XPOSE_BYTES = 4 * 32 * 33 * 4;     // per-epilogue-warp transpose scratch (coalesced fp32 stores)
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + XPOSE_BYTES;
 };
 
 template <typename T> struct FmtOf;
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_umma_kernel(const __gri
         // ===================== epilogue (warps 2..5) =====================
         const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
         const int row_in_tile = quarter * 32 + lane;
+        const uint32_t xpose = bar_base + 256u + static_cast<uint32_t>(warp - 2) * (32 * 33 * 4);
         const Epilogue& ep = p.ep;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -149,9 +151,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_umma_kernel(const __gri
                 uint32_t v[32];
                 tmem_ld_32x32(t_addr + c0, v);
                 tmem_ld_wait();
-                if (!row_ok) continue;
                 const int n = n0 + c0;
                 const bool full = (n + 32 <= p.N);
+                // fp32 rows whose pitch is not 16-byte aligned (e.g. the 3806-class action head) or a ragged last chunk: transpose
+                // through smem so that every store instruction writes 32 consecutive floats of ONE row (warp-uniform choice)
+                const bool xp = ep.out_fp32 && !ep.resid && (!full || (ep.ldo & 3) != 0);
+                if (!row_ok && !xp) continue;
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -195,7 +200,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_umma_kernel(const __gri
                 }
                 if (ep.out_fp32) {
                     float* op = reinterpret_cast<float*>(ep.out) + orow * ep.ldo + n;
-                    if (full && (ep.ldo & 3) == 0) {
+                    if (xp) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sts_f32(xpose + static_cast<uint32_t>((lane * 33 + j) * 4), f[j]);
+                        __syncwarp();
+                        const long long my_orow = row_ok ? static_cast<long long>(orow) : -1LL;
+                        float* obase = reinterpret_cast<float*>(ep.out) + n + lane;
+                        const bool col_ok = n + lane < p.N;
+#pragma unroll 4
+                        for (int r = 0; r < 32; ++r) {
+                            const long long ro = __shfl_sync(0xffffffffu, my_orow, r);
+                            if (ro >= 0 && col_ok) obase[ro * ep.ldo] = lds_f32(xpose + static_cast<uint32_t>((r * 33 + lane) * 4));
+                        }
+                        __syncwarp();
+                    } else if (full && (ep.ldo & 3) == 0) {
 #pragma unroll
                         for (int j = 0; j < 32; j += 4)
                             *reinterpret_cast<float4*>(op + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
