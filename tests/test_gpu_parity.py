@@ -117,6 +117,43 @@ def test_named_configs_vs_oracle(lib, name, B, dt):
         assert e <= TOL[dt], f"{name}/{k} [{dt}]: rel-L2 {e:.3e} > {TOL[dt]:.0e}"
 
 
+FUZZ = [  # (variant, d_model, nhead, num_layers, num_feats, input_modality, data_modality, include_verb_noun, B, Qv, Qa)
+    ("recognition", 192, 3, 2, 33, "audio_visual", "audio_visual", True, 3, 7, 5),     # E=384: two N-tiles, the second half-empty; hd=128
+    ("recognition", 160, 5, 2, 20, "audio_visual", "audio_visual", False, 2, 130, 1),  # E=320: ragged last N-tile (one half owns no column)
+    ("recognition", 192, 2, 1, 64, "audio_visual", "visual", True, 2, 40, 0),          # hd=192, Ft=128 (maximum), no audio queries
+    ("recognition", 128, 4, 3, 9, "visual", "visual", True, 5, 3, 0),                  # uni-modal visual, E=256, hd=64
+    ("recognition", 256, 16, 2, 17, "audio", "audio", False, 2, 0, 150),               # uni-modal audio, E=512, hd=32 (warp-MMA attention)
+    ("detection", 192, 6, 2, 25, "audio_visual", "visual", False, 2, 260, 0),          # detection, hd=64, 3 query tiles
+    ("detection", 128, 2, 2, 50, "audio_visual", "audio_visual", False, 1, 129, 129),  # detection AV, hd=128, Ft=100
+    ("detection", 64, 8, 1, 6, "audio_visual", "audio", False, 4, 0, 11),              # hd=16 (warp-MMA attention), audio data only
+]
+
+
+@pytest.mark.parametrize("case", range(len(FUZZ)))
+def test_shape_fuzz_vs_oracle(lib, case):
+    """Shapes the golden set does not contain (ragged N-tiles of the folded-LayerNorm GEMMs, Ft = 128, several query tiles, both
+    attention kernels, uni-modal variants), fp16 path against the oracle run live on the same seeded inputs."""
+    from oracle.tim_oracle import TIMOracle
+    from tim_b200.config import TIMConfig
+    variant, d, H, L, F, im, dm, vn, B, Qv, Qa = FUZZ[case]
+    if variant == "recognition":
+        nc = [[5, 7, 11], 3] if vn else [11, 3]
+    else:
+        nc = [9, 4]
+    cfg = TIMConfig(num_class=nc, visual_input_dim=72, audio_input_dim=40, d_model=d, nhead=H, num_layers=L, num_feats=F,
+                    input_modality=im, data_modality=dm, include_verb_noun=vn, variant=variant)
+    sd = synth_state_dict(cfg, case, "trained")
+    inp = synth_inputs(cfg, B, Qv, Qa, 100 + case, shared_queries=variant == "detection" and Qv == Qa)
+    ref = TIMOracle(cfg, sd, np.float32).forward(inp.get("vis"), inp.get("aud"), inp["times"], Qv, Qa, clip_chunk=1)
+    res = engine_run(cfg, sd, inp, Qv, Qa, "fp16")
+    for k, v in ref.items():
+        if v is None:
+            assert res.get(k) is None, k
+            continue
+        e = rel_l2(res[k], v)
+        assert e <= TOL_SMALL["fp16"], f"case {case} {k}: rel-L2 {e:.3e}"
+
+
 def test_full_size_properties(lib):
     """cfg2 at a bench-sized batch: size-independent properties instead of an oracle run.
     (a) clip independence: a clip's outputs are bit-identical whatever else is in the batch;
