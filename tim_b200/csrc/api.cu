@@ -1032,6 +1032,10 @@ int tim_forward_host(tim_ctx* c, const float* vis, const float* aud, const float
     if (cpc <= 0 || cpc > B) cpc = B;
     QueryPlan qp;
     TIM_TRY(plan_queries(c, T_, Qv, Qa, &qp));
+    // This call runs on the context's own non-blocking streams and blocks until the results are on the host. Work the caller
+    // enqueued earlier on ITS stream (tim_set_weight packing, a previous device-path forward) is not ordered against those
+    // streams, so settle the device first - a blocking API can afford it.
+    CU_OK(c, cudaDeviceSynchronize());
     if (!c->s_h2d) {
         CU_OK(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
         CU_OK(c, cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
