@@ -81,7 +81,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);     // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
@@ -113,28 +113,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
+    // Producer and MMA warps run their loops WARP-UNIFORMLY (all 32 lanes wait on the barriers and carry the loop state) and
+    // only the asynchronous-issue instructions sit under elect_one(): the descriptors, coordinates and barrier addresses are
+    // then provably uniform and live in uniform registers, instead of being moved there (R2UR + ELECT) in front of every
+    // UTCHMMA / UTMALDG of a single divergent thread - the MMA issue loop shares its scheduler with two busy epilogue warps
+    // and its instruction count is what keeps the tensor pipe fed.
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-                const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
-                const int m0 = tm * (2 * BM) + static_cast<int>(rank) * BM;
-                const int n0 = tn * BN + static_cast<int>(rank) * (BN / 2);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
-                    const uint32_t fb = mapa_shared(full_bar(stage), 0);     // the leader's barrier
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+            const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+            const int m0 = tm * (2 * BM) + static_cast<int>(rank) * BM;
+            const int n0 = tn * BN + static_cast<int>(rank) * (BN / 2);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                const uint32_t fb = mapa_shared(full_bar(stage), 0);     // the leader's barrier
+                if (elect_one()) {
                     if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * STAGE_BYTES);
                     tma_load_2d_cg2(smem_a + stage * A_BYTES, &p.tmA, fb, kb * BK, m0);
                     tma_load_2d_cg2(smem_b + stage * B_BYTES, &p.tmB, fb, kb * BK, n0);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
-        if (leader && lane == 0) {
+        if (leader) {
             constexpr uint32_t idesc = umma_idesc_f16(FmtOf2<T>::v, 2 * BM, BN);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
@@ -147,13 +152,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
                     tc_fence_after();
                     const uint64_t adesc = umma_desc_sw128(smem_a + stage * A_BYTES);
                     const uint64_t bdesc = umma_desc_sw128(smem_b + stage * B_BYTES);
+                    if (elect_one()) {                          // the same (lowest) lane every time: commits track its MMAs
 #pragma unroll
-                    for (int k = 0; k < BK / UK; ++k)
-                        umma_f16_ss_cg2(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                    umma_commit_cg2(empty_bar(stage), 3);       // frees this stage in both CTAs
+                        for (int k = 0; k < BK / UK; ++k)
+                            umma_f16_ss_cg2(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_commit_cg2(empty_bar(stage), 3);   // frees this stage in both CTAs
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit_cg2(tfull_bar(acc), 3);             // accumulator complete -> both epilogues
+                if (elect_one()) umma_commit_cg2(tfull_bar(acc), 3);     // accumulator complete -> both epilogues
                 if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
             }
         }
