@@ -115,7 +115,10 @@ __global__ void __launch_bounds__(AU_THREADS, 1) attention_umma_kernel(const __g
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        // producer and MMA warps run warp-uniformly (all lanes carry the loop state and wait on the barriers); one elected
+        // lane issues the asynchronous instructions. A loop under `if (lane == 0)` makes the compiler re-derive uniform
+        // operands per instruction and starves the issue slot the warp shares with the softmax / epilogue warps.
+        {
             // L2 prefetch iterator running AU_PF tiles ahead of the loads: with two smem stages the loads in flight
             // (<= 2 x 64 KB per SM) cannot cover the HBM latency-bandwidth product; the prefetches can.
             int pf_u = blockIdx.x, pf_t = 0;
@@ -126,22 +129,24 @@ __global__ void __launch_bounds__(AU_THREADS, 1) attention_umma_kernel(const __g
                 if (!pf_valid) return;
                 const int h0 = pf_ui.h * HD;
                 const bool tiles_too = p.pf_mode >= 2;
-                if (pf_t == pf_ui.t_lo) {
+                if (elect_one()) {
+                    if (pf_t == pf_ui.t_lo) {
+#pragma unroll
+                        for (int j = 0; j < KBOX; ++j) {
+                            tma_prefetch_l2_3d(&p.tmKV, E + h0 + 64 * j, 0, pf_ui.b);
+                            tma_prefetch_l2_3d(&p.tmKV, 2 * E + h0 + 64 * j, 0, pf_ui.b);
+                        }
+                    }
 #pragma unroll
                     for (int j = 0; j < KBOX; ++j) {
-                        tma_prefetch_l2_3d(&p.tmKV, E + h0 + 64 * j, 0, pf_ui.b);
-                        tma_prefetch_l2_3d(&p.tmKV, 2 * E + h0 + 64 * j, 0, pf_ui.b);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < KBOX; ++j) {
-                    if (!tiles_too) break;
-                    if (pf_t == 0) {
-                        tma_prefetch_l2_3d(&p.tmQf, h0 + 64 * j, 0, pf_ui.b);
-                    } else {
-                        tma_prefetch_l2_3d(&p.tmQq, h0 + 64 * j, (pf_t - 1) * AU_BM, pf_ui.b);
-                        tma_prefetch_l2_3d(&p.tmQq, E + h0 + 64 * j, (pf_t - 1) * AU_BM, pf_ui.b);
-                        tma_prefetch_l2_3d(&p.tmQq, 2 * E + h0 + 64 * j, (pf_t - 1) * AU_BM, pf_ui.b);    // own-value rows (epilogue)
+                        if (!tiles_too) break;
+                        if (pf_t == 0) {
+                            tma_prefetch_l2_3d(&p.tmQf, h0 + 64 * j, 0, pf_ui.b);
+                        } else {
+                            tma_prefetch_l2_3d(&p.tmQq, h0 + 64 * j, (pf_t - 1) * AU_BM, pf_ui.b);
+                            tma_prefetch_l2_3d(&p.tmQq, E + h0 + 64 * j, (pf_t - 1) * AU_BM, pf_ui.b);
+                            tma_prefetch_l2_3d(&p.tmQq, 2 * E + h0 + 64 * j, (pf_t - 1) * AU_BM, pf_ui.b);    // own-value rows (epilogue)
+                        }
                     }
                 }
                 if (++pf_t >= pf_ui.t_hi) {
@@ -155,32 +160,38 @@ __global__ void __launch_bounds__(AU_THREADS, 1) attention_umma_kernel(const __g
             for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++un) {
                 const UnitInfo ui = decode_unit(p, u);
                 mbar_wait(kf_empty, (un & 1u) ^ 1u);
-                mbar_arrive_expect_tx(kf_full, kv_bytes);
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(kf_full, kv_bytes);
 #pragma unroll
-                for (int j = 0; j < KBOX; ++j) tma_load_3d(sKF + j * box_kv, &p.tmKV, kf_full, E + ui.h * HD + 64 * j, 0, ui.b);
+                    for (int j = 0; j < KBOX; ++j) tma_load_3d(sKF + j * box_kv, &p.tmKV, kf_full, E + ui.h * HD + 64 * j, 0, ui.b);
+                }
                 for (int t = ui.t_lo; t < ui.t_hi; ++t, ++g) {
                     const int st = g % NST;
                     const uint32_t ph = (g / NST) & 1u;
                     if (p.pf_mode >= 1) prefetch_next();
                     mbar_wait(q_empty(st), ph ^ 1u);
-                    mbar_arrive_expect_tx(q_full(st), t == 0 ? C::Q_BYTES : 2 * C::Q_BYTES);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(q_full(st), t == 0 ? C::Q_BYTES : 2 * C::Q_BYTES);
 #pragma unroll
-                    for (int j = 0; j < KBOX; ++j) {
-                        if (t == 0) {
-                            tma_load_3d(sQ(st) + j * 16384, &p.tmQf, q_full(st), ui.h * HD + 64 * j, 0, ui.b);
-                        } else {
-                            tma_load_3d(sQ(st) + j * 16384, &p.tmQq, q_full(st), ui.h * HD + 64 * j, (t - 1) * AU_BM, ui.b);
-                            tma_load_3d(sB(st) + j * 16384, &p.tmQq, q_full(st), E + ui.h * HD + 64 * j, (t - 1) * AU_BM, ui.b);
+                        for (int j = 0; j < KBOX; ++j) {
+                            if (t == 0) {
+                                tma_load_3d(sQ(st) + j * 16384, &p.tmQf, q_full(st), ui.h * HD + 64 * j, 0, ui.b);
+                            } else {
+                                tma_load_3d(sQ(st) + j * 16384, &p.tmQq, q_full(st), ui.h * HD + 64 * j, (t - 1) * AU_BM, ui.b);
+                                tma_load_3d(sB(st) + j * 16384, &p.tmQq, q_full(st), E + ui.h * HD + 64 * j, (t - 1) * AU_BM, ui.b);
+                            }
                         }
                     }
                     if (t == ui.t_lo) {
                         // V_f after the unit's first Q tile: the MMA warp issues S of that tile before the last P.V of
                         // the previous unit, which is what releases the V_f buffer
                         mbar_wait(vf_empty, (un & 1u) ^ 1u);
-                        mbar_arrive_expect_tx(vf_full, kv_bytes);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(vf_full, kv_bytes);
 #pragma unroll
-                        for (int j = 0; j < KBOX; ++j)
-                            tma_load_3d(sVF + j * box_kv, &p.tmKV, vf_full, 2 * E + ui.h * HD + 64 * j, 0, ui.b);
+                            for (int j = 0; j < KBOX; ++j)
+                                tma_load_3d(sVF + j * box_kv, &p.tmKV, vf_full, 2 * E + ui.h * HD + 64 * j, 0, ui.b);
+                        }
                     }
                 }
             }
@@ -188,7 +199,7 @@ __global__ void __launch_bounds__(AU_THREADS, 1) attention_umma_kernel(const __g
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        {
             const uint32_t idesc_s = umma_idesc_f16(FmtOfA<T>::v, AU_BM, static_cast<uint32_t>(Fp));
             const uint32_t idesc_self = umma_idesc_f16(FmtOfA<T>::v, AU_BM, AU_BM);
             const uint32_t idesc_o = umma_idesc_f16(FmtOfA<T>::v, AU_BM, HD) | (1u << 16);     // B (= V_f) is MN-major
@@ -198,13 +209,15 @@ __global__ void __launch_bounds__(AU_THREADS, 1) attention_umma_kernel(const __g
                 mbar_wait(p_full(st), ph);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(st * C::TMEM_STAGE);      // O overwrites the consumed S
-                for (int k = 0; k < ksteps_o; ++k) {
-                    const uint64_t adesc = umma_desc_sw128(sP(st) + (k >> 2) * 16384) + 2u * (k & 3);
-                    const uint64_t bdesc = umma_desc_mn_sw128(sVF + k * 2048, box_kv);
-                    umma_f16_ss(d_tmem, adesc, bdesc, idesc_o, k != 0 ? 1u : 0u);
+                if (elect_one()) {
+                    for (int k = 0; k < ksteps_o; ++k) {
+                        const uint64_t adesc = umma_desc_sw128(sP(st) + (k >> 2) * 16384) + 2u * (k & 3);
+                        const uint64_t bdesc = umma_desc_mn_sw128(sVF + k * 2048, box_kv);
+                        umma_f16_ss(d_tmem, adesc, bdesc, idesc_o, k != 0 ? 1u : 0u);
+                    }
+                    umma_commit(o_full(st));
+                    if (last) umma_commit(vf_empty);
                 }
-                umma_commit(o_full(st));
-                if (last) umma_commit(vf_empty);
             };
             uint32_t g = 0, un = 0;
             bool have_prev = false, prev_first = false, prev_last = false;
@@ -218,23 +231,25 @@ __global__ void __launch_bounds__(AU_THREADS, 1) attention_umma_kernel(const __g
                     mbar_wait(q_full(st), ph);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(st * C::TMEM_STAGE);
-#pragma unroll
-                    for (int k = 0; k < HD / 16; ++k) {
-                        const uint64_t adesc = umma_desc_sw128(sQ(st) + (k >> 2) * 16384) + 2u * (k & 3);
-                        const uint64_t bdesc = umma_desc_sw128(sKF + (k >> 2) * box_kv) + 2u * (k & 3);
-                        umma_f16_ss(d_tmem, adesc, bdesc, idesc_s, k != 0 ? 1u : 0u);
-                    }
-                    if (t > 0) {
+                    const bool first = t == ui.t_lo, last = t == ui.t_hi - 1;
+                    if (elect_one()) {
 #pragma unroll
                         for (int k = 0; k < HD / 16; ++k) {
                             const uint64_t adesc = umma_desc_sw128(sQ(st) + (k >> 2) * 16384) + 2u * (k & 3);
-                            const uint64_t bdesc = umma_desc_sw128(sB(st) + (k >> 2) * 16384) + 2u * (k & 3);
-                            umma_f16_ss(d_tmem + 128, adesc, bdesc, idesc_self, k != 0 ? 1u : 0u);
+                            const uint64_t bdesc = umma_desc_sw128(sKF + (k >> 2) * box_kv) + 2u * (k & 3);
+                            umma_f16_ss(d_tmem, adesc, bdesc, idesc_s, k != 0 ? 1u : 0u);
                         }
+                        if (t > 0) {
+#pragma unroll
+                            for (int k = 0; k < HD / 16; ++k) {
+                                const uint64_t adesc = umma_desc_sw128(sQ(st) + (k >> 2) * 16384) + 2u * (k & 3);
+                                const uint64_t bdesc = umma_desc_sw128(sB(st) + (k >> 2) * 16384) + 2u * (k & 3);
+                                umma_f16_ss(d_tmem + 128, adesc, bdesc, idesc_self, k != 0 ? 1u : 0u);
+                            }
+                        }
+                        umma_commit(s_full(st));
+                        if (last) umma_commit(kf_empty);
                     }
-                    umma_commit(s_full(st));
-                    const bool first = t == ui.t_lo, last = t == ui.t_hi - 1;
-                    if (last) umma_commit(kf_empty);
                     if (NST == 1) {
                         issue_pv(st, ph, un, first, last);
                     } else {

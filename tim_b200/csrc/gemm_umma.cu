@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_umma_kernel(const __gri
     uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * C::STAGE_BYTES + 8 * (2 * STAGES + 4));
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);     // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
     const int num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
     const int num_tiles = p.tiles_m * p.tiles_n;
@@ -80,50 +80,51 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_umma_kernel(const __gri
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
 
+    // producer and MMA warps: warp-uniform loops, elect_one() only around the asynchronous-issue instructions (see gemm_umma2.cu)
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
-                const int g0 = (tm / p.tiles_r) * p.rm.box_g;
-                const int r0 = (tm % p.tiles_r) * p.rm.box_r;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
+        int stage = 0; uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+            const int g0 = (tm / p.tiles_r) * p.rm.box_g;
+            const int r0 = (tm % p.tiles_r) * p.rm.box_r;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(empty_bar(stage), phase ^ 1u);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(full_bar(stage), a_bytes + C::B_STAGE_BYTES);
                     tma_load_3d(smem_a + stage * A_STAGE_BYTES, &p.tmA, full_bar(stage), kb * BLOCK_K, p.rm.a_row_off + r0, g0);
                     tma_load_2d(smem_b + stage * C::B_STAGE_BYTES, &p.tmB, full_bar(stage), kb * BLOCK_K, tn * BLOCK_N);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_f16(FmtOf<T>::v, BLOCK_M, BLOCK_N);
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        constexpr uint32_t idesc = umma_idesc_f16(FmtOf<T>::v, BLOCK_M, BLOCK_N);
+        int stage = 0; uint32_t phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(full_bar(stage), phase);
-                    tc_fence_after();
-                    const uint64_t adesc = umma_desc_sw128(smem_a + stage * A_STAGE_BYTES);
-                    const uint64_t bdesc = umma_desc_sw128(smem_b + stage * C::B_STAGE_BYTES);
+                const uint64_t adesc = umma_desc_sw128(smem_a + stage * A_STAGE_BYTES);
+                const uint64_t bdesc = umma_desc_sw128(smem_b + stage * C::B_STAGE_BYTES);
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                         // advance 16 elements (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
                         umma_f16_ss(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(empty_bar(stage));          // frees the smem stage once these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(tfull_bar(acc));                // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             }
+            if (elect_one()) umma_commit(tfull_bar(acc));   // accumulator complete -> epilogue
+            if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
         }
         __syncwarp();
     } else {
