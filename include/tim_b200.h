@@ -138,6 +138,26 @@ int tim_label_queries(const float* queries, const float* gt_segs, const int64_t*
 int tim_smooth_labels(const int64_t* label_ids, int stride, int col, int64_t rows, int num_classes, double smoothing, float* out,
                       void* stream);
 
+/* Detection post-processing: 1-D soft-NMS / NMS over G independent groups of proposals (a group = one class of one video), one
+ * launch for all groups. Replaces the reference's scalar CPU extension and the per-class / per-video loops that drive it:
+ *   tim_softnms_1d  <- nms_1d_cpu.softnms (detection/eval_detection/csrc/nms_cpu.cpp:67-160) under SoftNMSop (nms.py:35-61)
+ *   tim_nms_1d      <- nms_1d_cpu.nms     (csrc/nms_cpu.cpp:19-58) under NMSop (nms.py:7-33: scores <= min_score are dropped
+ *                      first when min_score > 0, at most max_num picks when max_num > 0)
+ * segs [N,2], scores [N] fp32; group g owns rows group_offsets[g] .. group_offsets[g+1] (int64 [G+1], ascending). For group g the
+ * picks are written in pick order (= descending final score) to rows group_offsets[g] .. + kept[g] of dets [N,3] = (start, end,
+ * score after decay) and inds [N] (index of the pick INSIDE its group); rows beyond kept[g] are left untouched. method: 0 vanilla,
+ * 1 linear, 2 gaussian exp(-iou^2 / sigma). Pick order and indices equal the reference's, including its order-dependent handling
+ * of equal scores (tim_nms_1d breaks ties by input index, i.e. a stable descending sort; the reference's torch.sort leaves that
+ * order unspecified). Scores must not be NaN. workspace: tim_nms_workspace_bytes(N) bytes of device memory. All pointers are
+ * device pointers; stateless, errors through tim_last_error(NULL). */
+size_t tim_nms_workspace_bytes(int64_t N);
+int tim_softnms_1d(const float* segs, const float* scores, const int64_t* group_offsets, int G, int64_t N, float iou_threshold,
+                   float sigma, float min_score, int method, float* dets /*[N,3]*/, int64_t* inds /*[N]*/, int* kept /*[G]*/,
+                   void* workspace, size_t workspace_bytes, void* stream);
+int tim_nms_1d(const float* segs, const float* scores, const int64_t* group_offsets, int G, int64_t N, float iou_threshold,
+               float min_score, int64_t max_num, float* dets /*[N,3]*/, int64_t* inds /*[N]*/, int* kept /*[G]*/, void* workspace,
+               size_t workspace_bytes, void* stream);
+
 /* Live per-kernel-class timing (bench.py's roofline object): between begin and end every launch is bracketed by a
  * CUDA-event pair on its own stream. Classes: 0 GEMM (tcgen05 / fp32 SIMT) other than 5 and 6, 1 attention, 2 LayerNorm /
  * row statistics, 3 token assembly, 4 other row kernels, 5 encoder GEMMs with a folded LayerNorm in front (in_proj, linear1:

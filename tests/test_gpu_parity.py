@@ -482,3 +482,130 @@ def test_errors_are_loud(lib):
         eng.set_weight("time_mlp.0.bias", torch.zeros(3))
     eng.set_weight("drloc_mlp.0.bias", torch.zeros(512))          # accepted and ignored
     eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# detection post-processing: 1-D (soft-)NMS kernels through tim_softnms_1d / tim_nms_1d
+# ---------------------------------------------------------------------------------------------------------------------
+from tests.test_oracle_golden import NMS_CASES, NMS_SCORE_RTOL, nms_case, nms_golden   # noqa: E402
+
+
+def _device_group_nms(segs, scores, prm, kind):
+    """One group through the library; returns (inds, dets) like the reference extension."""
+    from tim_b200.postprocess import grouped_nms
+    keys = torch.zeros((len(scores),), dtype=torch.int64)
+    if kind == "soft":
+        s, p, _, src = grouped_nms(torch.from_numpy(segs), torch.from_numpy(scores), keys, nms="soft", device=torch.device("cuda", 0), **prm)
+    else:
+        s, p, _, src = grouped_nms(torch.from_numpy(segs), torch.from_numpy(scores), keys, nms="vanilla", min_score=0.0,
+                                   device=torch.device("cuda", 0), **prm)
+    return src.cpu().numpy(), np.concatenate([s.cpu().numpy(), p.cpu().numpy()[:, None]], 1)
+
+
+@pytest.mark.parametrize("name", NMS_CASES)
+def test_nms_kernel_vs_reference_golden(lib, name):
+    """CUDA (soft-)NMS against the outputs of the reference's compiled extension / batched_nms driver (tests/golden/nms.npz):
+    pick order, indices and segments exact; decayed scores to NMS_SCORE_RTOL (expf rounding). Hard NMS with equal scores is
+    compared with the oracle's stable order (the reference's is torch-sort dependent) plus the reference's kept score sequence."""
+    from oracle import nms_oracle as o
+    from tim_b200.postprocess import batched_nms
+    g = nms_golden()
+    kind, segs, scores, cls, prm = nms_case(g, name)
+    if kind == "soft":
+        inds, dets = _device_group_nms(segs, scores, prm, kind)
+        ref = g[f"{name}/dets"]
+        assert np.array_equal(inds, g[f"{name}/inds"])
+        assert np.array_equal(dets[:, :2], ref[:, :2])
+        np.testing.assert_allclose(dets[:, 2], ref[:, 2], rtol=NMS_SCORE_RTOL, atol=0)
+    elif kind == "nms":
+        inds, dets = _device_group_nms(segs, scores, prm, kind)
+        assert np.array_equal(inds, o.nms_1d(segs, scores, **prm))
+        assert np.array_equal(dets[:, 2], scores[g[f"{name}/inds"]])
+        assert np.array_equal(dets[:, :2], segs[inds])
+    else:
+        s, p, c = batched_nms(segs, scores, cls, device=torch.device("cuda", 0), **prm)
+        assert np.array_equal(s, g[f"{name}/out_segs"]) and np.array_equal(c, g[f"{name}/out_cls"])
+        np.testing.assert_allclose(p, g[f"{name}/out_scores"], rtol=NMS_SCORE_RTOL, atol=0)
+
+
+def _random_proposals(rng, n, n_centres=6):
+    c = rng.uniform(0, 60, n_centres)
+    start = c[rng.integers(0, n_centres, n)] + rng.normal(0, 0.5, n)
+    segs = np.stack([start, start + np.abs(rng.normal(3, 0.6, n)) + 0.05], 1).astype(np.float32)
+    return segs, rng.uniform(0.01, 1, n).astype(np.float32)
+
+
+@pytest.mark.parametrize("nms,method", [("soft", 2), ("soft", 1), ("soft", 0), ("vanilla", 0)])
+def test_nms_many_groups_vs_oracle(lib, nms, method):
+    """Many (video, class) groups of ragged sizes in one launch (sizes 1 .. 700, duplicates and equal scores included) against
+    the oracle run group by group; also checks batched_nms_videos' ordering (video ascending, score descending)."""
+    from oracle import nms_oracle as o
+    from tim_b200.postprocess import batched_nms_videos
+    rng = np.random.default_rng(11 + method)
+    n_vid, n_cls = 5, 9
+    N = 6000
+    segs, scores = _random_proposals(rng, N, 12)
+    scores[::7] = np.round(scores[::7], 1)                   # equal scores
+    segs[::11] = np.round(segs[::11], 0)                     # duplicate / nested segments
+    segs[:, 1] = np.maximum(segs[:, 1], segs[:, 0] + np.float32(0.05))
+    vid = rng.integers(0, n_vid, N)
+    cls = (rng.integers(0, n_cls, N) ** 2) % 23             # uneven class sizes, sparse ids
+    vid[:3], cls[:3] = 4, 22                                 # a 3-entry group
+    prm = dict(iou_threshold=0.3, min_score=0.02, sigma=0.3, method=method, nms=nms)
+    s, p, c, v = (t.cpu().numpy() for t in batched_nms_videos(segs, scores, cls, vid, device=torch.device("cuda", 0), **prm))
+    at = 0
+    for video in range(n_vid):
+        sel = vid == video
+        rs, rp, rc = o.batched_nms(segs[sel], scores[sel], cls[sel], **prm)
+        k = len(rp)
+        assert np.all(v[at:at + k] == video)
+        np.testing.assert_allclose(p[at:at + k], rp, rtol=NMS_SCORE_RTOL, atol=0)
+        # equal final scores may be ordered differently by the two final sorts: compare as sorted rows
+        got = sorted(zip(s[at:at + k, 0].tolist(), s[at:at + k, 1].tolist(), c[at:at + k].tolist()))
+        want = sorted(zip(rs[:, 0].tolist(), rs[:, 1].tolist(), rc.tolist()))
+        assert got == want, video
+        at += k
+    assert at == len(p)
+
+
+def test_nms_group_larger_than_shared_memory(lib):
+    """A group above the kernel's shared-memory capacity (4096 proposals) runs from the global scratch: same result as the
+    oracle, and the same result as when it is one of several groups."""
+    from oracle import nms_oracle as o
+    rng = np.random.default_rng(5)
+    segs, scores = _random_proposals(rng, 9000, 8)
+    prm = dict(iou_threshold=0.1, sigma=0.25, min_score=0.05, method=2)
+    inds, dets = _device_group_nms(segs, scores, prm, "soft")
+    ri, rd = o.softnms_1d(segs, scores, **prm)
+    assert np.array_equal(inds, ri) and np.array_equal(dets[:, :2], rd[:, :2])
+    np.testing.assert_allclose(dets[:, 2], rd[:, 2], rtol=NMS_SCORE_RTOL, atol=0)
+    hi, hd_ = _device_group_nms(segs, scores, dict(iou_threshold=0.4), "nms")
+    assert np.array_equal(hi, o.nms_1d(segs, scores, 0.4))
+
+
+def test_nms_edge_cases_and_errors(lib):
+    from tim_b200 import _lib
+    from tim_b200.postprocess import batched_nms, grouped_nms
+    dev = torch.device("cuda", 0)
+    s, p, c = batched_nms(np.zeros((0, 2), np.float32), np.zeros((0,), np.float32), np.zeros((0,), np.int64), 0.1, 0.001, device=dev)
+    assert s.shape == (0, 2) and p.shape == (0,) and c.shape == (0,)
+    # every proposal its own class: nothing is suppressed, order = descending score
+    segs = np.array([[0, 1], [0, 1], [0, 1]], np.float32)
+    sc = np.array([0.2, 0.9, 0.5], np.float32)
+    s, p, c = batched_nms(segs, sc, np.array([7, 3, 5]), 0.1, 0.001, device=dev)
+    assert p.tolist() == sorted(sc.tolist(), reverse=True) and c.tolist() == [3, 5, 7]
+    # hard NMS: max_seg_num caps the picks per class, min_score filters first (nms.py:15-27)
+    segs = np.array([[0, 1], [2, 3], [4, 5], [6, 7]], np.float32)
+    sc = np.array([0.9, 0.8, 0.0005, 0.7], np.float32)
+    s, p, c = batched_nms(segs, sc, np.zeros(4, np.int64), 0.5, 0.001, nms="vanilla", max_seg_num=2, device=dev)
+    assert p.tolist() == [np.float32(0.9), np.float32(0.8)]
+    s, p, c = batched_nms(segs, sc, np.zeros(4, np.int64), 0.5, 0.001, nms="vanilla", device=dev)
+    assert len(p) == 3
+    with pytest.raises(_lib.TimError):
+        grouped_nms(torch.zeros((2, 2)), torch.ones(2), torch.zeros(2, dtype=torch.int64), iou_threshold=0.1, min_score=0.0,
+                    method=3, device=dev)
+    with pytest.raises(_lib.TimError):
+        grouped_nms(torch.zeros((2, 2)), torch.ones(2), torch.zeros(2, dtype=torch.int64), iou_threshold=0.1, min_score=0.0,
+                    method=2, sigma=0.0, device=dev)
+    with pytest.raises(NotImplementedError):
+        batched_nms(segs, sc, np.zeros(4, np.int64), 0.5, 0.001, multi_class=False, device=dev)

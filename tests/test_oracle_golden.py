@@ -121,3 +121,100 @@ def test_label_oracle_matches_reference_golden(name):
             assert ref.size == 0
             continue
         assert np.array_equal(smooth_labels(ids[:, k if name != "aud" else 0], C_, sm), ref)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# detection post-processing: 1-D (soft-)NMS
+# ---------------------------------------------------------------------------------------------------------------------
+def nms_golden():
+    return np.load(os.path.join(GOLD, "nms.npz"))
+
+
+def nms_case(g, name):
+    """(kind, segs, scores, cls | None, params) of one golden case."""
+    prm = {k.split("/p_")[1]: g[k].item() for k in g.files if k.startswith(f"{name}/p_")}
+    cls = g[f"{name}/cls"] if f"{name}/cls" in g.files else None
+    return str(g[f"{name}/kind"]), g[f"{name}/segs"], g[f"{name}/scores"], cls, prm
+
+
+NMS_CASES = [str(n) for n in np.load(os.path.join(GOLD, "nms.npz"))["names"]]
+NMS_SCORE_RTOL = 1e-6          # glibc expf (reference) vs correctly rounded exp (oracle, device): at most an ulp or two
+
+
+@pytest.mark.parametrize("name", NMS_CASES)
+def test_nms_oracle_matches_reference_golden(name):
+    """oracle/nms_oracle.py against the outputs of the reference's own compiled extension and its batched_nms driver
+    (tests/golden/nms.npz, minted by tools/make_golden_nms.py): pick order and indices exact, segments exact, decayed scores to
+    NMS_SCORE_RTOL. For hard NMS with equal scores the reference's pick among them follows torch's unstable sort, so that case
+    pins the kept score sequence and the kept count instead of the indices."""
+    from oracle import nms_oracle as o
+    g = nms_golden()
+    kind, segs, scores, cls, prm = nms_case(g, name)
+    if kind == "soft":
+        inds, dets = o.softnms_1d(segs, scores, **prm)
+        assert np.array_equal(inds, g[f"{name}/inds"])
+        ref = g[f"{name}/dets"]
+        assert np.array_equal(dets[:, :2], ref[:, :2])
+        np.testing.assert_allclose(dets[:, 2], ref[:, 2], rtol=NMS_SCORE_RTOL, atol=0)
+    elif kind == "nms":
+        inds = o.nms_1d(segs, scores, **prm)
+        if name.endswith("ties"):
+            assert np.array_equal(scores[inds], scores[g[f"{name}/inds"]])
+        else:
+            assert np.array_equal(inds, g[f"{name}/inds"])
+    else:
+        s, p, c = o.batched_nms(segs, scores, cls, **prm)
+        assert np.array_equal(s, g[f"{name}/out_segs"]) and np.array_equal(c, g[f"{name}/out_cls"])
+        np.testing.assert_allclose(p, g[f"{name}/out_scores"], rtol=NMS_SCORE_RTOL, atol=0)
+
+
+def test_nms_oracle_matches_compiled_reference_random():
+    """More seeded cases against oracle/_ref/nms_1d_cpu.so (the reference's source compiled by oracle/build_ref.py) when it is
+    present; the golden file above is the pin that travels."""
+    from oracle import build_ref, nms_oracle as o
+    mod = build_ref.load()
+    if mod is None:
+        pytest.skip("oracle/_ref/nms_1d_cpu.so not built (reference tree absent)")
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(7)
+    for trial in range(12):
+        n = int(rng.integers(1, 400))
+        c = rng.uniform(0, 30, 5)
+        start = c[rng.integers(0, 5, n)] + rng.normal(0, 0.5, n)
+        segs = np.stack([start, start + np.abs(rng.normal(2, 0.5, n)) + 0.05], 1).astype(np.float32)
+        scores = rng.uniform(0.01, 1, n).astype(np.float32)
+        method, mins, thr = trial % 3, float(rng.choice([0.001, 0.05])), float(rng.choice([0.1, 0.5]))
+        dets = torch.zeros((n, 3))
+        ref_inds = mod.softnms(torch.from_numpy(segs), torch.from_numpy(scores), dets, thr, 0.25, mins, method).numpy()
+        inds, d = o.softnms_1d(segs, scores, thr, 0.25, mins, method)
+        assert np.array_equal(inds, ref_inds), trial
+        np.testing.assert_allclose(d, dets[:len(inds)].numpy(), rtol=NMS_SCORE_RTOL, atol=0)
+        assert np.array_equal(o.nms_1d(segs, scores, thr), mod.nms(torch.from_numpy(segs), torch.from_numpy(scores), thr).numpy())
+
+
+def test_parallel_deletion_equals_sequential_scan():
+    """The identity tim_b200/csrc/nms.cu relies on: the reference deletes inside its decay scan by moving the LAST live entry into
+    the hole and re-examining it (nms_cpu.cpp:147-156); with n' survivors, that leaves the k-th hole below n' (ascending) holding
+    the k-th surviving entry at or above n' counted from the end. Literal transcription vs the closed form, random flags."""
+    rng = np.random.default_rng(3)
+    for _ in range(3000):
+        n = int(rng.integers(1, 48))
+        i = int(rng.integers(0, n))
+        vals = list(rng.permutation(n))
+        pr = float(rng.choice([0.05, 0.3, 0.7, 1.0]))
+        removed = {v for q, v in enumerate(vals) if q > i and rng.random() < pr}
+        a, m, pos = list(vals), n, i + 1
+        while pos < m:                                     # the reference's scan
+            if a[pos] in removed:
+                a[pos] = a[m - 1]
+                m -= 1
+                pos -= 1
+            pos += 1
+        b = list(vals)
+        n2 = n - len(removed)
+        holes = [q for q in range(i + 1, n2) if b[q] in removed]
+        movers = [q for q in range(n2, n) if b[q] not in removed]
+        assert len(holes) == len(movers)
+        for k, h in enumerate(holes):
+            b[h] = vals[movers[len(movers) - 1 - k]]
+        assert a[:m] == b[:n2]

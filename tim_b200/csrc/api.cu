@@ -1075,20 +1075,40 @@ int tim_forward_host(tim_ctx* c, const float* vis, const float* aud, const float
     TIM_TRY(encoder_ws(c, cpc, T_, Qv, Qa, &need_e));
     TIM_TRY(ensure_ws(c, need_t > need_e ? need_t : need_e));
 
-    // chunk schedule: full chunks of cpc clips with tapered ends (cpc/4, cpc/2 ... cpc/2, cpc/4) so that the un-overlapped
-    // H2D of the first chunk and D2H of the last chunk are short
+    // chunk schedule: full chunks of about cpc clips with tapered ends (a quarter, a half ... a half, a quarter) so that the
+    // un-overlapped H2D of the first chunk and D2H of the last chunk are short. On the 16-bit path chunk sizes are aligned to
+    // whole WAVES of GEMM tiles: the encoder GEMMs run 256-row tiles on num_sms persistent CTAs, so a chunk whose row-tile count
+    // is a multiple of num_sms / gcd(num_sms, E / 256) fills every wave of all four of them (E = 1024 on 148 SMs: 37 row tiles
+    // = 47 clips of 200 tokens); a 64-clip chunk would leave out_proj / linear2 at 1.35 waves = 68 % occupancy.
     std::vector<int> chunk_b0, chunk_nb;
     {
+        const int rows_per_clip = c->Ft + qp.Qt;
+        int unit_tiles = 0;
+        if (g.compute_dtype != TIM_FP32 && c->E % 256 == 0 && rows_per_clip > 0) {
+            int a = c->num_sms, b = c->E / 256;
+            while (b) { const int t = a % b; a = b; b = t; }
+            unit_tiles = c->num_sms / a;
+        }
+        auto unit_clips = [&](int k) { return static_cast<int>(static_cast<long long>(k) * unit_tiles * 256 / rows_per_clip); };
         std::vector<int> head, tail;
-        int left = B;
-        if (B >= 4 * cpc && cpc >= 8) {
+        int left = B, body = cpc;
+        const int body_units = (unit_tiles > 0 && unit_clips(1) >= 8) ? cpc / unit_clips(1) : 0;
+        if (body_units >= 1) {
+            body = unit_clips(body_units);
+            if (B >= 3 * body && body_units >= 4) {
+                head = {unit_clips(body_units / 4), unit_clips(body_units / 2)};
+                tail = {head[1], head[0]};
+            }
+        } else if (B >= 4 * cpc && cpc >= 8) {
             head = {cpc / 4, cpc / 2};
             tail = {cpc / 2, cpc / 4};
-            left -= cpc / 4 * 2 + cpc / 2 * 2;
         }
+        for (int n : head) left -= 2 * n;
         int b0 = 0;
         for (int n : head) { chunk_b0.push_back(b0); chunk_nb.push_back(n); b0 += n; }
-        while (left > 0) { const int n = left < cpc ? left : cpc; chunk_b0.push_back(b0); chunk_nb.push_back(n); b0 += n; left -= n; }
+        // the remainder that does not fill a body chunk goes early (behind the head), not into the D2H tail
+        if (left % body) { const int n = left % body; chunk_b0.push_back(b0); chunk_nb.push_back(n); b0 += n; left -= n; }
+        while (left > 0) { chunk_b0.push_back(b0); chunk_nb.push_back(body); b0 += body; left -= body; }
         for (int n : tail) { chunk_b0.push_back(b0); chunk_nb.push_back(n); b0 += n; }
     }
     const int nchunks = static_cast<int>(chunk_nb.size());
