@@ -4,10 +4,12 @@
 // Replaces the torch addmm calls under  */models/helpers/transformers.py:102-109,  encodings.py:140-153,
 // tim.py:66-74, head.py (reference is library calls only; there is no reference kernel).
 //
-// Structure (one persistent CTA per SM, 192 threads):
+// Structure (one persistent CTA per SM, 320 threads):
 //   warp 0   : TMA producer  - A tile (128 rows x 64 k) and W tile (BLOCK_N x 64 k) per stage, 128B swizzle
 //   warp 1   : MMA issuer    - one elected lane issues tcgen05.mma 128 x BLOCK_N x 16, fp32 accumulators in TMEM
-//   warps 2-5: epilogue      - tcgen05.ld 32 lanes x 32 columns, bias / ReLU / erf-GELU / residual, vector stores
+//   warps 2-9: epilogue      - tcgen05.ld 32 lanes x 32 columns, bias / ReLU / erf-GELU / residual, vector stores; the two
+//                              warps of a TMEM lane quarter take half of the tile's columns each (one epilogue warp per
+//                              scheduler left the tcgen05.ld / bias-load / store latencies exposed: 20 % issue utilisation)
 // Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue; two accumulator
 // stages so the epilogue of tile i overlaps the main loop of tile i+1), and a static persistent tile schedule
 // (tile = blockIdx.x + i * gridDim.x, N fastest so CTAs running concurrently share the A tile through L2).
@@ -22,16 +24,21 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                    // 64 x 2 B = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
-constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BUDGET = 192 * 1024;
+constexpr int NUM_THREADS = 320;                // TMA warp, MMA warp, 8 epilogue warps
+constexpr int EPI_WARPS = 8;
+constexpr int SMEM_BUDGET = 184 * 1024;          // pipeline stages (3 x 48 KB at BLOCK_N = 256); the rest holds the epilogue scratch
 
 template <int BLOCK_N> struct Cfg {
     static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
     static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
     static constexpr int STAGES = SMEM_BUDGET / STAGE_BYTES;
     static constexpr int TMEM_COLS = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;   // two accumulator stages (power of two)
-    static constexpr int XPOSE_BYTES = 4 * 32 * 33 * 4;     // per-epilogue-warp transpose scratch (coalesced fp32 stores)
+    // per-epilogue-warp scratch for the coalesced fp32 stores: a 32 x 33 float transpose tile + the 32 output-row offsets
+    static constexpr int XPOSE_WARP_BYTES = 32 * 33 * 4 + 32 * 8;
+    static constexpr int XPOSE_BYTES = EPI_WARPS * XPOSE_WARP_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + XPOSE_BYTES;
+    static_assert(SMEM_BYTES <= 227 * 1024, "exceeds the per-CTA shared memory of sm_100");
+    static_assert((2 * STAGES + 4) * 8 + 4 <= 256, "barrier area too small");
 };
 
 template <typename T> struct FmtOf;
@@ -68,7 +75,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_umma_kernel(const __gri
     if (warp == 1) {
         if (lane == 0) {
             for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-            for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+            for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
             fence_mbar_init();
         }
         __syncwarp();
@@ -128,10 +135,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_umma_kernel(const __gri
         }
         __syncwarp();
     } else {
-        // ===================== epilogue (warps 2..5) =====================
+        // ===================== epilogue (warps 2..9) =====================
         const int quarter = warp & 3;                        // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;                    // which half of the tile's columns
         const int row_in_tile = quarter * 32 + lane;
-        const uint32_t xpose = bar_base + 256u + static_cast<uint32_t>(warp - 2) * (32 * 33 * 4);
+        const uint32_t xpose = bar_base + 256u + static_cast<uint32_t>(warp - 2) * C::XPOSE_WARP_BYTES;
+        const uint32_t xrows = xpose + 32 * 33 * 4;          // 32 x int64: output element offset of each row of the quarter, -1 = no row
         const Epilogue& ep = p.ep;
         int acc = 0; uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -146,33 +155,44 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_umma_kernel(const __gri
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+            const bool xp_tile = ep.out_fp32 && !ep.resid;   // the transposed-store path may be taken in this tile
+            if (xp_tile) {
+                __syncwarp();
+                sts_u64(xrows + static_cast<uint32_t>(lane) * 8u, row_ok ? static_cast<unsigned long long>(orow) * static_cast<unsigned long long>(ep.ldo) : ~0ull);
+                __syncwarp();
+            }
 #pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+            for (int c0 = half * (BLOCK_N / 2); c0 < (half + 1) * (BLOCK_N / 2); c0 += 32) {
                 if (n0 + c0 >= p.N) break;                   // warp-uniform
                 uint32_t v[32];
                 tmem_ld_32x32(t_addr + c0, v);
-                tmem_ld_wait();
                 const int n = n0 + c0;
                 const bool full = (n + 32 <= p.N);
+                // bias of the chunk, fetched while the TMEM load is in flight
+                float bia[32];
+                if (ep.bias) {
+                    if (full) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + j));
+                            bia[j] = b4.x; bia[j + 1] = b4.y; bia[j + 2] = b4.z; bia[j + 3] = b4.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) bia[j] = (n + j < p.N) ? __ldg(ep.bias + n + j) : 0.0f;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) bia[j] = 0.0f;
+                }
+                tmem_ld_wait();
                 // fp32 rows whose pitch is not 16-byte aligned (e.g. the 3806-class action head) or a ragged last chunk: transpose
                 // through smem so that every store instruction writes 32 consecutive floats of ONE row (warp-uniform choice)
                 const bool xp = ep.out_fp32 && !ep.resid && (!full || (ep.ldo & 3) != 0);
                 if (!row_ok && !xp) continue;
                 float f[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                if (ep.bias) {
-                    if (full) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n + j));
-                            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) if (n + j < p.N) f[j] += __ldg(ep.bias + n + j);
-                    }
-                }
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + bia[j];
                 if (ep.act == ACT_RELU) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
@@ -205,13 +225,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) linear_umma_kernel(const __gri
 #pragma unroll
                         for (int j = 0; j < 32; ++j) sts_f32(xpose + static_cast<uint32_t>((lane * 33 + j) * 4), f[j]);
                         __syncwarp();
-                        const long long my_orow = row_ok ? static_cast<long long>(orow) : -1LL;
                         float* obase = reinterpret_cast<float*>(ep.out) + n + lane;
                         const bool col_ok = n + lane < p.N;
-#pragma unroll 4
+#pragma unroll 8
                         for (int r = 0; r < 32; ++r) {
-                            const long long ro = __shfl_sync(0xffffffffu, my_orow, r);
-                            if (ro >= 0 && col_ok) obase[ro * ep.ldo] = lds_f32(xpose + static_cast<uint32_t>((r * 33 + lane) * 4));
+                            const unsigned long long ro = lds_u64(xrows + static_cast<uint32_t>(r) * 8u);      // broadcast read
+                            const float val = lds_f32(xpose + static_cast<uint32_t>((r * 33 + lane) * 4));
+                            if (ro != ~0ull && col_ok) obase[ro] = val;
                         }
                         __syncwarp();
                     } else if (full && (ep.ldo & 3) == 0) {
