@@ -260,7 +260,10 @@ def main():
     hv = vis.cpu().pin_memory() if vis is not None else None
     ha = aud.cpu().pin_memory() if aud is not None else None
     ht = times.cpu().pin_memory()
-    chunk = args.chunk or max(1, B // 4)
+    # target chunk of the H2D / compute / D2H pipeline; the library tapers the ends and aligns chunk sizes to whole waves of GEMM
+    # tiles (tim_forward_host). B // 3 measured best on cfg2 (27.8 ms vs 27.9 at B // 5 and 28.9 at B // 4, whose remainder
+    # chunk of 34 clips runs at a quarter wave)
+    chunk = args.chunk or max(1, B // 3)
     # what the reference's eval loop brings back to the host: the logits / regression outputs (recognition/scripts/test.py:
     # 106-131 reads output[0] only); the feature rows output[1] feed the drloc loss in training and stay on the device
     hout = eng._alloc_outputs(B, Qv, Qa, pinned=True, want_feats=False)

@@ -112,6 +112,9 @@ int tim_encoder_fwd_indexed(tim_ctx* ctx, const tim_feature_bank* bank, const fl
 /* End-to-end call on HOST buffers (pinned or pageable): time_mlp + encoder with the H2D input copies and D2H
  * result copies inside the call, chunked over clips and overlapped on three internal streams. Blocks until the
  * outputs are in host memory. `times` is [B, T, 2]; outputs as in tim_outputs but host pointers.
+ * clips_per_chunk is the TARGET chunk (<= 0 or > B: the whole batch): no chunk is larger; the first and last chunks are tapered
+ * (a quarter, a half of it) so that the un-overlapped first H2D / last D2H are short, and on the 16-bit path chunk sizes are
+ * rounded down to whole waves of GEMM row tiles (num_sms / gcd(num_sms, E / 256) tiles of 256 token rows).
  * h2d_bytes / d2h_bytes (optional) receive the bytes moved. */
 int tim_forward_host(tim_ctx* ctx, const float* vis, const float* aud, const float* times, int B, int T, int Qv, int Qa,
                      const tim_outputs* host_outs, int clips_per_chunk, uint64_t* h2d_bytes, uint64_t* d2h_bytes);

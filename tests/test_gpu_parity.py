@@ -568,12 +568,13 @@ def test_nms_many_groups_vs_oracle(lib, nms, method):
     assert at == len(p)
 
 
-def test_nms_group_larger_than_shared_memory(lib):
-    """A group above the kernel's shared-memory capacity (4096 proposals) runs from the global scratch: same result as the
-    oracle, and the same result as when it is one of several groups."""
+@pytest.mark.parametrize("n", [1025, 3000, 9000])
+def test_nms_large_groups(lib, n):
+    """Groups above 1024 proposals run on the 1024-thread launch shape (shared memory up to 8192 proposals, global scratch
+    above): same result as the oracle."""
     from oracle import nms_oracle as o
-    rng = np.random.default_rng(5)
-    segs, scores = _random_proposals(rng, 9000, 8)
+    rng = np.random.default_rng(5 + n)
+    segs, scores = _random_proposals(rng, n, 8)
     prm = dict(iou_threshold=0.1, sigma=0.25, min_score=0.05, method=2)
     inds, dets = _device_group_nms(segs, scores, prm, "soft")
     ri, rd = o.softnms_1d(segs, scores, **prm)

@@ -1,13 +1,13 @@
 // 1-D soft-NMS / NMS of detection proposals on the device. The reference's only native code is a scalar
 // CPU extension (detection/eval_detection/csrc/nms_cpu.cpp: softnms_1d_cpu :67-160, nms_1d_cpu :19-58) called once per class of
-// every video from a joblib pool (nms.py:123-155, format_predictions_epic.py:146-157). Here ONE launch handles every
+// every video from a joblib pool (nms.py:123-155, format_predictions_epic.py:146-157). Here one call handles every
 // (video, class) group: one CTA per group, the group's proposals in shared memory (global scratch for groups above NMS_SMEM_CAP).
 //
 // The reference algorithm is a selection sort whose result depends on the ORDER the live entries are stored in (ties take the
 // first maximum in current array order, and a deleted entry is overwritten by the last live one), so that order is reproduced
-// exactly: each round does (1) a block-wide arg-max of the live tail, first maximum in position order; (2) the swap to the
-// front; (3) the decay of every other live score, all in the reference's fp32 operation order with explicit round-to-nearest
-// intrinsics; (4) the reference's "move the last live entry into the hole" deletions, done for all holes of the round at once:
+// exactly: each round does (1) a block-wide arg-max of the live tail, first maximum in position order, whose reduction carries
+// the pick's segment along so that every thread ends up holding it; (2) the swap to the front, folded into (3) the decay of every
+// other live score, all in the reference's fp32 operation order with explicit round-to-nearest intrinsics; (4) the reference's "move the last live entry into the hole" deletions, done for all holes of the round at once:
 // with n' live entries left, the k-th hole below n' (ascending) receives the k-th surviving entry at or above n' counted from the
 // END — which is what the sequential scan produces (tests/test_oracle_golden.py checks that identity against a literal transcription).
 // Picks and indices are identical to the reference; the gaussian weight is exp() taken in double and rounded once to fp32
@@ -21,10 +21,13 @@
 namespace tim {
 namespace {
 
-constexpr int NMS_THREADS = 256;
-constexpr int NMS_WARPS = NMS_THREADS / 32;
-constexpr int NMS_SMEM_CAP = 4096;                       // proposals of one group held in shared memory
-constexpr int NMS_SMEM_BYTES = NMS_SMEM_CAP * 6 * 4;     // x1, x2, score, area, index, hole / mover lists
+// Two launch shapes cover all groups; a CTA whose group belongs to the other shape exits at once (no host round trip to sort
+// groups by size): groups of up to NMS_SMALL_MAX proposals run on 128 threads with 24 KB of shared memory (many CTAs per SM - the
+// median (video, class) group of an EPIC evaluation holds about ten proposals), larger ones on 1024 threads with 192 KB (one CTA
+// per SM; the largest groups are the critical path of the launch, and a round costs two block barriers plus n / 1024 updates per
+// thread). Groups above NMS_BIG_CAP work from global scratch.
+constexpr int NMS_SMALL_MAX = 1024;
+constexpr int NMS_BIG_CAP = 8192;
 
 struct NmsParams {
     const float* segs;              // [N, 2]
@@ -38,37 +41,62 @@ struct NmsParams {
     float* dets;                    // [N, 3] rows (start, end, score) of group g at offs[g] .. offs[g] + kept[g]
     long long* inds;                // [N] index INSIDE the group of every pick, same placement
     int* kept;                      // [G]
-    float* ws;                      // [6, N] scratch for groups larger than NMS_SMEM_CAP
+    float* ws;                      // [6, N] scratch for groups larger than NMS_BIG_CAP
     long long N;
 };
 
+// arg-max candidate with its payload, so that after the reduction every thread holds the pick in registers
+struct Cand {
+    float s; int tie, pos;          // pos < 0: empty
+    float x1, x2, ar; int id;
+};
 __device__ __forceinline__ bool better(float s, int tie, float bs, int btie) { return s > bs || (s == bs && tie < btie); }
+__device__ __forceinline__ void take(Cand& a, const Cand& b) {
+    if (b.pos >= 0 && (a.pos < 0 || better(b.s, b.tie, a.s, a.tie))) a = b;
+}
+__device__ __forceinline__ Cand warp_best(Cand c) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        Cand o;
+        o.s = __shfl_xor_sync(0xffffffffu, c.s, d); o.tie = __shfl_xor_sync(0xffffffffu, c.tie, d);
+        o.pos = __shfl_xor_sync(0xffffffffu, c.pos, d); o.x1 = __shfl_xor_sync(0xffffffffu, c.x1, d);
+        o.x2 = __shfl_xor_sync(0xffffffffu, c.x2, d); o.ar = __shfl_xor_sync(0xffffffffu, c.ar, d);
+        o.id = __shfl_xor_sync(0xffffffffu, c.id, d);
+        take(c, o);
+    }
+    return c;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
 
-__global__ void __launch_bounds__(NMS_THREADS) softnms_kernel(const NmsParams p) {
+template <int THREADS, int CAP, bool BIG>
+__global__ void __launch_bounds__(THREADS) softnms_kernel(const NmsParams p) {
+    constexpr int NW = THREADS / 32;
     extern __shared__ float nms_smem[];
-    __shared__ float red_s[NMS_WARPS];
-    __shared__ int red_tie[NMS_WARPS], red_pos[NMS_WARPS];
-    __shared__ int scan_h[NMS_WARPS], scan_m[NMS_WARPS];
-    __shared__ float pick[3];
-    __shared__ int pick_pos, removed_cnt;
+    __shared__ Cand red[NW];
+    __shared__ int red_cnt[NW], scan_h[NW], scan_m[NW];
 
     const int g = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long o = p.offs[g];
     int n = static_cast<int>(p.offs[g + 1] - o);
-    if (n <= 0) { if (tid == 0) p.kept[g] = 0; return; }
+    if (n <= 0) { if (!BIG && tid == 0) p.kept[g] = 0; return; }
+    if ((n > NMS_SMALL_MAX) != BIG) return;                  // the other launch shape owns this group
 
     float *x1, *x2, *sc, *ar;
     int *id, *lst;
-    if (n <= NMS_SMEM_CAP) {
-        x1 = nms_smem; x2 = x1 + NMS_SMEM_CAP; sc = x2 + NMS_SMEM_CAP; ar = sc + NMS_SMEM_CAP;
-        id = reinterpret_cast<int*>(ar + NMS_SMEM_CAP); lst = id + NMS_SMEM_CAP;
+    if (n <= CAP) {
+        x1 = nms_smem; x2 = x1 + CAP; sc = x2 + CAP; ar = sc + CAP;
+        id = reinterpret_cast<int*>(ar + CAP); lst = id + CAP;
     } else {
         x1 = p.ws + o; x2 = x1 + p.N; sc = x2 + p.N; ar = sc + p.N;
         id = reinterpret_cast<int*>(ar + p.N); lst = id + p.N;
     }
     const float ninf = __int_as_float(0xff800000);
-    for (int q = tid; q < n; q += NMS_THREADS) {
+    for (int q = tid; q < n; q += THREADS) {
         const float2 s = reinterpret_cast<const float2*>(p.segs)[o + q];
         float v = p.scores[o + q];
         if (p.hard && p.min_score > 0.0f && !(v > p.min_score)) v = ninf;      // nms.py:15-19: scores <= min_score never enter
@@ -80,51 +108,44 @@ __global__ void __launch_bounds__(NMS_THREADS) softnms_kernel(const NmsParams p)
 
     int i = 0;
     while (i < n) {
-        // (1) first maximum of the live tail [i, n)
-        float bs = ninf; int btie = 0x7fffffff, bpos = -1;
-        for (int q = i + tid; q < n; q += NMS_THREADS) {
+        // (1) first maximum of the live tail [i, n): per-thread scan, warp reduction, then every warp reduces the warp results
+        Cand c; c.s = ninf; c.tie = 0x7fffffff; c.pos = -1; c.x1 = c.x2 = c.ar = 0.0f; c.id = 0;
+        for (int q = i + tid; q < n; q += THREADS) {
             const float s = sc[q];
             const int tie = p.hard ? id[q] : q;
-            if (bpos < 0 || better(s, tie, bs, btie)) { bs = s; btie = tie; bpos = q; }
+            if (c.pos < 0 || better(s, tie, c.s, c.tie)) { c.s = s; c.tie = tie; c.pos = q; }
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            const float os = __shfl_xor_sync(0xffffffffu, bs, d);
-            const int ot = __shfl_xor_sync(0xffffffffu, btie, d), op = __shfl_xor_sync(0xffffffffu, bpos, d);
-            if (op >= 0 && (bpos < 0 || better(os, ot, bs, btie))) { bs = os; btie = ot; bpos = op; }
-        }
-        if (lane == 0) { red_s[warp] = bs; red_tie[warp] = btie; red_pos[warp] = bpos; }
+        if (c.pos >= 0) { c.x1 = x1[c.pos]; c.x2 = x2[c.pos]; c.ar = ar[c.pos]; c.id = id[c.pos]; }
+        c = warp_best(c);
+        if (lane == 0) red[warp] = c;
         __syncthreads();
+        if (lane < NW) c = red[lane]; else c.pos = -1;
+        c = warp_best(c);                                   // the pick, in every thread's registers
+        const int m = c.pos;
+        if (p.hard && (c.s == ninf || (p.max_num > 0 && i >= p.max_num))) break;   // nothing above min_score left / max_num reached
         if (tid == 0) {
-            for (int w = 1; w < NMS_WARPS; ++w)
-                if (red_pos[w] >= 0 && (bpos < 0 || better(red_s[w], red_tie[w], bs, btie))) { bs = red_s[w]; btie = red_tie[w]; bpos = red_pos[w]; }
-            // (2) swap the pick to position i and emit it (nms_cpu.cpp:105-122)
-            const int m = bpos;
-            const float mx1 = x1[m], mx2 = x2[m], msc = sc[m], mar = ar[m];
-            const int mid = id[m];
-            x1[m] = x1[i]; x2[m] = x2[i]; sc[m] = sc[i]; ar[m] = ar[i]; id[m] = id[i];
-            x1[i] = mx1; x2[i] = mx2; sc[i] = msc; ar[i] = mar; id[i] = mid;
-            pick[0] = mx1; pick[1] = mx2; pick[2] = mar;
-            const bool stop = p.hard && (msc == ninf || (p.max_num > 0 && i >= p.max_num));
-            pick_pos = stop ? -1 : m;
-            removed_cnt = 0;
-            if (!stop) {
-                float* d = p.dets + (o + i) * 3;
-                d[0] = mx1; d[1] = mx2; d[2] = msc;
-                p.inds[o + i] = mid;
-            }
+            float* d = p.dets + (o + i) * 3;
+            d[0] = c.x1; d[1] = c.x2; d[2] = c.s;
+            p.inds[o + i] = c.id;
         }
-        __syncthreads();
-        if (pick_pos < 0) break;                          // hard mode: nothing above min_score left / max_num reached
-        const float ix1 = pick[0], ix2 = pick[1], iarea = pick[2];
+        const float ix1 = c.x1, ix2 = c.x2, iarea = c.ar;
 
-        // (3) decay the rest (nms_cpu.cpp:126-144)
+        // (2) + (3) swap the pick to position i (nms_cpu.cpp:105-122) and decay the rest (:126-144) in one pass: the thread that
+        // owns position m moves the entry of position i there (nobody else touches i or m in this pass)
         int my_removed = 0;
-        for (int q = i + 1 + tid; q < n; q += NMS_THREADS) {
-            const float xx1 = fmaxf(ix1, x1[q]), xx2 = fminf(ix2, x2[q]);
+        for (int q = i + 1 + tid; q < n; q += THREADS) {
+            float qx1, qx2, qar, s;
+            if (q == m) {
+                qx1 = x1[i]; qx2 = x2[i]; qar = ar[i]; s = sc[i];
+                const int qid = id[i];
+                x1[i] = c.x1; x2[i] = c.x2; ar[i] = c.ar; sc[i] = c.s; id[i] = c.id;
+                x1[q] = qx1; x2[q] = qx2; ar[q] = qar; id[q] = qid;
+            } else {
+                qx1 = x1[q]; qx2 = x2[q]; qar = ar[q]; s = sc[q];
+            }
+            const float xx1 = fmaxf(ix1, qx1), xx2 = fminf(ix2, qx2);
             const float inter = fmaxf(0.0f, __fsub_rn(xx2, xx1));
-            const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(iarea, ar[q]), inter));
-            float s = sc[q];
+            const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(iarea, qar), inter));
             if (p.hard) {
                 if (ovr >= p.thr) s = ninf;
                 my_removed += (s == ninf);
@@ -132,23 +153,22 @@ __global__ void __launch_bounds__(NMS_THREADS) softnms_kernel(const NmsParams p)
                 float w = 1.0f;
                 if (p.method == 0) { if (ovr >= p.thr) w = 0.0f; }
                 else if (p.method == 1) { if (ovr >= p.thr) w = __fsub_rn(1.0f, ovr); }
-                else if (p.method == 2) { w = static_cast<float>(exp(static_cast<double>(__fdiv_rn(-__fmul_rn(ovr, ovr), p.sigma)))); }
+                else { w = static_cast<float>(exp(static_cast<double>(__fdiv_rn(-__fmul_rn(ovr, ovr), p.sigma)))); }
                 s = __fmul_rn(s, w);
                 my_removed += (s < p.min_score);
             }
             sc[q] = s;
         }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) my_removed += __shfl_xor_sync(0xffffffffu, my_removed, d);
-        if (lane == 0 && my_removed) atomicAdd(&removed_cnt, my_removed);
+        my_removed = warp_sum(my_removed);
+        if (lane == 0) red_cnt[warp] = my_removed;
         __syncthreads();
-        const int R = removed_cnt;
+        const int R = warp_sum(lane < NW ? red_cnt[lane] : 0);
         if (R == 0) { ++i; continue; }
 
         // (4) deletions of the round (nms_cpu.cpp:147-156): holes below n2 take the survivors at or above n2, last first
         const int len = n - (i + 1);
         const int n2 = n - R;
-        const int chunk = (len + NMS_THREADS - 1) / NMS_THREADS;
+        const int chunk = (len + THREADS - 1) / THREADS;
         const int q0 = i + 1 + tid * chunk, q1 = min(q0 + chunk, n);
         int nh = 0, nm = 0;
         for (int q = q0; q < q1; ++q) {
@@ -164,11 +184,14 @@ __global__ void __launch_bounds__(NMS_THREADS) softnms_kernel(const NmsParams p)
         }
         if (lane == 31) { scan_h[warp] = ph; scan_m[warp] = pm; }
         __syncthreads();
-        int bh = 0, bm = 0, K = 0;
-        for (int w = 0; w < NMS_WARPS; ++w) {
-            if (w < warp) { bh += scan_h[w]; bm += scan_m[w]; }
-            K += scan_h[w];
+        int wh = lane < NW ? scan_h[lane] : 0, wm = lane < NW ? scan_m[lane] : 0;   // inclusive scan over the warp totals
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int a = __shfl_up_sync(0xffffffffu, wh, d), b = __shfl_up_sync(0xffffffffu, wm, d);
+            if (lane >= d) { wh += a; wm += b; }
         }
+        const int K = __shfl_sync(0xffffffffu, wh, NW - 1);
+        const int bh = warp ? __shfl_sync(0xffffffffu, wh, warp - 1) : 0, bm = warp ? __shfl_sync(0xffffffffu, wm, warp - 1) : 0;
         int rh = bh + ph - nh, rm = bm + pm - nm;          // exclusive ranks of this thread's first hole / mover
         int* holes = lst;
         int* movers = lst + (n + 1) / 2;                   // K <= len / 2
@@ -178,7 +201,7 @@ __global__ void __launch_bounds__(NMS_THREADS) softnms_kernel(const NmsParams p)
             if (!rem && q >= n2) movers[rm++] = q;
         }
         __syncthreads();
-        for (int k = tid; k < K; k += NMS_THREADS) {
+        for (int k = tid; k < K; k += THREADS) {
             const int dst = holes[k], src = movers[K - 1 - k];
             x1[dst] = x1[src]; x2[dst] = x2[src]; sc[dst] = sc[src]; ar[dst] = ar[src]; id[dst] = id[src];
         }
@@ -192,10 +215,16 @@ __global__ void __launch_bounds__(NMS_THREADS) softnms_kernel(const NmsParams p)
 int fail(const char* msg) { set_global_error(msg); return TIM_ERR_INVALID; }
 
 int launch(const NmsParams& p, cudaStream_t s, const char* who) {
-    static SmemAttrCache cache;
-    cudaError_t e = ensure_dynamic_smem(softnms_kernel, NMS_SMEM_BYTES, cache);
+    auto small = softnms_kernel<128, NMS_SMALL_MAX, false>;
+    auto big = softnms_kernel<1024, NMS_BIG_CAP, true>;
+    constexpr size_t small_bytes = NMS_SMALL_MAX * 6 * 4, big_bytes = NMS_BIG_CAP * 6 * 4;
+    static SmemAttrCache cache_small, cache_big;
+    cudaError_t e = ensure_dynamic_smem(small, small_bytes, cache_small);
+    if (e == cudaSuccess) e = ensure_dynamic_smem(big, big_bytes, cache_big);
     if (e == cudaSuccess) {
-        softnms_kernel<<<static_cast<unsigned>(p.G), NMS_THREADS, NMS_SMEM_BYTES, s>>>(p);
+        // two launches on the caller's stream; every CTA of the shape that does not own its group returns immediately
+        big<<<static_cast<unsigned>(p.G), 1024, big_bytes, s>>>(p);
+        small<<<static_cast<unsigned>(p.G), 128, small_bytes, s>>>(p);
         e = cudaGetLastError();
     }
     if (e != cudaSuccess) { set_global_error((std::string(who) + ": " + cudaGetErrorString(e)).c_str()); return TIM_ERR_CUDA; }
