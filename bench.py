@@ -89,12 +89,18 @@ def cpu_port(cfg, Qv, Qa, clips, steps, warmup, seed=1234):
     inp = synth_inputs(cfg, clips, Qv, Qa, seed, shared_queries=cfg.variant == "detection")
     o = TIMOracle(cfg, sd, np.float32)
     ts = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        o.forward(inp.get("vis"), inp.get("aud"), inp["times"], Qv, Qa, clip_chunk=8)
-        if i >= warmup:
-            ts.append(time.perf_counter() - t0)
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    # all host threads, whatever the launcher put in the environment: torchrun exports OMP_NUM_THREADS=1 to its workers when
+    # nproc-per-node > 1, which would pin numpy's BLAS to one thread and make the CPU arm 3x slower at N > 1 than at N = 1
+    from threadpoolctl import threadpool_info, threadpool_limits
+    with threadpool_limits(limits=cores):
+        used = max([i.get("num_threads", 1) for i in threadpool_info()] or [1])
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            o.forward(inp.get("vis"), inp.get("aud"), inp["times"], Qv, Qa, clip_chunk=8)
+            if i >= warmup:
+                ts.append(time.perf_counter() - t0)
+    cores = min(cores, used)
     t = sum(ts) / len(ts)
     return {"value": clips * (Qv + Qa) / t, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{clips} clips/step x {steps} steps of the same workload, fp32 numpy (OpenBLAS threads = cores), "
