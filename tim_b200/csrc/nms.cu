@@ -245,6 +245,7 @@ int tim_softnms_1d(const float* segs, const float* scores, const int64_t* group_
     if (G == 0) return TIM_OK;
     if (!segs || !scores || !group_offsets || !dets || !inds || !kept) return fail("tim_softnms_1d: NULL argument");
     if (G < 0 || N < 0) return fail("tim_softnms_1d: negative size");
+    if (N > 0x7fffffffLL) return fail("tim_softnms_1d: more than 2^31 - 1 proposals (positions inside a group are 32-bit)");
     if (method < 0 || method > 2) return fail("tim_softnms_1d: method must be 0 (vanilla), 1 (linear) or 2 (gaussian)");
     if (method == 2 && !(sigma > 0.0f)) return fail("tim_softnms_1d: sigma must be positive for the gaussian method");
     if (!workspace || workspace_bytes < tim_nms_workspace_bytes(N)) return fail("tim_softnms_1d: workspace smaller than tim_nms_workspace_bytes(N)");
@@ -260,6 +261,7 @@ int tim_nms_1d(const float* segs, const float* scores, const int64_t* group_offs
     if (G == 0) return TIM_OK;
     if (!segs || !scores || !group_offsets || !dets || !inds || !kept) return fail("tim_nms_1d: NULL argument");
     if (G < 0 || N < 0) return fail("tim_nms_1d: negative size");
+    if (N > 0x7fffffffLL) return fail("tim_nms_1d: more than 2^31 - 1 proposals (positions inside a group are 32-bit)");
     if (!workspace || workspace_bytes < tim_nms_workspace_bytes(N)) return fail("tim_nms_1d: workspace smaller than tim_nms_workspace_bytes(N)");
     NmsParams p{segs, scores, reinterpret_cast<const long long*>(group_offsets), G, iou_threshold, 1.0f, min_score, 0, 1, max_num,
                 dets, reinterpret_cast<long long*>(inds), kept, static_cast<float*>(workspace), N};
