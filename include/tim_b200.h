@@ -161,6 +161,21 @@ int tim_nms_1d(const float* segs, const float* scores, const int64_t* group_offs
                float min_score, int64_t max_num, float* dets /*[N,3]*/, int64_t* inds /*[N]*/, int* kept /*[G]*/, void* workspace,
                size_t workspace_bytes, void* stream);
 
+/* Detection post-processing in front of the NMS, on the device (all pointers are device pointers; stateless, errors through
+ * tim_last_error(NULL)).
+ * tim_det_decode <- FeatureMeter.update (detection/time_interval_machine/utils/meters.py:652-724): preds = sigmoid(logits) [R,C]
+ *   and proposals[r, :] = double(fp32(clamp(reg[r, :], 0, max_time) * win_size)) + win_start[r / rows_per_window] (seconds of the
+ *   video; float64 like the reference's tensor, whose window metadata collates to float64). Either output may be NULL.
+ * tim_det_count / tim_det_emit <- the thresholding loop of detection/eval_detection/format_predictions.py:103-125: proposals are
+ *   rounded to 3 decimals (numpy: multiply, rint, divide in double), rows with end - start <= 0 are dropped, every class whose
+ *   score exceeds score_threshold gives one detection. counts[r] = detections of row r; with offsets = the exclusive prefix sum of
+ *   counts (formed by the caller), tim_det_emit writes them in (row, class) order: source row, class, score, fp32 segment. */
+int tim_det_decode(const float* logits, const float* reg, const double* win_start, int rows_per_window, int64_t R, int C, float win_size,
+                   float max_time, float* preds /*[R,C] or NULL*/, double* proposals /*[R,2] or NULL*/, void* stream);
+int tim_det_count(const float* preds, const double* proposals, int64_t R, int C, float score_threshold, int* counts /*[R]*/, void* stream);
+int tim_det_emit(const float* preds, const double* proposals, int64_t R, int C, float score_threshold, const int64_t* offsets /*[R]*/,
+                 int64_t* out_row, int64_t* out_cls, float* out_score, float* out_seg /*[n,2]*/, void* stream);
+
 /* Live per-kernel-class timing (bench.py's roofline object): between begin and end every launch is bracketed by a
  * CUDA-event pair on its own stream. Classes: 0 GEMM (tcgen05 / fp32 SIMT) other than 5 and 6, 1 attention, 2 LayerNorm /
  * row statistics, 3 token assembly, 4 other row kernels, 5 encoder GEMMs with a folded LayerNorm in front (in_proj, linear1:

@@ -132,3 +132,45 @@ def batched_nms(segs, scores, cls_idxs, iou_threshold, min_score, sigma=0.5, met
     s, p, c = np.concatenate(out_s), np.concatenate(out_p), np.concatenate(out_c)
     order = np.argsort(-p.astype(np.float64), kind="stable")
     return s[order], p[order], c[order]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# in front of the NMS: FeatureMeter.update and the thresholding loop of format_predictions.py
+# ---------------------------------------------------------------------------------------------------------------------
+def decode_predictions(logits, reg, window_start, window_size, max_time):
+    """detection/time_interval_machine/utils/meters.py:652-700 (visual branch; the audio branch :702-722 is the same arithmetic):
+    preds = sigmoid(logits) fp32; proposals = clamp(reg, 0, max_time) * window_size + window_start of the row's window.
+    dtypes as the reference's tensors have them: the product is fp32 (a 0-dim float64 window_size does not promote a fp32
+    tensor), the sum is float64 (window_start [R,1] is a float64 tensor with a dimension)."""
+    logits = np.asarray(logits, F)
+    reg = np.asarray(reg, F).reshape(-1, 2)
+    ws = np.asarray(window_start, np.float64).reshape(-1)
+    R = reg.shape[0]
+    with np.errstate(over="ignore"):
+        preds = (F(1.0) / (F(1.0) + np.exp(-logits).astype(F))).astype(F)
+    v = np.minimum(np.maximum(reg, F(0.0)), F(max_time)).astype(F)
+    scaled = (v * F(window_size)).astype(F)
+    return preds, scaled.astype(np.float64) + np.repeat(ws, R // ws.shape[0])[:, None]
+
+
+def threshold_detections(preds, proposals, score_threshold):
+    """detection/eval_detection/format_predictions.py:103-125: proposals rounded to 3 decimals (np.round on float64), rows with
+    end - start <= 0 dropped, one detection per class whose score exceeds the threshold, in (row, class) order.
+    -> (row [n] i64, cls [n] i64, score [n] f32, segs [n,2] f32 = torch.FloatTensor of the rounded proposals)."""
+    preds = np.asarray(preds, F)
+    p = np.round(np.asarray(proposals, np.float64).reshape(-1, 2), 3)
+    live = (p[:, 1] - p[:, 0]) > 0.0
+    row, cls = np.nonzero((preds > F(score_threshold)) & live[:, None])
+    return row.astype(np.int64), cls.astype(np.int64), preds[row, cls], p[row].astype(F)
+
+
+def format_predictions(preds, proposals, video_ids, score_threshold=0.03, sigma=0.25, iou_threshold=0.1, min_score=0.001, method=2):
+    """main() of detection/eval_detection/format_predictions.py:98-141: {video: (segs [k,2] f32, scores [k] f32, cls [k] i64)} with
+    every video's detections sorted by descending score (stable), after per-class gaussian soft-NMS."""
+    row, cls, score, segs = threshold_detections(preds, proposals, score_threshold)
+    vids = np.asarray(video_ids)[row]
+    out = {}
+    for v in np.unique(np.asarray(video_ids)):
+        m = vids == v
+        out[str(v)] = batched_nms(segs[m], score[m], cls[m], iou_threshold, min_score, sigma=sigma, method=method, nms="soft")
+    return out

@@ -650,3 +650,67 @@ def test_nms_evaluation_size_vs_compiled_reference(lib):
         assert np.all(np.diff(p[at:at + n]) <= 0) and len(set(src[at:at + n].tolist())) == n
         at += n
     assert at == len(p)
+
+
+def test_detection_postprocessing_chain_vs_reference_golden(lib):
+    """tim_det_decode / tim_det_count / tim_det_emit + the NMS kernels against the UNMODIFIED reference chain
+    (tests/golden/detpost.npz: FeatureMeter.update, then main() of eval_detection/format_predictions.py):
+      decode      proposals (float64 seconds) bit-exact, sigmoid scores to 1e-6;
+      threshold   on the reference's own scores / proposals: rows, classes, scores, fp32 segments identical to the oracle's loop;
+      whole chain per video: classes and 3-decimal segments identical to the reference's submission entries, scores to 1e-6."""
+    from oracle import nms_oracle as o
+    from tests.test_oracle_golden import detpost_golden
+    from tim_b200.postprocess import decode_predictions, format_predictions, threshold_detections
+    dev = torch.device("cuda", 0)
+    g = detpost_golden()
+    window_size, thr, sigma, _ = g["params"]
+    preds, props = [], []
+    for b in range(2):
+        p, pr = decode_predictions(torch.from_numpy(g[f"b{b}/logits"]), torch.from_numpy(g[f"b{b}/reg"]),
+                                   torch.from_numpy(g[f"b{b}/window_start"]), window_size, float(g[f"b{b}/queries"].max()), device=dev)
+        preds.append(p.cpu().numpy())
+        props.append(pr.cpu().numpy())
+    assert np.array_equal(np.concatenate(props), g["v_proposals"])
+    np.testing.assert_allclose(np.concatenate(preds), g["action"], rtol=NMS_SCORE_RTOL, atol=0)
+
+    row, cls, score, segs = (t.cpu().numpy() for t in threshold_detections(torch.from_numpy(g["action"]), torch.from_numpy(g["v_proposals"]),
+                                                                            thr, device=dev))
+    orow, ocls, oscore, osegs = o.threshold_detections(g["action"], g["v_proposals"], thr)
+    assert np.array_equal(row, orow) and np.array_equal(cls, ocls) and np.array_equal(score, oscore) and np.array_equal(segs, osegs)
+    assert len(row) == 2865                                   # "Creating Submission from 2865 predictions" in the reference's log
+
+    names, vidx = np.unique(g["video_ids"], return_inverse=True)
+    s, p, c, v = (t.cpu().numpy() for t in format_predictions(torch.from_numpy(g["action"]), torch.from_numpy(g["v_proposals"]),
+                                                              torch.from_numpy(vidx), thr, sigma, device=dev))
+    for i, name in enumerate(names):
+        m = v == i
+        assert np.array_equal(c[m], g[f"result/{name}/action"])
+        assert np.array_equal(np.array([[round(float(a), 3), round(float(b), 3)] for a, b in s[m]]), g[f"result/{name}/segment"])
+        np.testing.assert_allclose(p[m].astype(np.float64), g[f"result/{name}/score"], rtol=NMS_SCORE_RTOL, atol=0)
+    # no detections at all: empty outputs, no launch with empty buffers
+    row, cls, score, segs = threshold_detections(torch.zeros((5, 7)), torch.zeros((5, 2), dtype=torch.float64), 0.03, device=dev)
+    assert row.numel() == 0 and segs.shape == (0, 2)
+
+
+def test_detection_postprocessing_properties_at_full_size(lib):
+    """cfg4-sized head outputs (96 windows x 2048 queries, 97 classes): decode + threshold against the numpy oracle (bit-exact
+    proposals / rows / classes; sigmoid to 1e-6 with the threshold applied to the device's own scores), NaN regression outputs
+    propagate and are dropped, counts add up."""
+    from oracle import nms_oracle as o
+    from tim_b200.postprocess import decode_predictions, threshold_detections
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(9)
+    B, Q, C_ = 96, 2048, 97
+    logits = rng.normal(-5.5, 1.5, (B * Q, C_)).astype(np.float32)
+    st = rng.uniform(-0.05, 1.0, (B * Q,)).astype(np.float32)
+    reg = np.stack([st, st + rng.normal(0.08, 0.05, (B * Q,)).astype(np.float32)], 1)
+    reg[17] = np.nan
+    ws = (np.arange(B) * 15.0 + 0.123).astype(np.float64)
+    preds, props = decode_predictions(torch.from_numpy(logits), torch.from_numpy(reg), torch.from_numpy(ws), 30.0, 1.25, device=dev)
+    opreds, oprops = o.decode_predictions(logits, reg, ws, 30.0, 1.25)
+    assert np.array_equal(props.cpu().numpy(), oprops, equal_nan=True)
+    np.testing.assert_allclose(preds.cpu().numpy(), opreds, rtol=NMS_SCORE_RTOL, atol=0)
+    row, cls, score, segs = (t.cpu().numpy() for t in threshold_detections(preds, props, 0.03))
+    orow, ocls, oscore, osegs = o.threshold_detections(preds.cpu().numpy(), oprops, 0.03)
+    assert np.array_equal(row, orow) and np.array_equal(cls, ocls) and np.array_equal(score, oscore) and np.array_equal(segs, osegs)
+    assert 17 not in set(row.tolist()) and len(row) > 100000

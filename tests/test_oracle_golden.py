@@ -218,3 +218,33 @@ def test_parallel_deletion_equals_sequential_scan():
         for k, h in enumerate(holes):
             b[h] = vals[movers[len(movers) - 1 - k]]
         assert a[:m] == b[:n2]
+
+
+def detpost_golden():
+    return np.load(os.path.join(GOLD, "detpost.npz"))
+
+
+def test_detpost_oracle_matches_reference_golden():
+    """oracle/nms_oracle.py's decode / threshold / format restatements against the UNMODIFIED reference chain
+    (tests/golden/detpost.npz, tools/make_golden_detpost.py: FeatureMeter.update + finalize_metrics, then main() of
+    eval_detection/format_predictions.py with the reference's nms.py and compiled extension): proposals bit-exact (float64),
+    sigmoid scores to 1e-6 (exp rounding), final detections per video: classes and 3-decimal segments exact, scores to 1e-6."""
+    from oracle import nms_oracle as o
+    g = detpost_golden()
+    window_size, thr, sigma, _ = g["params"]
+    assert g["v_proposals"].dtype == np.float64 and g["action"].dtype == np.float32
+    preds, props = [], []
+    for b in range(2):
+        p, pr = o.decode_predictions(g[f"b{b}/logits"], g[f"b{b}/reg"], g[f"b{b}/window_start"], window_size,
+                                     g[f"b{b}/queries"].max())
+        preds.append(p)
+        props.append(pr)
+    assert np.array_equal(np.concatenate(props), g["v_proposals"])
+    np.testing.assert_allclose(np.concatenate(preds), g["action"], rtol=NMS_SCORE_RTOL, atol=0)
+    res = o.format_predictions(g["action"], g["v_proposals"], g["video_ids"], thr, sigma)
+    assert sorted(res) == sorted(str(v) for v in g["result_videos"])
+    for v in g["result_videos"]:
+        s, p, c = res[str(v)]
+        assert np.array_equal(c, g[f"result/{v}/action"])
+        assert np.array_equal(np.array([[round(float(a), 3), round(float(b), 3)] for a, b in s]), g[f"result/{v}/segment"])
+        np.testing.assert_allclose(p.astype(np.float64), g[f"result/{v}/score"], rtol=NMS_SCORE_RTOL, atol=0)

@@ -1,8 +1,17 @@
-"""Detection post-processing on the device: the reference's `detection/eval_detection/nms.py` (batched_nms :98-180, SoftNMSop
-:35-61, NMSop :7-33) over the library's `tim_softnms_1d` / `tim_nms_1d` (tim_b200/csrc/nms.cu) instead of the scalar CPU extension
-`nms_1d_cpu` (csrc/nms_cpu.cpp) and the per-class Python loop / per-video joblib pool that drive it
-(format_predictions_epic.py:146-157). PyTorch is used for device memory and the index plumbing (sorting proposals into
-(video, class) groups, gathering the kept rows); the suppression itself is one kernel launch for all groups.
+"""Detection post-processing on the device, mirroring the reference's evaluation chain:
+
+  decode_predictions     <- FeatureMeter.update (detection/time_interval_machine/utils/meters.py:652-724): sigmoid scores,
+                            regression outputs clamped and mapped back to seconds            (tim_det_decode)
+  threshold_detections   <- the thresholding loop of detection/eval_detection/format_predictions.py:103-125
+                                                                                              (tim_det_count / tim_det_emit)
+  batched_nms            <- detection/eval_detection/nms.py: batched_nms :98-180 (SoftNMSop :35-61, NMSop :7-33), same signature,
+                            instead of the scalar CPU extension nms_1d_cpu (csrc/nms_cpu.cpp)  (tim_softnms_1d / tim_nms_1d)
+  batched_nms_videos, format_predictions
+                         <- main() of format_predictions.py:98-141 / format_predictions_epic.py:114-157: all videos and classes
+                            of an evaluation in one call instead of a Python loop over proposals and a joblib pool over videos
+
+PyTorch is used for device memory and the index plumbing (sorting proposals into (video, class) groups, prefix sums, gathering
+the kept rows); the arithmetic runs in the library's kernels (tim_b200/csrc/detpost.cu, nms.cu).
 
 No CPU fallback: without a CUDA device or the built library every entry point raises.
 """
@@ -116,3 +125,77 @@ def batched_nms_videos(segs, scores, cls_idxs, video_idxs, iou_threshold, min_sc
         order = order[torch.sort(vid[order], stable=True)[1]]
         s, p, cls, vid = s[order], p[order], cls[order], vid[order]
     return s, p, cls, vid
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# in front of the NMS: FeatureMeter.update and the thresholding loop of format_predictions.py, on the device
+# ---------------------------------------------------------------------------------------------------------------------
+def decode_predictions(logits: torch.Tensor, regressions: torch.Tensor, window_start: torch.Tensor, window_size: float, max_time: float,
+                       device: Optional[torch.device] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """FeatureMeter.update for one modality (detection/time_interval_machine/utils/meters.py:652-724) without the host round
+    trip: logits [R, C] and regression outputs [R, 2] of a batch of B windows (R = B * queries, window-major, as the heads return
+    them), window_start [B] seconds -> (preds [R, C] fp32 = sigmoid(logits), proposals [R, 2] float64 in seconds of the video =
+    clamp(reg, 0, max_time) * window_size + window_start of the row's window). max_time is the largest query time of the batch
+    (meters.py:673), window_size the dataset's window length in seconds (:669)."""
+    lib = _lib.load()
+    device = torch.device(device) if device is not None else (logits.device if logits.is_cuda else torch.device("cuda", torch.cuda.current_device()))
+    if device.type != "cuda":
+        raise RuntimeError("tim_b200.postprocess runs on a CUDA device only (no CPU fallback)")
+    logits = logits.to(device=device, dtype=torch.float32).contiguous()
+    reg = regressions.to(device=device, dtype=torch.float32).reshape(-1, 2).contiguous()
+    ws = torch.as_tensor(window_start).to(device=device, dtype=torch.float64).reshape(-1).contiguous()
+    R, C_ = int(logits.shape[0]), int(logits.shape[1])
+    if reg.shape[0] != R or ws.numel() == 0 or R % ws.numel():
+        raise ValueError("logits [R,C], regressions [R,2] and window_start [B] with R = B * queries expected")
+    with torch.cuda.device(device):
+        preds = torch.empty((R, C_), dtype=torch.float32, device=device)
+        props = torch.empty((R, 2), dtype=torch.float64, device=device)
+        _lib.check(lib.tim_det_decode(_ptr(logits), _ptr(reg), _ptr(ws), R // int(ws.numel()), R, C_, float(window_size), float(max_time),
+                                      _ptr(preds), _ptr(props), torch.cuda.current_stream(device).cuda_stream), None)
+    return preds, props
+
+
+def threshold_detections(preds: torch.Tensor, proposals: torch.Tensor, score_threshold: float,
+                         device: Optional[torch.device] = None):
+    """The loop of detection/eval_detection/format_predictions.py:103-125 (format_predictions_epic.py:120-143) on the device:
+    proposals [R, 2] (float64 seconds) rounded to 3 decimals, empty ones dropped, one detection per (proposal, class) with
+    preds[r, c] > score_threshold, in (proposal, class) order. Returns device tensors (row [n] int64, cls [n] int64, score [n] fp32,
+    segs [n, 2] fp32 - what torch.FloatTensor(segs) gives the reference's NMS)."""
+    lib = _lib.load()
+    device = torch.device(device) if device is not None else (preds.device if preds.is_cuda else torch.device("cuda", torch.cuda.current_device()))
+    if device.type != "cuda":
+        raise RuntimeError("tim_b200.postprocess runs on a CUDA device only (no CPU fallback)")
+    preds = preds.to(device=device, dtype=torch.float32).contiguous()
+    props = proposals.to(device=device, dtype=torch.float64).reshape(-1, 2).contiguous()
+    R, C_ = int(preds.shape[0]), int(preds.shape[1])
+    if props.shape[0] != R:
+        raise ValueError("preds [R,C] and proposals [R,2] must agree on R")
+    thr = float(score_threshold)
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream(device).cuda_stream
+        counts = torch.zeros((R,), dtype=torch.int32, device=device)
+        if R:
+            _lib.check(lib.tim_det_count(_ptr(preds), _ptr(props), R, C_, thr, _ptr(counts), stream), None)
+        ends = torch.cumsum(counts, 0, dtype=torch.int64)
+        n = int(ends[-1]) if R else 0                       # the one host read: the output size
+        row = torch.empty((n,), dtype=torch.int64, device=device)
+        cls = torch.empty((n,), dtype=torch.int64, device=device)
+        score = torch.empty((n,), dtype=torch.float32, device=device)
+        segs = torch.empty((n, 2), dtype=torch.float32, device=device)
+        if n:
+            offs = (ends - counts).contiguous()
+            _lib.check(lib.tim_det_emit(_ptr(preds), _ptr(props), R, C_, thr, _ptr(offs), _ptr(row), _ptr(cls), _ptr(score), _ptr(segs), stream), None)
+    return row, cls, score, segs
+
+
+def format_predictions(preds, proposals, video_idxs, score_threshold=0.03, sigma=0.25, iou_threshold=0.1, min_score=0.001, method=2,
+                       nms="soft", device=None):
+    """Thresholding + per-video, per-class NMS of a whole evaluation in three launches: what main() of
+    detection/eval_detection/format_predictions.py:98-141 computes with a Python loop over proposals and a joblib pool over
+    videos. preds [R, C] (sigmoid scores), proposals [R, 2] (seconds), video_idxs [R] (integer id of each proposal's video).
+    Returns device tensors (segs [k,2], scores [k], cls [k], video [k]): videos ascending, inside a video by descending score
+    (the order of `results[video]` in the reference's submission file)."""
+    row, cls, score, segs = threshold_detections(preds, proposals, score_threshold, device=device)
+    vid = torch.as_tensor(video_idxs).to(device=row.device, dtype=torch.int64)[row]
+    return batched_nms_videos(segs, score, cls, vid, iou_threshold=iou_threshold, min_score=min_score, sigma=sigma, method=method,
+                              nms=nms, device=row.device)
