@@ -714,3 +714,41 @@ def test_detection_postprocessing_properties_at_full_size(lib):
     orow, ocls, oscore, osegs = o.threshold_detections(preds.cpu().numpy(), oprops, 0.03)
     assert np.array_equal(row, orow) and np.array_equal(cls, ocls) and np.array_equal(score, oscore) and np.array_equal(segs, osegs)
     assert 17 not in set(row.tolist()) and len(row) > 100000
+
+
+def test_hard_nms_evaluation_size_vs_compiled_reference(lib):
+    """tim_nms_1d on the evaluation-sized workload against the reference's compiled nms_1d_cpu.nms under the NMSop wrapper's
+    rules (nms.py:7-33: scores <= min_score dropped first, at most max_num picks), group by group. Scores are made pairwise
+    distinct: with equal scores the reference's order comes from torch's unstable sort and is not defined."""
+    import importlib.util
+    import os
+    from oracle import build_ref
+    from tim_b200.postprocess import grouped_nms
+    mod = build_ref.load()
+    if mod is None:
+        pytest.skip("oracle/_ref/nms_1d_cpu.so not built")
+    spec = importlib.util.spec_from_file_location("nms_bench", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                            "tools", "nms_bench.py"))
+    nb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(nb)
+    n_cls = 97
+    segs, _, cls, vid = nb.workload(8, 20000, n_cls, seed=4)
+    N = len(cls)
+    scores = (0.0005 + 0.9 * (np.random.default_rng(1).permutation(N) + 1) / (N + 1)).astype(np.float32)
+    assert len(np.unique(scores)) == N
+    keys = vid * n_cls + cls
+    thr, min_score, max_num = 0.3, 0.01, 40
+    s, p, k, src = (t.cpu().numpy() for t in grouped_nms(torch.from_numpy(segs), torch.from_numpy(scores), torch.from_numpy(keys),
+                                                         iou_threshold=thr, min_score=min_score, nms="vanilla", max_seg_num=max_num,
+                                                         device=torch.device("cuda", 0)))
+    at = 0
+    for key in np.unique(keys):
+        rows = np.nonzero(keys == key)[0]
+        rows = rows[scores[rows] > np.float32(min_score)]                  # nms.py:15-19
+        inds = mod.nms(torch.from_numpy(segs[rows]).contiguous(), torch.from_numpy(scores[rows]).contiguous(), thr).numpy()[:max_num]
+        n = len(inds)
+        assert np.array_equal(src[at:at + n], rows[inds]), key
+        assert np.all(k[at:at + n] == key) and (at + n == len(k) or k[at + n] != key), key
+        assert np.array_equal(s[at:at + n], segs[rows[inds]]) and np.array_equal(p[at:at + n], scores[rows[inds]])
+        at += n
+    assert at == len(p)

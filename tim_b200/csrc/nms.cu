@@ -76,8 +76,8 @@ template <int THREADS, int CAP, bool BIG>
 __global__ void __launch_bounds__(THREADS) softnms_kernel(const NmsParams p) {
     constexpr int NW = THREADS / 32;
     extern __shared__ float nms_smem[];
-    __shared__ Cand red[NW];
-    __shared__ int red_cnt[NW], scan_h[NW], scan_m[NW];
+    __shared__ Cand red[2][NW], red_scan[NW];
+    __shared__ int red_cnt[2][NW], scan_h[NW], scan_m[NW];
 
     const int g = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -106,21 +106,27 @@ __global__ void __launch_bounds__(THREADS) softnms_kernel(const NmsParams p) {
     }
     __syncthreads();
 
-    int i = 0;
-    while (i < n) {
-        // (1) first maximum of the live tail [i, n): per-thread scan, warp reduction, then every warp reduces the warp results
-        Cand c; c.s = ninf; c.tie = 0x7fffffff; c.pos = -1; c.x1 = c.x2 = c.ar = 0.0f; c.id = 0;
-        for (int q = i + tid; q < n; q += THREADS) {
+    const Cand none = {ninf, 0x7fffffff, -1, 0.0f, 0.0f, 0.0f, 0};
+    // arg-max of the live tail [i, n) from scratch (round 0, and after a round that deleted entries): per-thread scan, warp
+    // reduction, then every warp reduces the warp results, so the pick ends up in every thread's registers
+    auto scan_pick = [&](int from) -> Cand {
+        Cand c = none;
+        for (int q = from + tid; q < n; q += THREADS) {
             const float s = sc[q];
             const int tie = p.hard ? id[q] : q;
             if (c.pos < 0 || better(s, tie, c.s, c.tie)) { c.s = s; c.tie = tie; c.pos = q; }
         }
         if (c.pos >= 0) { c.x1 = x1[c.pos]; c.x2 = x2[c.pos]; c.ar = ar[c.pos]; c.id = id[c.pos]; }
         c = warp_best(c);
-        if (lane == 0) red[warp] = c;
+        if (lane == 0) red_scan[warp] = c;
         __syncthreads();
-        if (lane < NW) c = red[lane]; else c.pos = -1;
-        c = warp_best(c);                                   // the pick, in every thread's registers
+        c = lane < NW ? red_scan[lane] : none;
+        return warp_best(c);
+    };
+
+    int i = 0, par = 0;
+    Cand c = scan_pick(0);                                  // (1) first maximum of the live tail, first in position order
+    while (i < n) {
         const int m = c.pos;
         if (p.hard && (c.s == ninf || (p.max_num > 0 && i >= p.max_num))) break;   // nothing above min_score left / max_num reached
         if (tid == 0) {
@@ -131,17 +137,21 @@ __global__ void __launch_bounds__(THREADS) softnms_kernel(const NmsParams p) {
         const float ix1 = c.x1, ix2 = c.x2, iarea = c.ar;
 
         // (2) + (3) swap the pick to position i (nms_cpu.cpp:105-122) and decay the rest (:126-144) in one pass: the thread that
-        // owns position m moves the entry of position i there (nobody else touches i or m in this pass)
+        // owns position m moves the entry of position i there (nobody else touches i or m in this pass). The same pass tracks the
+        // maximum of the decayed scores: when the round deletes nothing, positions do not move and that maximum IS the next
+        // round's pick - one block barrier per round.
         int my_removed = 0;
+        Cand nc = none;
         for (int q = i + 1 + tid; q < n; q += THREADS) {
             float qx1, qx2, qar, s;
+            int qid = 0;
             if (q == m) {
-                qx1 = x1[i]; qx2 = x2[i]; qar = ar[i]; s = sc[i];
-                const int qid = id[i];
+                qx1 = x1[i]; qx2 = x2[i]; qar = ar[i]; s = sc[i]; qid = id[i];
                 x1[i] = c.x1; x2[i] = c.x2; ar[i] = c.ar; sc[i] = c.s; id[i] = c.id;
                 x1[q] = qx1; x2[q] = qx2; ar[q] = qar; id[q] = qid;
             } else {
                 qx1 = x1[q]; qx2 = x2[q]; qar = ar[q]; s = sc[q];
+                if (p.hard) qid = id[q];
             }
             const float xx1 = fmaxf(ix1, qx1), xx2 = fminf(ix2, qx2);
             const float inter = fmaxf(0.0f, __fsub_rn(xx2, xx1));
@@ -158,12 +168,21 @@ __global__ void __launch_bounds__(THREADS) softnms_kernel(const NmsParams p) {
                 my_removed += (s < p.min_score);
             }
             sc[q] = s;
+            const int tie = p.hard ? qid : q;
+            if (nc.pos < 0 || better(s, tie, nc.s, nc.tie)) { nc.s = s; nc.tie = tie; nc.pos = q; nc.x1 = qx1; nc.x2 = qx2; nc.ar = qar; }
         }
+        if (nc.pos >= 0) nc.id = id[nc.pos];                 // written, if at all, by this very thread (q == m)
+        nc = warp_best(nc);
         my_removed = warp_sum(my_removed);
-        if (lane == 0) red_cnt[warp] = my_removed;
+        if (lane == 0) { red[par][warp] = nc; red_cnt[par][warp] = my_removed; }
         __syncthreads();
-        const int R = warp_sum(lane < NW ? red_cnt[lane] : 0);
-        if (R == 0) { ++i; continue; }
+        const int R = warp_sum(lane < NW ? red_cnt[par][lane] : 0);
+        if (R == 0) {
+            c = lane < NW ? red[par][lane] : none;
+            c = warp_best(c);
+            ++i; par ^= 1;                                  // the buffers of this parity are rewritten two rounds from now
+            continue;
+        }
 
         // (4) deletions of the round (nms_cpu.cpp:147-156): holes below n2 take the survivors at or above n2, last first
         const int len = n - (i + 1);
@@ -206,8 +225,9 @@ __global__ void __launch_bounds__(THREADS) softnms_kernel(const NmsParams p) {
             x1[dst] = x1[src]; x2[dst] = x2[src]; sc[dst] = sc[src]; ar[dst] = ar[src]; id[dst] = id[src];
         }
         n = n2;
-        ++i;
+        ++i; par ^= 1;
         __syncthreads();
+        if (i < n) c = scan_pick(i);
     }
     if (tid == 0) p.kept[g] = i;
 }
