@@ -248,3 +248,41 @@ def test_detpost_oracle_matches_reference_golden():
         assert np.array_equal(c, g[f"result/{v}/action"])
         assert np.array_equal(np.array([[round(float(a), 3), round(float(b), 3)] for a, b in s]), g[f"result/{v}/segment"])
         np.testing.assert_allclose(p.astype(np.float64), g[f"result/{v}/score"], rtol=NMS_SCORE_RTOL, atol=0)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# backward oracle (groundwork for the training leg)
+# ---------------------------------------------------------------------------------------------------------------------
+GRAD_CASES = [str(n) for n in np.load(os.path.join(GOLD, "grads.npz"))["cases"]]
+
+
+@pytest.mark.parametrize("name", GRAD_CASES)
+def test_backward_oracle_matches_reference_autograd(name):
+    """oracle/tim_oracle_bwd.py (numpy reverse mode, float64) against torch.autograd over the UNMODIFIED reference
+    (tests/golden/grads.npz, tools/make_golden_grads.py): for every parameter that receives a gradient and for both feature
+    inputs, the L2 norm, the sum and 512 sampled entries of d L / d tensor agree to 1e-9 relative (of the tensor's largest sampled
+    magnitude); parameters autograd leaves without gradient get none here either."""
+    import zlib
+    from oracle.tim_oracle_bwd import TIMOracleGrad
+    g = np.load(os.path.join(GOLD, "grads.npz"))
+    case = MANIFEST[name]
+    cfg = TIMConfig(**case["cfg"])
+    sd = synth_state_dict(cfg, case["weight_seed"], case["style"])
+    inp = synth_inputs(cfg, case["B"], case["Qv"], case["Qa"], case["input_seed"], shared_queries=case["shared_queries"])
+    cot = {}
+    for key in g.files:
+        if key.startswith(f"{name}/out_shape/"):
+            k = key.rsplit("/", 1)[1]
+            cot[k] = np.random.default_rng(zlib.crc32(f"{name}/{k}".encode())).standard_normal(tuple(g[key]))
+    _, grads = TIMOracleGrad(cfg, sd, np.float64).forward_backward(inp.get("vis"), inp.get("aud"), inp["times"], case["Qv"], case["Qa"], cot)
+    want = [str(k) for k in g[f"{name}/keys"]]
+    assert sorted(grads) == want, (sorted(set(grads) ^ set(want)))
+    for k in want:
+        flat = np.asarray(grads[k], np.float64).reshape(-1)
+        idx = np.sort(np.random.default_rng(zlib.crc32(f"idx/{name}/{k}".encode())).choice(flat.size, size=min(512, flat.size), replace=False))
+        norm, total = g[f"{name}/stat/{k}"]
+        vals = g[f"{name}/vals/{k}"]
+        scale = max(np.abs(vals).max(), 1e-30)
+        assert np.abs(flat[idx] - vals).max() <= 1e-9 * scale, k
+        assert abs(np.sqrt((flat * flat).sum()) - norm) <= 1e-9 * max(norm, 1e-30), k
+        assert abs(flat.sum() - total) <= 1e-9 * max(norm * np.sqrt(flat.size), 1e-30), k
