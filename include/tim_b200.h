@@ -119,6 +119,11 @@ int tim_encoder_fwd_indexed(tim_ctx* ctx, const tim_feature_bank* bank, const fl
 int tim_forward_host(tim_ctx* ctx, const float* vis, const float* aud, const float* times, int B, int T, int Qv, int Qa,
                      const tim_outputs* host_outs, int clips_per_chunk, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 
+/* The chunk sizes tim_forward_host uses for a batch of B clips (pure host arithmetic, no device needed): writes up to max_out
+ * sizes to out and returns the number of chunks (negative tim_status on bad arguments). rows_per_clip = token rows per clip
+ * (tim_seq_len), E = 2 * d_model, sixteen_bit = compute dtype is not TIM_FP32. */
+int tim_host_chunk_schedule(int B, int clips_per_chunk, int rows_per_clip, int E, int num_sms, int sixteen_bit, int* out, int max_out);
+
 /* Introspection used by bench.py / tests. */
 size_t tim_workspace_bytes(const tim_ctx* ctx);         /* bytes currently held by the context's workspace */
 uint64_t tim_launch_count(const tim_ctx* ctx);          /* kernels launched by this context so far */

@@ -122,3 +122,47 @@ print("OK")
 """
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
+
+
+def test_forward_host_chunk_schedule(lib):
+    """The chunk sizes tim_forward_host cuts a batch into (pure host arithmetic of the library, no device): they add up to B, none
+    is empty or larger than the target, and on the 16-bit path with E a multiple of 256 every chunk except the remainder is a whole
+    number of GEMM waves (row tiles a multiple of num_sms / gcd(num_sms, E / 256), rounded down to whole clips); the ends taper."""
+    import ctypes as C
+    import math
+    import random
+
+    def sched(B, cpc, rows, E, sms, sixteen):
+        buf = (C.c_int * 4096)()
+        n = lib.tim_host_chunk_schedule(B, cpc, rows, E, sms, int(sixteen), buf, 4096)
+        assert 0 < n <= 4096, (B, cpc, rows, E, sms, sixteen, n)
+        return list(buf[:n])
+
+    # the bench's end-to-end call: cfg2, 1024 clips, target B // 3
+    assert sched(1024, 341, 200, 1024, 148, True) == [47, 142, 315, 331, 142, 47]
+    assert sched(1024, 256, 200, 1024, 148, True) == [47, 94, 34, 236, 236, 236, 94, 47]
+    # fp32 mode / widths the pair kernel does not tile: plain tapered chunks
+    assert sched(96, 24, 2148, 1024, 148, False) == [6, 12, 12, 24, 24, 12, 6]
+    assert sched(4, 0, 200, 1024, 148, True) == [4]
+    assert sched(5, 99, 13, 128, 148, True) == [5]
+    rnd = random.Random(0)
+    for _ in range(3000):
+        B = rnd.randint(1, 40000)
+        cpc = rnd.choice([0, rnd.randint(1, B), rnd.randint(1, 2 * B), B // 3 + 1, B // 4 + 1])
+        rows = rnd.choice([13, 24, 100, 200, 528, 2148])
+        E = rnd.choice([128, 256, 512, 1024, 1536, 2048, 96])
+        sms = rnd.choice([148, 132, 8])
+        sixteen = rnd.random() < 0.8
+        ch = sched(B, cpc, rows, E, sms, sixteen)
+        target = B if (cpc <= 0 or cpc > B) else cpc
+        assert sum(ch) == B and min(ch) > 0 and max(ch) <= target, (B, cpc, rows, E, sms, sixteen, ch)
+        if sixteen and E % 256 == 0:
+            unit_tiles = sms // math.gcd(sms, E // 256)
+            unit = unit_tiles * 256 // rows
+            if unit >= 8 and target >= unit and ((target + 1) * rows - 1) // (unit_tiles * 256) >= 1:
+                k = ((target + 1) * rows - 1) // (unit_tiles * 256)      # the largest k whose k units of waves fit the target
+                body = k * unit_tiles * 256 // rows          # a full-size chunk: k units of waves, rounded down to whole clips
+                assert max(ch) <= body and (B < body or max(ch) == body)
+                assert -(-body * rows // 256) <= k * unit_tiles    # its row tiles fit k units exactly
+                aligned = [c for c in ch if any(c == j * unit_tiles * 256 // rows for j in range(1, k + 1))]
+                assert len(aligned) >= len(ch) - 1          # at most one remainder chunk

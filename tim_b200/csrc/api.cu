@@ -1022,6 +1022,49 @@ int tim_encoder_fwd_indexed(tim_ctx* c, const tim_feature_bank* fb, const float*
     });
 }
 
+// Chunk sizes of tim_forward_host (pure host arithmetic; tim_host_chunk_schedule exposes it to the CPU tests). cpc = target clips
+// per chunk, 1 <= cpc <= B. Every chunk is <= cpc and > 0, the sizes add up to B.
+static std::vector<int> chunk_schedule(int B, int cpc, int rows_per_clip, int E, int num_sms, bool sixteen_bit) {
+    int unit_tiles = 0;
+    if (sixteen_bit && E > 0 && E % 256 == 0 && rows_per_clip > 0 && num_sms > 0) {
+        int a = num_sms, b = E / 256;
+        while (b) { const int t = a % b; a = b; b = t; }
+        unit_tiles = num_sms / a;
+    }
+    auto unit_clips = [&](int k) { return static_cast<int>(static_cast<long long>(k) * unit_tiles * 256 / rows_per_clip); };
+    std::vector<int> head, tail, out;
+    int left = B, body = cpc;
+    // the largest k with unit_clips(k) <= cpc (unit_clips(k) can exceed k * unit_clips(1): floor(k * u) >= k * floor(u))
+    const int body_units = (unit_tiles > 0 && unit_clips(1) >= 8)
+        ? static_cast<int>(((static_cast<long long>(cpc) + 1) * rows_per_clip - 1) / (static_cast<long long>(unit_tiles) * 256)) : 0;
+    if (body_units >= 1) {
+        body = unit_clips(body_units);
+        if (B >= 3 * body && body_units >= 4) {
+            head = {unit_clips(body_units / 4), unit_clips(body_units / 2)};
+            tail = {head[1], head[0]};
+        }
+    } else if (B >= 4 * cpc && cpc >= 8) {
+        head = {cpc / 4, cpc / 2};
+        tail = {cpc / 2, cpc / 4};
+    }
+    for (int n : head) left -= 2 * n;
+    for (int n : head) out.push_back(n);
+    // the remainder that does not fill a body chunk goes early (behind the head), not into the D2H tail
+    if (left % body) { out.push_back(left % body); left -= left % body; }
+    while (left > 0) { out.push_back(body); left -= body; }
+    for (int n : tail) out.push_back(n);
+    return out;
+}
+
+int tim_host_chunk_schedule(int B, int clips_per_chunk, int rows_per_clip, int E, int num_sms, int sixteen_bit, int* out, int max_out) {
+    if (B <= 0 || rows_per_clip <= 0 || E <= 0 || num_sms <= 0 || (max_out > 0 && !out)) return TIM_ERR_INVALID;
+    int cpc = clips_per_chunk;
+    if (cpc <= 0 || cpc > B) cpc = B;
+    const std::vector<int> v = chunk_schedule(B, cpc, rows_per_clip, E, num_sms, sixteen_bit != 0);
+    for (size_t i = 0; i < v.size() && static_cast<int>(i) < max_out; ++i) out[i] = v[i];
+    return static_cast<int>(v.size());
+}
+
 int tim_forward_host(tim_ctx* c, const float* vis, const float* aud, const float* times, int B, int T_, int Qv, int Qa,
                      const tim_outputs* ho, int cpc, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
     if (!c) return TIM_ERR_INVALID;
@@ -1080,36 +1123,10 @@ int tim_forward_host(tim_ctx* c, const float* vis, const float* aud, const float
     // whole WAVES of GEMM tiles: the encoder GEMMs run 256-row tiles on num_sms persistent CTAs, so a chunk whose row-tile count
     // is a multiple of num_sms / gcd(num_sms, E / 256) fills every wave of all four of them (E = 1024 on 148 SMs: 37 row tiles
     // = 47 clips of 200 tokens); a 64-clip chunk would leave out_proj / linear2 at 1.35 waves = 68 % occupancy.
-    std::vector<int> chunk_b0, chunk_nb;
+    std::vector<int> chunk_b0, chunk_nb = chunk_schedule(B, cpc, c->Ft + qp.Qt, c->E, c->num_sms, g.compute_dtype != TIM_FP32);
     {
-        const int rows_per_clip = c->Ft + qp.Qt;
-        int unit_tiles = 0;
-        if (g.compute_dtype != TIM_FP32 && c->E % 256 == 0 && rows_per_clip > 0) {
-            int a = c->num_sms, b = c->E / 256;
-            while (b) { const int t = a % b; a = b; b = t; }
-            unit_tiles = c->num_sms / a;
-        }
-        auto unit_clips = [&](int k) { return static_cast<int>(static_cast<long long>(k) * unit_tiles * 256 / rows_per_clip); };
-        std::vector<int> head, tail;
-        int left = B, body = cpc;
-        const int body_units = (unit_tiles > 0 && unit_clips(1) >= 8) ? cpc / unit_clips(1) : 0;
-        if (body_units >= 1) {
-            body = unit_clips(body_units);
-            if (B >= 3 * body && body_units >= 4) {
-                head = {unit_clips(body_units / 4), unit_clips(body_units / 2)};
-                tail = {head[1], head[0]};
-            }
-        } else if (B >= 4 * cpc && cpc >= 8) {
-            head = {cpc / 4, cpc / 2};
-            tail = {cpc / 2, cpc / 4};
-        }
-        for (int n : head) left -= 2 * n;
         int b0 = 0;
-        for (int n : head) { chunk_b0.push_back(b0); chunk_nb.push_back(n); b0 += n; }
-        // the remainder that does not fill a body chunk goes early (behind the head), not into the D2H tail
-        if (left % body) { const int n = left % body; chunk_b0.push_back(b0); chunk_nb.push_back(n); b0 += n; left -= n; }
-        while (left > 0) { chunk_b0.push_back(b0); chunk_nb.push_back(body); b0 += body; left -= body; }
-        for (int n : tail) { chunk_b0.push_back(b0); chunk_nb.push_back(n); b0 += n; }
+        for (int n : chunk_nb) { chunk_b0.push_back(b0); b0 += n; }
     }
     const int nchunks = static_cast<int>(chunk_nb.size());
     struct EventSet {                                   // destroyed on every exit path
