@@ -166,3 +166,23 @@ def test_forward_host_chunk_schedule(lib):
                 assert -(-body * rows // 256) <= k * unit_tiles    # its row tiles fit k units exactly
                 aligned = [c for c in ch if any(c == j * unit_tiles * 256 // rows for j in range(1, k + 1))]
                 assert len(aligned) >= len(ch) - 1          # at most one remainder chunk
+
+
+def test_postprocess_without_a_device_is_a_loud_error(lib):
+    """tim_b200.postprocess has no CPU path either: without a CUDA device every entry point raises instead of computing on the
+    host (and an explicit CPU device is refused)."""
+    import numpy as np
+    import torch
+    from tim_b200 import postprocess as pp
+    segs, scores, cls = np.array([[0.0, 1.0], [0.5, 1.5]], np.float32), np.array([0.9, 0.8], np.float32), np.zeros(2, np.int64)
+    with pytest.raises(RuntimeError, match="CUDA device only"):
+        pp.batched_nms(segs, scores, cls, 0.1, 0.001, device="cpu")
+    with pytest.raises(RuntimeError, match="CUDA device only"):
+        pp.threshold_detections(torch.zeros((2, 3)), torch.zeros((2, 2), dtype=torch.float64), 0.03, device="cpu")
+    with pytest.raises(RuntimeError, match="CUDA device only"):
+        pp.decode_predictions(torch.zeros((2, 3)), torch.zeros((2, 2)), torch.zeros(1, dtype=torch.float64), 30.0, 1.0, device="cpu")
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            pp.batched_nms(segs, scores, cls, 0.1, 0.001)
+    with pytest.raises(NotImplementedError):
+        pp.batched_nms(segs, scores, cls, 0.1, 0.001, multi_class=False)
