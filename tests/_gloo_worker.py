@@ -32,6 +32,25 @@ def main():
         assert np.array_equal(act.numpy(), full["action"])
         assert t == float(world)
         print("GLOO_SHARD_OK")
+    # the training leg's one collective: gradients in ONE flat buffer, one all-reduce (sum / world) - against per-tensor averaging
+    from tim_b200.dist import FlatGrads
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.LayerNorm(5), torch.nn.Linear(5, 3))
+    flat = FlatGrads(net.named_parameters())
+    assert all(p.grad.data_ptr() == flat.view(n).data_ptr() for n, p in net.named_parameters())
+    assert all(lo % FlatGrads.ALIGN_ELEMS == 0 for lo, _ in flat.offsets.values())
+    x = torch.randn((4, 7), generator=torch.Generator().manual_seed(10 + rank))
+    net(x).square().sum().backward()                        # autograd accumulates INTO the flat views
+    mine = {n: p.grad.clone() for n, p in net.named_parameters()}
+    assert flat.buffer.abs().sum() > 0
+    flat.all_reduce()
+    for n, p in net.named_parameters():
+        parts = [torch.zeros_like(mine[n]) for _ in range(world)]
+        dist.all_gather(parts, mine[n])
+        assert torch.allclose(p.grad, sum(parts) / world, rtol=1e-6, atol=1e-7), n
+        assert p.grad.data_ptr() == flat.view(n).data_ptr()
+    if rank == 0:
+        print("GLOO_FLATGRAD_OK")
     dist.destroy_process_group()
 
 

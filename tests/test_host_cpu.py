@@ -90,6 +90,7 @@ def test_gloo_world2_sharded_forward_matches_single():
                        cwd=ROOT, env={**os.environ, "OMP_NUM_THREADS": "2"})
     assert r.returncode == 0, r.stdout + r.stderr
     assert "GLOO_SHARD_OK" in r.stdout
+    assert "GLOO_FLATGRAD_OK" in r.stdout              # flat gradient buffer + one all-reduce (training-leg groundwork)
 
 
 @pytest.mark.parametrize("variant", ["recognition", "detection"])

@@ -66,3 +66,47 @@ def gather_rows(local: torch.Tensor, rows_per_clip: int, B: int) -> torch.Tensor
         lo, hi = shard_range(B, r, world)
         parts.append(bufs[r][:(hi - lo) * rows_per_clip])
     return torch.cat(parts, 0)
+
+
+class FlatGrads:
+    """Groundwork for the training leg: ONE contiguous fp32 buffer holds the gradient of
+    every parameter, `param.grad` are views into it, and one all-reduce per step (sum, then divide by the world size) replaces
+    DDP's bucketed all-reduce (`recognition/time_interval_machine/models/build.py:58-63`). The backward kernels will write their
+    weight gradients straight into this buffer (`tim_encoder_bwd`'s flat dW argument); AdamW keeps seeing ordinary `.grad` tensors.
+
+    Layout: parameters in the order given (state_dict order), each segment padded to 128 bytes so that every view is aligned for
+    vector / TMA access. `offsets[name] = (first element, number of elements)`.
+    """
+
+    ALIGN_ELEMS = 32            # 128 bytes of fp32
+
+    def __init__(self, named_params, device=None):
+        named = [(n, p) for n, p in named_params if p.requires_grad]
+        if not named:
+            raise ValueError("FlatGrads: no parameter requires a gradient")
+        device = device if device is not None else named[0][1].device
+        self.offsets = {}
+        at = 0
+        for n, p in named:
+            self.offsets[n] = (at, p.numel())
+            at += (p.numel() + self.ALIGN_ELEMS - 1) // self.ALIGN_ELEMS * self.ALIGN_ELEMS
+        self.buffer = torch.zeros((at,), dtype=torch.float32, device=device)
+        self._params = named
+        for n, p in named:
+            lo, cnt = self.offsets[n]
+            p.grad = self.buffer[lo:lo + cnt].view_as(p)
+
+    def zero_(self) -> None:
+        self.buffer.zero_()
+
+    def all_reduce(self, group=None, average: bool = True) -> None:
+        """The one data-path collective of a training step: NCCL on GPUs (NVLink / NVSwitch), gloo in the CPU tests."""
+        if not (dist.is_available() and dist.is_initialized()):
+            return
+        dist.all_reduce(self.buffer, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            self.buffer.div_(dist.get_world_size(group))
+
+    def view(self, name: str) -> torch.Tensor:
+        lo, cnt = self.offsets[name]
+        return self.buffer[lo:lo + cnt]
