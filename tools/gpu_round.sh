@@ -29,3 +29,13 @@ if [ "${SKIP_NCU:-0}" != "1" ]; then
       -o $OUT/prof_gemm_$TAG -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline > $OUT/ncu_full_$TAG.log 2>&1
   echo "ncu full exit $?"
 fi
+
+# detection post-processing kernels (soft-NMS of an evaluation-sized input against the reference's compiled extension)
+if [ "${SKIP_NMS:-0}" != "1" ]; then
+  timeout 200 python tools/nms_bench.py --out $OUT/nms_bench_$TAG.json > $OUT/nms_bench_$TAG.log 2>&1
+  echo "nms bench exit $?"; tail -n 1 $OUT/nms_bench_$TAG.log | cut -c1-400
+fi
+# per-launch summaries of the full captures (what profiles/*_ncu_full_*.csv hold)
+for rep in $OUT/prof_gemm_$TAG.ncu-rep; do
+  [ -f "$rep" ] && python tools/ncu_summary.py "$rep" > "${rep%.ncu-rep}.csv" 2>/dev/null
+done
