@@ -286,3 +286,19 @@ def test_backward_oracle_matches_reference_autograd(name):
         assert np.abs(flat[idx] - vals).max() <= 1e-9 * scale, k
         assert abs(np.sqrt((flat * flat).sum()) - norm) <= 1e-9 * max(norm, 1e-30), k
         assert abs(flat.sum() - total) <= 1e-9 * max(norm * np.sqrt(flat.size), 1e-30), k
+
+
+@pytest.mark.parametrize("name", sorted(MANIFEST))
+def test_torch_op_port_matches_reference_golden(name):
+    """oracle/tim_oracle_torch.py - the TIMED CPU arm of bench.py, which restates the reference with the PyTorch CPU calls the
+    reference's modules make - against the golden vectors of the real reference: same tolerance as the numpy oracle (it is in fact
+    bit-identical to the reference on the machine that minted them), so what the bench times on the host computes the reference's
+    outputs."""
+    pytest.importorskip("torch")
+    from oracle.tim_oracle_torch import TIMOracleTorch
+    cfg, sd, inp, gold, case = load_case(name)
+    Qv = inp["times"].shape[1] - cfg.F_tot if case["pyramid"] else case["Qv"]
+    out = TIMOracleTorch(cfg, sd).forward(inp.get("vis"), inp.get("aud"), inp["times"], Qv, case["Qa"])
+    for k, ref in gold.items():
+        assert out[k] is not None, k
+        assert rel_l2(out[k], ref) <= 2e-6, (k, rel_l2(out[k], ref))
