@@ -187,3 +187,30 @@ def test_postprocess_without_a_device_is_a_loud_error(lib):
             pp.batched_nms(segs, scores, cls, 0.1, 0.001)
     with pytest.raises(NotImplementedError):
         pp.batched_nms(segs, scores, cls, 0.1, 0.001, multi_class=False)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (CPU only, no GPU needed): ONE JSON line on stdout carrying the keys the driver reads - the same
+    metric / unit / config as the GPU arm, `impl: reference`, a `cpu_baseline` describing the run and an `e2e` object without
+    device copies; under torchrun only rank 0 prints (checked here by running a second process as RANK=1)."""
+    import json
+    env = {**os.environ, "OMP_NUM_THREADS": "1"}           # what torchrun hands its workers
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1", "--steps", "1",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e", "impl"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["metric"] == "clips_x_queries_per_sec" and d["unit"] == "clips*queries/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["value"] > 0 and "workload" in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["value"] == d["value"] and cb["cores"] >= 1 and cb["sample"]
+    assert cb["cores"] == len(os.sched_getaffinity(0)), "the CPU arm must use every host thread even under OMP_NUM_THREADS=1"
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    r1 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1", "--steps", "1",
+                         "--warmup", "1", "--gpus", "2"], capture_output=True, text=True, timeout=600, cwd=ROOT,
+                        env={**env, "RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
