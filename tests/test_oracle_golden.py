@@ -302,3 +302,46 @@ def test_torch_op_port_matches_reference_golden(name):
     for k, ref in gold.items():
         assert out[k] is not None, k
         assert rel_l2(out[k], ref) <= 2e-6, (k, rel_l2(out[k], ref))
+
+
+@pytest.mark.parametrize("B,Ft,Qt,H,hd", [(2, 12, 7, 2, 16), (3, 10, 0, 2, 8), (1, 5, 9, 1, 32)])
+def test_two_stream_attention_oracles_match_dense_masked_attention(B, Ft, Qt, H, hd):
+    """oracle/kernel_oracles.py (forward and backward of the attention core in the library's two-stream layout, exploiting the mask's
+    structure) against the reference's formulation - a dense S x S masked softmax per clip (tim.py:161-166 mask) differentiated by
+    torch.autograd in float64: outputs and d L / d qkv agree to 1e-12."""
+    torch = pytest.importorskip("torch")
+    from oracle.kernel_oracles import LN2, attention_bwd_two_stream, attention_fwd_two_stream
+    rng = np.random.default_rng(Ft * 7 + Qt)
+    E, S = H * hd, Ft + Qt
+    M = B * S
+    qkv = rng.standard_normal((M, 3 * E))
+    dout = rng.standard_normal((M, E))
+    out, _ = attention_fwd_two_stream(qkv, B, Ft, Qt, H, hd)
+    dqkv = attention_bwd_two_stream(qkv, dout, B, Ft, Qt, H, hd)
+
+    x = torch.from_numpy(qkv).requires_grad_(True)
+    mask = torch.ones(S, S, dtype=torch.bool)
+    mask[:, :Ft] = False
+    mask.fill_diagonal_(False)
+    ref = torch.zeros(M, E, dtype=torch.float64)
+    for b in range(B):
+        rows = torch.cat([torch.arange(b * Ft, (b + 1) * Ft), B * Ft + torch.arange(b * Qt, (b + 1) * Qt)])
+        xb = x[rows]
+        q, k, v = (xb[:, i * E:(i + 1) * E].reshape(S, H, hd).transpose(0, 1) for i in range(3))
+        p = torch.softmax(((q @ k.transpose(1, 2)) * LN2).masked_fill(mask[None], float("-inf")), -1)
+        ref = ref.index_add(0, rows, (p @ v).transpose(0, 1).reshape(S, E))
+    (ref * torch.from_numpy(dout)).sum().backward()
+    assert np.abs(out - ref.detach().numpy()).max() <= 1e-12 * max(1.0, np.abs(out).max())
+    assert np.abs(dqkv - x.grad.numpy()).max() <= 1e-12 * max(1.0, np.abs(dqkv).max())
+
+
+def test_layernorm_bwd_rows_matches_autograd():
+    torch = pytest.importorskip("torch")
+    from oracle.kernel_oracles import layernorm_bwd_rows
+    rng = np.random.default_rng(2)
+    x, dy, g, b = rng.standard_normal((37, 64)), rng.standard_normal((37, 64)), rng.standard_normal(64), rng.standard_normal(64)
+    tx, tg, tb = (torch.from_numpy(a).requires_grad_(True) for a in (x, g, b))
+    (torch.nn.functional.layer_norm(tx, (64,), tg, tb, 1e-5) * torch.from_numpy(dy)).sum().backward()
+    dx, dg, db = layernorm_bwd_rows(dy, x, g)
+    for got, want in ((dx, tx.grad), (dg, tg.grad), (db, tb.grad)):
+        assert np.abs(got - want.numpy()).max() <= 1e-12 * max(1.0, np.abs(got).max())
