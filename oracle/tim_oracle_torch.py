@@ -33,10 +33,13 @@ from tim_b200.config import RECOGNITION, TIMConfig
 
 
 class TIMOracleTorch:
-    def __init__(self, cfg: TIMConfig, sd: Dict[str, np.ndarray], dtype=torch.float32):
+    def __init__(self, cfg: TIMConfig, sd: Dict[str, np.ndarray], dtype=torch.float32, device="cpu"):
+        """device="cpu" is the timed CPU arm; a CUDA device gives the eager-PyTorch GPU baseline of tools/eager_baseline.py (the same
+        library calls the reference would make on a GPU)."""
         self.cfg = cfg
         self.dt = dtype
-        self.sd = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dtype) for k, v in sd.items()}
+        self.dev = torch.device(device)
+        self.sd = {k: torch.from_numpy(np.ascontiguousarray(v)).to(device=self.dev, dtype=dtype) for k, v in sd.items()}
 
     def time_mlp(self, times: torch.Tensor) -> torch.Tensor:
         s = self.sd
@@ -88,7 +91,7 @@ class TIMOracleTorch:
         """x [S, B, E] -> [B, S, E]; the reference's mask construction and encoder loop (tim.py:161-168, transformers.py:32-48)."""
         cfg, s = self.cfg, self.sd
         S, B, E = x.shape
-        masks = torch.ones((S, S))
+        masks = torch.ones((S, S), device=x.device)
         masks[:, :cfg.F_tot] = 0.
         masks = masks.fill_diagonal_(0.).unsqueeze(0)
         masks = masks.repeat_interleave(cfg.nhead * B, dim=0).bool()
@@ -143,10 +146,16 @@ class TIMOracleTorch:
     @torch.no_grad()
     def forward(self, vis, aud, times, Qv: int, Qa: int) -> Dict[str, Optional[np.ndarray]]:
         """numpy in, numpy out (dict as TIMOracle.forward): time_mlp + encoder on raw interval times [B, T, 2]."""
-        t = (lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(self.dt))
-        te = self.time_mlp(t(times))
-        x = self.backbone(self.assemble(t(vis), t(aud), te, Qv, Qa))
+        t = (lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(device=self.dev, dtype=self.dt))
+        out = self.forward_tensors(t(vis), t(aud), t(times), Qv, Qa)
+        return {k: (None if v is None else v.float().cpu().numpy()) for k, v in out.items()}
+
+    @torch.no_grad()
+    def forward_tensors(self, vis, aud, times, Qv: int, Qa: int) -> Dict[str, Optional[torch.Tensor]]:
+        """Tensors (already on self.dev) in, tensors out - no host round trip (what tools/eager_baseline.py times)."""
+        te = self.time_mlp(times)
+        x = self.backbone(self.assemble(vis, aud, te, Qv, Qa))
         out = self.heads(x, Qv, Qa)
         out["feats"] = x[:, :self.cfg.F_tot]
         out["time_encodings"] = te
-        return {k: (None if v is None else v.numpy()) for k, v in out.items()}
+        return out

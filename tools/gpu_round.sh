@@ -39,3 +39,8 @@ fi
 for rep in $OUT/prof_gemm_$TAG.ncu-rep; do
   [ -f "$rep" ] && python tools/ncu_summary.py "$rep" > "${rep%.ncu-rep}.csv" 2>/dev/null
 done
+# secondary baseline: the reference's own PyTorch calls, eager, on the same GPU
+if [ "${SKIP_EAGER:-0}" != "1" ]; then
+  timeout 300 python tools/eager_baseline.py --out $OUT/eager_baseline_$TAG.json > $OUT/eager_baseline_$TAG.log 2>&1
+  echo "eager baseline exit $?"; tail -n 1 $OUT/eager_baseline_$TAG.log | cut -c1-600
+fi
