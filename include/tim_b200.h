@@ -1,4 +1,4 @@
-/* libtim_b200 — C ABI of the B200-native TIM encoder forward.
+/* libtim_b200 — C ABI of the B200-native TIM encoder: forward, and the training leg (backward + gradient all-reduce).
  *
  * The reference (JacobChalk/TIM) has no FFI: its seam for this path is the Python nn.Module
  *     TIM.forward(inputs, forward_type, ...)      recognition/time_interval_machine/models/tim.py:174-191
@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TIM_ABI_VERSION 1
+#define TIM_ABI_VERSION 2
 
 typedef enum {
     TIM_OK = 0,
@@ -181,12 +181,49 @@ int tim_det_count(const float* preds, const double* proposals, int64_t R, int C,
 int tim_det_emit(const float* preds, const double* proposals, int64_t R, int C, float score_threshold, const int64_t* offsets /*[R]*/,
                  int64_t* out_row, int64_t* out_cls, float* out_score, float* out_seg /*[n,2]*/, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Training leg. Replaces what torch.autograd + DistributedDataParallel do for this path when the
+ * reference trains: recognition/scripts/train.py:190-260 (forward under autocast), :354-366 (GradScaler.scale(loss).backward(),
+ * optimizer step), recognition/time_interval_machine/models/build.py:58-63 (DDP bucketed gradient all-reduce),
+ * detection/time_interval_machine/models/tim.py:272-337 (forward_train). Dropout is NOT applied (p = 0 semantics; the Python
+ * drop-in refuses modules whose dropout probability is non-zero instead of silently diverging).
+ *
+ *  tim_train_enable      allocates the transposed weight copies the input-gradient GEMMs read; every weight must be set (again)
+ *                        with tim_set_weight afterwards.
+ *  tim_bind_grad         gradient destination (device fp32, 16-byte aligned, the parameter's shape) of one state_dict key. The
+ *                        backward ACCUMULATES into it (+=), like autograd into param.grad; the caller zeroes it (zero_grad).
+ *                        Binding all keys to slices of ONE flat buffer makes the data-parallel exchange a single collective.
+ *  tim_time_mlp_fwd_train / tim_time_mlp_bwd        "time_mlp" forward that keeps its activations, and its backward
+ *                        (d_out [B, T, d_model] = gradient of the time encodings, i.e. d_time_enc of tim_encoder_bwd plus
+ *                        whatever else the loss sent there).
+ *  tim_encoder_fwd_train / tim_encoder_bwd          "encoder" forward that keeps its activations (one outstanding forward per
+ *                        context), and its backward: grad_outs holds the gradients of the outputs (NULL where the loss does not
+ *                        touch an output), d_time_enc [B, T, d_model] receives the gradient w.r.t. the time encodings. Gradients
+ *                        w.r.t. the input features are not produced (they are data).
+ *  tim_comm_unique_id / tim_comm_init / tim_allreduce_grads     the one data-path collective: ncclAllReduce (average) over the
+ *                        flat gradient buffer on `stream`, on a communicator of the library's own (NCCL is dlopen'ed: the copy
+ *                        torch already mapped). Rank 0 creates the 128-byte id, the caller ships it to the other ranks.
+ * 16-bit modes use 16-bit gradient operands with fp32 accumulation, exactly like the reference's autocast backward: with fp16
+ * keep the reference's GradScaler (train.py:354-366) so that small gradients do not underflow. */
+int tim_train_enable(tim_ctx* ctx);
+int tim_bind_grad(tim_ctx* ctx, const char* key, float* dst);
+int tim_time_mlp_fwd_train(tim_ctx* ctx, const float* times, float* out, int B, int T, void* stream);
+int tim_time_mlp_bwd(tim_ctx* ctx, const float* d_out, void* stream);
+int tim_encoder_fwd_train(tim_ctx* ctx, const float* vis, const float* aud, const float* time_enc, int B, int T, int Qv, int Qa,
+                          const tim_outputs* outs, void* stream);
+int tim_encoder_bwd(tim_ctx* ctx, const tim_outputs* grad_outs, float* d_time_enc, void* stream);
+size_t tim_train_tape_bytes(const tim_ctx* ctx);        /* bytes held by the saved activations */
+int tim_comm_unique_id(void* out128);
+int tim_comm_init(tim_ctx* ctx, const void* id128, int rank, int world);
+int tim_allreduce_grads(tim_ctx* ctx, float* buf, size_t n, void* stream);
+
 /* Live per-kernel-class timing (bench.py's roofline object): between begin and end every launch is bracketed by a
  * CUDA-event pair on its own stream. Classes: 0 GEMM (tcgen05 / fp32 SIMT) other than 5 and 6, 1 attention, 2 LayerNorm /
- * row statistics, 3 token assembly, 4 other row kernels, 5 encoder GEMMs with a folded LayerNorm in front (in_proj, linear1:
- * tensor-bound), 6 encoder GEMMs that also write the residual stream (out_proj, linear2: 12 - 14 KB of HBM traffic per row).
+ * row statistics (forward and backward), 3 token assembly, 4 other row kernels, 5 encoder GEMMs with a folded LayerNorm in front
+ * (in_proj, linear1: tensor-bound), 6 encoder GEMMs that also write the residual stream (out_proj, linear2: 12 - 14 KB of HBM
+ * traffic per row), 7 input-gradient GEMMs, 8 weight-gradient GEMMs, 9 attention backward.
  * end() synchronises the device and fills ms / algorithmic FLOPs / launch counts. */
-#define TIM_PROFILE_CLASSES 7
+#define TIM_PROFILE_CLASSES 10
 int tim_profile_begin(tim_ctx* ctx);
 int tim_profile_end(tim_ctx* ctx, double* ms, double* flops, uint64_t* count, int n_classes);
 
@@ -201,6 +238,15 @@ int tim_bench_linear(int compute_dtype, const void* A16, const void* W16, const 
 /* attention over a two-stream qkv buffer [(B*Ft + B*Qt), 3*H*hd] fp32 -> out [(B*Ft + B*Qt), H*hd] fp32.
  * The q columns must already carry the hd^-0.5 * log2(e) factor that tim_set_weight folds into in_proj. */
 int tim_test_attention(int compute_dtype, const float* qkv, float* out, int B, int Ft, int Qt, int H, int hd, void* stream);
+
+/* dW[N, K] (fp32, accumulated into) += dY[M, N]^T X[M, K] through the selected compute path; splits <= 0: chosen by the library */
+int tim_test_wgrad(int compute_dtype, const float* dY, const float* X, float* dW, int M, int N, int K, int splits, void* stream);
+int tim_bench_wgrad(int compute_dtype, const void* dY16, const void* X16, float* dW, int M, int N, int K, int splits, int iters,
+                    float* ms_per_iter);
+/* attention backward at the kernel boundary: qkv / dqkv [(B*Ft + B*Qt), 3*H*hd], dO [.., H*hd], fp32 device buffers; dq is scaled by
+ * qscale (ln 2: gradient w.r.t. the stored, pre-scaled q; hd^-0.5: w.r.t. the un-scaled in_proj output) */
+int tim_test_attention_bwd(int compute_dtype, const float* qkv, const float* dO, float* dqkv, int B, int Ft, int Qt, int H, int hd,
+                           float qscale, void* stream);
 
 /* timing hook (tools/attn_bench.py): `iters` back-to-back attention launches on a 16-bit two-stream qkv buffer
  * [(B*Ft + B*Qt), 3*H*hd] -> out16 [(B*Ft + B*Qt), H*hd]; version 1 = warp-MMA kernel, 2 = tcgen05 kernel (where supported). */

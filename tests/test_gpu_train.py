@@ -1,0 +1,305 @@
+"""Parity tests of the TRAINING leg (need a B200): backward kernels and the whole forward + backward through the C ABI against
+ (1) the kernel-boundary oracles (oracle/kernel_oracles.py) for the weight-gradient GEMM and the attention backward,
+ (2) the gradient fingerprints tests/golden/grads.npz minted from torch.autograd over the UNMODIFIED reference (float64),
+ (3) the numpy reverse-mode oracle (oracle/tim_oracle_bwd.py, itself pinned to (2) to 1e-9) on every gradient tensor in full,
+ (4) the autograd drop-in (patch_model in train() mode: loss.backward(), optimizer.zero_grad(), parameter updates).
+
+Tolerances (rel-L2 per gradient tensor, dropout 0):  fp32 path <= 2e-5,  fp16 path <= 1e-3 (2e-3 where noted),  bf16 <= 2e-2.
+Reference: recognition/scripts/train.py:190-260, 354-366; detection/time_interval_machine/models/tim.py:272-337.
+"""
+import ctypes as C
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from tim_b200.config import TIMConfig, named_config          # noqa: E402
+from tim_b200.synth import rel_l2, synth_inputs, synth_state_dict   # noqa: E402
+from tests.test_oracle_golden import GOLD, MANIFEST   # noqa: E402
+
+DT = {"fp32": 0, "bf16": 1, "fp16": 2}
+GTOL = {"fp32": 2e-5, "fp16": 1e-3, "bf16": 2e-2}
+GRAD_CASES = [str(n) for n in np.load(os.path.join(GOLD, "grads.npz"))["cases"]]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU test selected but no CUDA device is visible")
+    from tim_b200 import _lib
+    return _lib.load()
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _round(x, dt):
+    if dt == "fp32":
+        return x
+    t = torch.from_numpy(x)
+    return t.to(torch.float16 if dt == "fp16" else torch.bfloat16).to(torch.float32).numpy()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# kernel boundary
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", ["fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("M,N,K,splits", [(64, 256, 256, 0), (1000, 3072, 1024, 0), (333, 97, 1024, 0), (5000, 1024, 2048, 3), (130, 44, 48, 1),
+                                          (4096, 512, 2304, 0), (77, 3806, 64, 0), (20000, 256, 512, 0)])
+def test_wgrad_kernel(lib, M, N, K, splits, dt):
+    """dW += dY^T X (gemm_wgrad.cu: MN-major tcgen05 operands, split over token rows, TMA reduce-add) against float64 on the
+    operands as the kernel sees them (rounded to the operand type); accumulation into a non-zero dW; ragged N / K / M."""
+    from tim_b200 import _lib
+    rng = np.random.default_rng(M * 31 + N + K)
+    dy = rng.standard_normal((M, N)).astype(np.float32)
+    x = rng.standard_normal((M, K)).astype(np.float32)
+    w0 = rng.standard_normal((N, K)).astype(np.float32)
+    dev = torch.device("cuda", 0)
+    dW = torch.from_numpy(w0.copy()).to(dev)
+    tdy, tx = torch.from_numpy(dy).to(dev), torch.from_numpy(x).to(dev)
+    _lib.check(lib.tim_test_wgrad(DT[dt], _ptr(tdy), _ptr(tx), _ptr(dW), M, N, K, splits, None))
+    ref = w0.astype(np.float64) + _round(dy, dt).astype(np.float64).T @ _round(x, dt).astype(np.float64)
+    e = rel_l2(dW.cpu().numpy(), ref)
+    assert e <= 3e-6, f"wgrad {M}x{N}x{K} [{dt}]: rel-L2 {e:.3e}"
+
+
+ATT_SHAPES = [(2, 12, 7, 2, 16), (3, 100, 100, 2, 128), (2, 128, 200, 1, 192), (2, 100, 0, 2, 64), (1, 50, 130, 4, 32), (2, 33, 65, 3, 64),
+              (1, 100, 300, 2, 128)]
+
+
+@pytest.mark.parametrize("dt", ["fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("B,Ft,Qt,H,hd", ATT_SHAPES)
+def test_attention_bwd_kernel(lib, B, Ft, Qt, H, hd, dt):
+    """attention_bwd.cu against oracle/kernel_oracles.attention_bwd_two_stream (float64, itself checked against the reference's dense
+    masked softmax under torch.autograd to 1e-12): dq (w.r.t. the stored q), dk, dv separately."""
+    from oracle.kernel_oracles import LN2, attention_bwd_two_stream
+    from tim_b200 import _lib
+    rng = np.random.default_rng(B * 1000 + Ft * 10 + Qt + hd)
+    E = H * hd
+    M = B * (Ft + Qt)
+    qkv = rng.standard_normal((M, 3 * E)).astype(np.float32)
+    qkv[:, :E] *= np.float32(hd ** -0.5 * 1.4426950408889634)          # what the packed in_proj weights do
+    dout = rng.standard_normal((M, E)).astype(np.float32)
+    dev = torch.device("cuda", 0)
+    out = torch.zeros((M, 3 * E), dtype=torch.float32, device=dev)
+    tq, td = torch.from_numpy(qkv).to(dev), torch.from_numpy(dout).to(dev)
+    _lib.check(lib.tim_test_attention_bwd(DT[dt], _ptr(tq), _ptr(td), _ptr(out), B, Ft, Qt, H, hd, float(LN2), None))
+    ref = attention_bwd_two_stream(_round(qkv, dt).astype(np.float64), _round(dout, dt).astype(np.float64), B, Ft, Qt, H, hd)
+    got = out.cpu().numpy()
+    tol = {"fp32": 1e-5, "fp16": 2e-3, "bf16": 1.5e-2}[dt]
+    for name, lo in (("dq", 0), ("dk", E), ("dv", 2 * E)):
+        e = rel_l2(got[:, lo:lo + E], ref[:, lo:lo + E])
+        assert e <= tol, f"{name} B={B} Ft={Ft} Qt={Qt} H={H} hd={hd} [{dt}]: rel-L2 {e:.3e}"
+    # rows of query tokens: their k / v columns carry only the own-key / own-value terms; feature rows of different clips are independent
+    assert np.isfinite(got).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# whole forward + backward through the C ABI
+# ---------------------------------------------------------------------------------------------------------------------
+def cotangents(name, shapes):
+    return {k: np.random.default_rng(zlib.crc32(f"{name}/{k}".encode())).standard_normal(tuple(shp)) for k, shp in shapes.items()}
+
+
+def engine_grads(cfg, sd, inp, Qv, Qa, dt, cot_fn, repeat=1):
+    """time_mlp + encoder forward in training mode, backward with the given cotangents -> (outputs, {key: gradient})."""
+    from tim_b200.plugin import TIMEngine
+    dev = torch.device("cuda", 0)
+    eng = TIMEngine(cfg, 0, dt)
+    eng.enable_training()
+    eng.load_state_dict(sd)
+    grads = {k: torch.zeros(tuple(np.shape(sd[k])), dtype=torch.float32, device=dev) for k in eng._keys}
+    for k, g in grads.items():
+        eng.bind_grad(k, g)
+    vis = torch.from_numpy(inp["vis"]).to(dev) if "vis" in inp else None
+    aud = torch.from_numpy(inp["aud"]).to(dev) if "aud" in inp else None
+    times = torch.from_numpy(inp["times"]).to(dev)
+    for _ in range(repeat):
+        te = eng.time_mlp_train(times)
+        out = eng.encoder_train(vis, aud, te, Qv, Qa)
+        cot = cot_fn({k: tuple(v.shape) for k, v in out.items() if v is not None})
+        d_te = eng.encoder_bwd({k: torch.from_numpy(np.asarray(v, np.float32)).to(dev) for k, v in cot.items()})
+        eng.time_mlp_bwd(d_te)
+    torch.cuda.synchronize()
+    res = {k: (v.cpu().numpy() if v is not None else None) for k, v in out.items()}
+    res["time_encodings"] = te.cpu().numpy()
+    gr = {k: v.cpu().numpy() for k, v in grads.items()}
+    assert eng.tape_bytes > 0
+    eng.close()
+    return res, gr
+
+
+@pytest.mark.parametrize("dt", ["fp32", "fp16", "bf16"])
+@pytest.mark.parametrize("name", GRAD_CASES)
+def test_gradients_vs_reference_autograd_golden(lib, name, dt):
+    """Every parameter gradient of the CUDA training leg against the fingerprints of torch.autograd over the unmodified reference
+    (tests/golden/grads.npz: 512 sampled entries + L2 norm per tensor, float64)."""
+    g = np.load(os.path.join(GOLD, "grads.npz"))
+    case = MANIFEST[name]
+    cfg = TIMConfig(**case["cfg"])
+    sd = synth_state_dict(cfg, case["weight_seed"], case["style"])
+    inp = synth_inputs(cfg, case["B"], case["Qv"], case["Qa"], case["input_seed"], shared_queries=case["shared_queries"])
+    shapes = {key.rsplit("/", 1)[1]: tuple(g[key]) for key in g.files if key.startswith(f"{name}/out_shape/")}
+
+    def cot_fn(out_shapes):
+        for k, shp in out_shapes.items():
+            assert tuple(shapes[k]) == tuple(shp), (k, shapes[k], shp)
+        return cotangents(name, shapes)
+
+    _, grads = engine_grads(cfg, sd, inp, case["Qv"], case["Qa"], dt, cot_fn)
+    want = [str(k) for k in g[f"{name}/keys"] if not str(k).startswith("input.")]
+    tol = GTOL[dt] * (1.0 if name == "recog_cfg1" or dt == "fp32" else 2.0)      # tiny widths: few terms per sum, looser in 16 bits
+    worst = ("", 0.0)
+    for k in want:
+        flat = grads[k].astype(np.float64).reshape(-1)
+        idx = np.sort(np.random.default_rng(zlib.crc32(f"idx/{name}/{k}".encode())).choice(flat.size, size=min(512, flat.size), replace=False))
+        vals = g[f"{name}/vals/{k}"]
+        norm = float(g[f"{name}/stat/{k}"][0])
+        # sampled entries against the tensor's RMS (a fingerprint has no full tensor to take the norm of the difference over)
+        rms = norm / np.sqrt(flat.size)
+        e = float(np.sqrt(np.mean((flat[idx] - vals) ** 2))) / max(rms, 1e-30)
+        en = abs(float(np.linalg.norm(flat)) - norm) / max(norm, 1e-30)
+        if e > worst[1]:
+            worst = (k, e)
+        assert e <= tol and en <= tol, f"{name}/{k} [{dt}]: sampled rel error {e:.3e}, norm error {en:.3e} > {tol:.0e}"
+    for k in [str(x) for x in g[f"{name}/no_grad"]]:
+        if k in grads:
+            assert not grads[k].any(), f"{name}/{k}: autograd leaves this parameter without gradient"
+    print(f"[grads] {name} [{dt}]: worst {worst[0]} {worst[1]:.2e}")
+
+
+@pytest.mark.parametrize("dt", ["fp32", "fp16"])
+@pytest.mark.parametrize("name", ["recog_av_small", "recog_av_qa0", "det_av", "det_visual_vn", "recog_hd192"])
+def test_gradients_vs_oracle_full_tensors(lib, name, dt):
+    """Full gradient tensors (rel-L2 over the whole tensor) and the time-encoding path against the numpy reverse-mode oracle, plus
+    accumulation: two identical forward / backward passes double every gradient."""
+    from oracle.tim_oracle_bwd import TIMOracleGrad
+    case = MANIFEST[name]
+    cfg = TIMConfig(**case["cfg"])
+    sd = synth_state_dict(cfg, case["weight_seed"], case["style"])
+    inp = synth_inputs(cfg, case["B"], case["Qv"], case["Qa"], case["input_seed"], shared_queries=case["shared_queries"])
+    holder = {}
+
+    def cot_fn(out_shapes):
+        holder["cot"] = cotangents(name, out_shapes)
+        return holder["cot"]
+
+    res, g1 = engine_grads(cfg, sd, inp, case["Qv"], case["Qa"], dt, cot_fn)
+    out_ref, gref = TIMOracleGrad(cfg, sd, np.float64).forward_backward(inp.get("vis"), inp.get("aud"), inp["times"], case["Qv"], case["Qa"],
+                                                                       holder["cot"])
+    ftol = {"fp32": 1e-5, "fp16": 3e-3}[dt]
+    for k, v in out_ref.items():
+        if v is not None and res.get(k) is not None:
+            assert rel_l2(res[k], v) <= ftol, (k, rel_l2(res[k], v))
+    tol = GTOL[dt] * (1.0 if dt == "fp32" else 2.0)
+    for k, ref in gref.items():
+        if k.startswith("input."):
+            continue
+        e = rel_l2(g1[k].reshape(-1), np.asarray(ref).reshape(-1))
+        assert e <= tol, f"{name}/{k} [{dt}]: rel-L2 {e:.3e} > {tol:.0e}"
+    _, g2 = engine_grads(cfg, sd, inp, case["Qv"], case["Qa"], dt, cot_fn, repeat=2)
+    for k in gref:
+        if not k.startswith("input."):
+            assert rel_l2(g2[k], 2.0 * g1[k]) <= 1e-5, k
+
+
+@pytest.mark.parametrize("name,B", [("cfg2", 2), ("cfg3", 1)])
+def test_gradients_named_configs_fp16_vs_fp32_path(lib, name, B):
+    """BASELINE.json configs at their real widths: the fp16 tensor-core training leg against the library's own fp32 CUDA-core leg
+    (which the tests above hold to 2e-5 of the reference's autograd) on the same seeded inputs and cotangents."""
+    cfg, Qv, Qa = named_config(name)
+    sd = synth_state_dict(cfg, 0, "trained")
+    inp = synth_inputs(cfg, B, Qv, Qa, 1234 + 10 * int(name[-1]))
+
+    def cot_fn(out_shapes):
+        return cotangents(name, out_shapes)
+
+    _, g32 = engine_grads(cfg, sd, inp, Qv, Qa, "fp32", cot_fn)
+    _, g16 = engine_grads(cfg, sd, inp, Qv, Qa, "fp16", cot_fn)
+    worst = max((rel_l2(g16[k], g32[k]), k) for k in g32)
+    print(f"[grads] {name}: worst fp16 vs fp32 {worst[1]} {worst[0]:.2e}")
+    assert worst[0] <= 2e-3, worst
+
+
+def test_patch_model_training_dropin(lib):
+    """The autograd drop-in: a module with the reference's parameter tree in train() mode -> loss.backward() fills param.grad (views
+    of one flat buffer), optimizer.zero_grad() (set_to_none) between steps is survived, an optimizer step is picked up by the next
+    forward, non-zero dropout is refused."""
+    from oracle.tim_oracle_bwd import TIMOracleGrad
+    from tests._fake_tim import FakeTIM
+    from tim_b200.plugin import patch_model
+    name = "recog_av_small"
+    case = MANIFEST[name]
+    cfg = TIMConfig(**case["cfg"])
+    sd = synth_state_dict(cfg, case["weight_seed"], case["style"])
+    Qv, Qa = case["Qv"], case["Qa"]
+    inp = synth_inputs(cfg, case["B"], Qv, Qa, case["input_seed"])
+    dev = torch.device("cuda", 0)
+    model = patch_model(FakeTIM(cfg, sd).to(dev).train(), compute_dtype="fp32")
+    opt = torch.optim.SGD(model.parameters(), lr=0.05)
+    vis, aud, times = (torch.from_numpy(inp[k]).to(dev) for k in ("vis", "aud", "times"))
+    sd_now = {k: np.array(v, copy=True) for k, v in sd.items()}
+    for step in range(2):
+        opt.zero_grad()                                             # set_to_none=True: the flat views must be re-attached
+        te = model(times, "time_mlp")
+        (verb, noun, action, audio), feats = model([vis, aud], "encoder", te, Qv, Qa)
+        outs = dict(verb=verb, noun=noun, action=action, audio=audio, feats=feats)
+        cot = cotangents(name, {k: tuple(v.shape) for k, v in outs.items() if v is not None})
+        loss = sum((v * torch.from_numpy(cot[k].astype(np.float32)).to(dev)).sum() for k, v in outs.items() if v is not None)
+        loss.backward()
+        _, gref = TIMOracleGrad(cfg, sd_now, np.float64).forward_backward(inp["vis"], inp["aud"], inp["times"], Qv, Qa, cot)
+        params = dict(model.named_parameters())
+        flat = model._tim_b200.flat
+        for k, ref in gref.items():
+            if k.startswith("input."):
+                continue
+            p = params[k]
+            assert p.grad is not None and p.grad.data_ptr() == flat.view(k).data_ptr(), k
+            assert rel_l2(p.grad.cpu().numpy().reshape(-1), np.asarray(ref).reshape(-1)) <= 2e-5, (step, k)
+        opt.step()
+        for k in sd_now:
+            if k in params:
+                sd_now[k] = params[k].detach().cpu().numpy().copy()
+    # eval-mode forward after training uses the updated weights
+    model.eval()
+    with torch.no_grad():
+        te = model(times, "time_mlp")
+        (_, _, action, _), _ = model([vis, aud], "encoder", te, Qv, Qa)
+    from oracle.tim_oracle import TIMOracle
+    ref = TIMOracle(cfg, sd_now, np.float32).forward(inp["vis"], inp["aud"], inp["times"], Qv, Qa)
+    assert rel_l2(action.cpu().numpy(), ref["action"]) <= 1e-5
+    # dropout is not implemented: a module that would apply it is refused, not silently run without it
+    m2 = FakeTIM(cfg, sd).to(dev)
+    m2.add_module("some_dropout", torch.nn.Dropout(0.1))
+    m2 = patch_model(m2.train(), compute_dtype="fp32")
+    with pytest.raises(NotImplementedError):
+        m2(times, "time_mlp")
+
+
+def test_training_errors_are_loud(lib):
+    from tim_b200 import _lib
+    from tim_b200.plugin import TIMEngine
+    cfg, Qv, Qa = named_config("cfg1")
+    sd = synth_state_dict(cfg, 0, "trained")
+    inp = synth_inputs(cfg, 2, Qv, Qa, 5)
+    dev = torch.device("cuda", 0)
+    eng = TIMEngine(cfg, 0, "fp16")
+    eng.load_state_dict(sd)
+    times = torch.from_numpy(inp["times"]).to(dev)
+    with pytest.raises(_lib.TimError):                       # training not enabled
+        eng.time_mlp_train(times)
+    eng.enable_training()
+    with pytest.raises(_lib.TimError):                       # weights not re-set after enabling (transposed copies missing)
+        eng.time_mlp_train(times)
+    eng.load_state_dict(sd)
+    te = eng.time_mlp_train(times)
+    with pytest.raises(_lib.TimError):                       # no gradient destination bound
+        eng.time_mlp_bwd(torch.ones_like(te))
+    with pytest.raises(_lib.TimError):                       # backward without forward
+        eng.encoder_bwd.__func__(eng, {}) if False else _lib.check(eng.lib.tim_encoder_bwd(eng._ctx, C.byref(_lib.tim_outputs()), None, None), eng._ctx)
+    eng.close()

@@ -10,7 +10,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtim_b200.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 TIM_OK = 0
 STATUS_NAMES = {0: "TIM_OK", -1: "TIM_ERR_INVALID", -2: "TIM_ERR_CUDA", -3: "TIM_ERR_NO_DEVICE",
@@ -74,6 +74,22 @@ SYMBOLS = {
                                       C.POINTER(C.c_float)]),
     "tim_test_attention": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p]),
+    "tim_train_enable": (C.c_int, [C.c_void_p]),
+    "tim_bind_grad": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p]),
+    "tim_time_mlp_fwd_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "tim_time_mlp_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tim_encoder_fwd_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.POINTER(tim_outputs), C.c_void_p]),
+    "tim_encoder_bwd": (C.c_int, [C.c_void_p, C.POINTER(tim_outputs), C.c_void_p, C.c_void_p]),
+    "tim_train_tape_bytes": (C.c_size_t, [C.c_void_p]),
+    "tim_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "tim_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "tim_allreduce_grads": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tim_test_wgrad": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "tim_bench_wgrad": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.POINTER(C.c_float)]),
+    "tim_test_attention_bwd": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_float, C.c_void_p]),
 }
 
 _lib = None

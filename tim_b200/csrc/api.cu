@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 #include <map>
 #include <string>
 #include <type_traits>
@@ -44,6 +45,13 @@ struct LinearW {
     float* cs = nullptr;        // [N]
     float* bwf = nullptr;       // [N]
     CUtensorMap tmB2f;          // CTA-pair map of wf
+    // training leg: transposed copy [K, Np] (Np = N rounded up to 8, zero-padded; unscaled) = the K-major "weight" of the dgrad GEMM
+    void* wt = nullptr;
+    int Np = 0;
+    CUtensorMap tmBt, tmBt2;
+    bool has_tmBt2 = false;
+    int block_n_t = 0;
+    bool wt_set = false;
 };
 
 struct Slot {                   // one state_dict key
@@ -73,8 +81,14 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 }  // namespace
 
+struct tim_train_state;
+struct ncclUniqueIdBlob { char internal[128]; };
+
 struct tim_ctx {
     tim_config cfg;
+    tim_train_state* train = nullptr;   // training leg (train.inl); allocated by tim_train_enable
+    int class_override = -1;            // profiling class forced onto run_linear launches (dgrad GEMMs)
+    int wgrad_splits = 0;               // 0: chosen per shape (TIM_B200_WGRAD_SPLITS overrides)
     int device = 0, num_sms = 0;
     int d = 0, E = 0, FF = 0, H = 0, hd = 0, L = 0, F = 0, Fv = 0, Fa = 0, Ft = 0;
     bool vis_data = false, aud_data = false, vn_tokens = false;
@@ -154,7 +168,8 @@ cudaEvent_t prof_event(tim_ctx* c) {
     do {                                                                                                   \
         tim_ctx::ProfRec _pr;                                                                              \
         const bool _prof = (ctx)->profiling;                                                               \
-        if (_prof) { _pr.a = prof_event(ctx); _pr.b = prof_event(ctx); _pr.cls = (cls_); _pr.flops = (flops_); \
+        if (_prof) { _pr.a = prof_event(ctx); _pr.b = prof_event(ctx);                                     \
+                     _pr.cls = ((ctx)->class_override >= 0 && (cls_) != 2) ? (ctx)->class_override : (cls_); _pr.flops = (flops_); \
                      cudaEventRecord(_pr.a, (stream_)); }                                                  \
         cudaError_t _e = (expr);                                                                           \
         (ctx)->launches++;                                                                                 \
@@ -840,6 +855,8 @@ int encoder_ws(tim_ctx* c, int B, int T_, int Qv, int Qa, size_t* need, bool ind
 
 }  // namespace
 
+#include "train.inl"
+
 // ======================================================================================================================
 // extern "C"
 // ======================================================================================================================
@@ -897,6 +914,7 @@ int tim_create(tim_ctx** out, const tim_config* cfg, int device) {
     c->esize = g.compute_dtype == TIM_FP32 ? 4 : 2;
     if (const char* gv = std::getenv("TIM_B200_GEMM")) c->gemm_version = std::atoi(gv) == 1 ? 1 : 2;
     if (const char* av = std::getenv("TIM_B200_ATTN")) c->attn_version = std::atoi(av) == 1 ? 1 : 2;
+    if (const char* wv = std::getenv("TIM_B200_WGRAD_SPLITS")) c->wgrad_splits = std::atoi(wv);
     if (c->d % 4) return bail(c->fail(TIM_ERR_INVALID, "d_model must be a multiple of 4"));
     if (c->vis_data && !g.n_action) return bail(c->fail(TIM_ERR_INVALID, "visual data modality needs n_action > 0"));
     if (c->aud_data && !g.n_audio) return bail(c->fail(TIM_ERR_INVALID, "audio data modality needs n_audio > 0"));
@@ -926,6 +944,12 @@ void tim_destroy(tim_ctx* c) {
     for (void* p : c->allocs) cudaFree(p);
     if (c->ws) cudaFree(c->ws);
     if (c->fold_alarm_host) cudaFreeHost(const_cast<int*>(c->fold_alarm_host));
+    if (c->train) {
+        if (c->train->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->train->nccl_comm);
+        if (c->train->mem) cudaFree(c->train->mem);
+        if (c->train->tmem) cudaFree(c->train->tmem);
+        delete c->train;
+    }
     if (c->io) cudaFree(c->io);
     for (auto& r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -965,6 +989,14 @@ int tim_set_weight(tim_ctx* c, const char* key, const float* data, const int64_t
             case TIM_FP16: LAUNCH(c, launch_cast<__half>(data, static_cast<__half*>(w.w), w.N, w.K, w.scale_rows, w.scale, s)); break;
         }
         if (w.foldable) CU_OK(c, cudaMemcpyAsync(w.w32, data, static_cast<size_t>(w.N) * w.K * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        if (w.wt) {
+            switch (c->cfg.compute_dtype) {
+                case TIM_FP32: LAUNCH(c, launch_transpose_pack<float>(data, static_cast<float*>(w.wt), w.N, w.K, w.Np, s)); break;
+                case TIM_BF16: LAUNCH(c, launch_transpose_pack<__nv_bfloat16>(data, static_cast<__nv_bfloat16*>(w.wt), w.N, w.K, w.Np, s)); break;
+                case TIM_FP16: LAUNCH(c, launch_transpose_pack<__half>(data, static_cast<__half*>(w.wt), w.N, w.K, w.Np, s)); break;
+            }
+            w.wt_set = true;
+        }
     }
     c->fold_dirty = true;
     sl.set = true;
@@ -1188,6 +1220,128 @@ int tim_forward_host(tim_ctx* c, const float* vis, const float* aud, const float
         return c->fail(TIM_ERR_CUDA, "tim_forward_host: stream sync failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
     if (h2d_bytes) *h2d_bytes = up;
     if (d2h_bytes) *d2h_bytes = down;
+    return TIM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------- training leg
+int tim_train_enable(tim_ctx* c) {
+    if (!c) return TIM_ERR_INVALID;
+    if (c->train && c->train->enabled) return TIM_OK;
+    CU_OK(c, cudaSetDevice(c->device));
+    if (!c->train) c->train = new tim_train_state();
+    tim_train_state& tr = *c->train;
+    const bool f32 = c->cfg.compute_dtype == TIM_FP32;
+    int maxn = 8;
+    for (auto& kv : c->slots) {
+        Slot& sl = kv.second;
+        if (sl.kind == Slot::VEC) { tr.names[sl.vec] = kv.first; continue; }
+        LinearW& w = *sl.lin;
+        if (sl.kind == Slot::LIN_B) { tr.names[w.bias] = kv.first; continue; }
+        tr.names[w.w] = kv.first;
+        if (w.N > maxn) maxn = w.N;
+        if (w.K > maxn) maxn = w.K;
+        if (w.wt) continue;
+        w.Np = f32 ? w.N : ((w.N + 7) & ~7);
+        TIM_TRY(dev_alloc(c, &w.wt, static_cast<size_t>(w.K) * w.Np * c->esize));
+        CU_OK(c, cudaMemset(w.wt, 0, static_cast<size_t>(w.K) * w.Np * c->esize));
+        w.wt_set = false;
+        if (!f32) {
+            LinearW v;
+            v.N = w.K; v.K = w.Np; v.w = w.wt;
+            TIM_TRY(make_tmap_w(c, v));
+            w.tmBt = v.tmB; w.tmBt2 = v.tmB2; w.has_tmBt2 = v.has_tmB2; w.block_n_t = v.block_n;
+        }
+    }
+    TIM_TRY(dev_alloc(c, reinterpret_cast<void**>(&tr.zero_bias), static_cast<size_t>(maxn) * sizeof(float)));
+    CU_OK(c, cudaMemset(tr.zero_bias, 0, static_cast<size_t>(maxn) * sizeof(float)));
+    tr.zero_bias_n = maxn;
+    tr.enabled = true;
+    return TIM_OK;
+}
+
+int tim_bind_grad(tim_ctx* c, const char* key, float* dst) {
+    if (!c || !key) return TIM_ERR_INVALID;
+    if (!c->train || !c->train->enabled) return c->fail(TIM_ERR_INVALID, "tim_bind_grad: call tim_train_enable first");
+    if (!std::strncmp(key, "drloc_mlp.", 10) || !std::strncmp(key, "pool.", 5)) return TIM_OK;
+    auto it = c->slots.find(key);
+    if (it == c->slots.end()) return c->fail(TIM_ERR_WEIGHTS, "unknown state_dict key '%s' for this configuration", key);
+    if (dst && (reinterpret_cast<uintptr_t>(dst) & 15)) return c->fail(TIM_ERR_INVALID, "gradient destination of '%s' is not 16-byte aligned", key);
+    Slot& sl = it->second;
+    const void* p = sl.kind == Slot::VEC ? static_cast<const void*>(sl.vec) : (sl.kind == Slot::LIN_W ? sl.lin->w : static_cast<const void*>(sl.lin->bias));
+    c->train->grads[p] = dst;
+    return TIM_OK;
+}
+
+int tim_time_mlp_fwd_train(tim_ctx* c, const float* times, float* out, int B, int T_, void* stream) {
+    if (!c) return TIM_ERR_INVALID;
+    if (!times || !out || B <= 0 || T_ <= 0) return c->fail(TIM_ERR_INVALID, "tim_time_mlp_fwd_train: bad arguments");
+    TIM_TRY(train_ready(c));
+    CU_OK(c, cudaSetDevice(c->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return dispatch_dtype(c, [&](auto tag) { return time_mlp_train_fwd<decltype(tag)>(c, times, out, B, T_, s); });
+}
+
+int tim_time_mlp_bwd(tim_ctx* c, const float* d_out, void* stream) {
+    if (!c) return TIM_ERR_INVALID;
+    if (!d_out) return c->fail(TIM_ERR_INVALID, "tim_time_mlp_bwd: bad arguments");
+    TIM_TRY(train_ready(c));
+    CU_OK(c, cudaSetDevice(c->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return dispatch_dtype(c, [&](auto tag) { return time_mlp_train_bwd<decltype(tag)>(c, d_out, s); });
+}
+
+int tim_encoder_fwd_train(tim_ctx* c, const float* vis, const float* aud, const float* te, int B, int T_, int Qv, int Qa,
+                          const tim_outputs* outs, void* stream) {
+    if (!c) return TIM_ERR_INVALID;
+    if (!te || !outs || B <= 0 || T_ <= 0) return c->fail(TIM_ERR_INVALID, "tim_encoder_fwd_train: bad arguments");
+    TIM_TRY(train_ready(c));
+    CU_OK(c, cudaSetDevice(c->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return dispatch_dtype(c, [&](auto tag) { return encoder_train_fwd<decltype(tag)>(c, vis, aud, te, B, T_, Qv, Qa, outs, s); });
+}
+
+int tim_encoder_bwd(tim_ctx* c, const tim_outputs* grad_outs, float* d_time_enc, void* stream) {
+    if (!c) return TIM_ERR_INVALID;
+    if (!grad_outs) return c->fail(TIM_ERR_INVALID, "tim_encoder_bwd: bad arguments");
+    TIM_TRY(train_ready(c));
+    CU_OK(c, cudaSetDevice(c->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    return dispatch_dtype(c, [&](auto tag) { return encoder_train_bwd<decltype(tag)>(c, grad_outs, d_time_enc, s); });
+}
+
+size_t tim_train_tape_bytes(const tim_ctx* c) { return (c && c->train) ? c->train->mem_bytes + c->train->tmem_bytes : 0; }
+
+int tim_comm_unique_id(void* out128) {
+    if (!out128) return TIM_ERR_INVALID;
+    if (const char* e = load_nccl()) { g_create_error = e; return TIM_ERR_INVALID; }
+    const int r = g_nccl.GetUniqueId(out128);
+    if (r != 0) { g_create_error = std::string("ncclGetUniqueId failed: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?"); return TIM_ERR_CUDA; }
+    return TIM_OK;
+}
+
+int tim_comm_init(tim_ctx* c, const void* id128, int rank, int world) {
+    if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return TIM_ERR_INVALID;
+    if (!c->train) c->train = new tim_train_state();
+    if (const char* e = load_nccl()) return c->fail(TIM_ERR_INVALID, "%s", e);
+    CU_OK(c, cudaSetDevice(c->device));
+    if (c->train->nccl_comm) { g_nccl.CommDestroy(c->train->nccl_comm); c->train->nccl_comm = nullptr; }
+    ncclUniqueIdBlob id;
+    std::memcpy(&id, id128, sizeof(id));
+    const int r = g_nccl.CommInitRank(&c->train->nccl_comm, world, id, rank);
+    if (r != 0) return c->fail(TIM_ERR_CUDA, "ncclCommInitRank failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    c->train->world = world;
+    return TIM_OK;
+}
+
+int tim_allreduce_grads(tim_ctx* c, float* buf, size_t n, void* stream) {
+    if (!c) return TIM_ERR_INVALID;
+    if (!buf || !n) return c->fail(TIM_ERR_INVALID, "tim_allreduce_grads: bad arguments");
+    if (!c->train || !c->train->nccl_comm) return c->fail(TIM_ERR_INVALID, "tim_allreduce_grads: no communicator (tim_comm_init)");
+    CU_OK(c, cudaSetDevice(c->device));
+    // one collective over the flat buffer, averaged over the ranks (what DDP does bucket by bucket, models/build.py:58-63)
+    const int r = g_nccl.AllReduce(buf, buf, n, /*ncclFloat32*/ 7, /*ncclAvg*/ 4, c->train->nccl_comm, static_cast<cudaStream_t>(stream));
+    if (r != 0) return c->fail(TIM_ERR_CUDA, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?");
+    c->launches++;
     return TIM_OK;
 }
 
@@ -1444,6 +1598,130 @@ int tim_test_attention(int dtype, const float* qkv, float* out, int B, int Ft, i
     if (e != cudaSuccess) return fin(c->fail(TIM_ERR_CUDA, "tim_test_attention: %s", cudaGetErrorString(e)));
     e = cudaStreamSynchronize(s);
     if (e != cudaSuccess) return fin(c->fail(TIM_ERR_CUDA, "tim_test_attention: %s", cudaGetErrorString(e)));
+    return TIM_OK;
+}
+
+// dW[N, K] (fp32, accumulated into) += dY[M, N]^T X[M, K] through the selected compute path (16-bit paths cast dY and X on the device
+// first; N is padded to a multiple of 8 columns for the TMA pitch). splits <= 0: chosen by the library.
+int tim_test_wgrad(int dtype, const float* dY, const float* X, float* dW, int M, int N, int K, int splits, void* stream) {
+    TmpCtx t;
+    tim_ctx* c = &t.c;
+    auto fin = [&](int r) { g_create_error = c->err; return r; };
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
+        g_create_error = "tim_test_wgrad: no sm_100 device";
+        return TIM_ERR_NO_DEVICE;
+    }
+    c->num_sms = prop.multiProcessorCount; c->device = dev; c->cfg.compute_dtype = dtype; c->esize = dtype == TIM_FP32 ? 4 : 2;
+    c->wgrad_splits = splits;
+    int r;
+    if (dtype == TIM_FP32) {
+        r = run_wgrad<float>(c, dY, N, X, K, dW, K, M, N, K, s);
+    } else {
+        r = get_encode_fn(c);
+        if (r) return fin(r);
+        const int Np = (N + 7) & ~7, Kp = (K + 7) & ~7;
+        void *y16 = nullptr, *x16 = nullptr;
+        if (t.alloc(&y16, static_cast<size_t>(M) * Np * 2) != cudaSuccess || t.alloc(&x16, static_cast<size_t>(M) * Kp * 2) != cudaSuccess)
+            return fin(c->fail(TIM_ERR_NOMEM, "alloc"));
+        if (dtype == TIM_BF16) {
+            launch_cast_pad<__nv_bfloat16>(dY, static_cast<__nv_bfloat16*>(y16), M, N, Np, s);
+            launch_cast_pad<__nv_bfloat16>(X, static_cast<__nv_bfloat16*>(x16), M, K, Kp, s);
+            r = run_wgrad<__nv_bfloat16>(c, y16, Np, x16, Kp, dW, K, M, N, K, s);
+        } else {
+            launch_cast_pad<__half>(dY, static_cast<__half*>(y16), M, N, Np, s);
+            launch_cast_pad<__half>(X, static_cast<__half*>(x16), M, K, Kp, s);
+            r = run_wgrad<__half>(c, y16, Np, x16, Kp, dW, K, M, N, K, s);
+        }
+    }
+    if (r) return fin(r);
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return fin(c->fail(TIM_ERR_CUDA, "tim_test_wgrad: %s", cudaGetErrorString(e)));
+    return TIM_OK;
+}
+
+// timing hook (tools/wgrad_bench.py): `iters` back-to-back weight-gradient launches on 16-bit device operands
+int tim_bench_wgrad(int dtype, const void* dY16, const void* X16, float* dW, int M, int N, int K, int splits, int iters, float* ms_per_iter) {
+    TmpCtx t;
+    tim_ctx* c = &t.c;
+    auto fin = [&](int r) { g_create_error = c->err; return r; };
+    int dev = 0;
+    cudaDeviceProp prop;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
+        g_create_error = "tim_bench_wgrad: no sm_100 device";
+        return TIM_ERR_NO_DEVICE;
+    }
+    if (dtype != TIM_BF16 && dtype != TIM_FP16) return fin(c->fail(TIM_ERR_INVALID, "tim_bench_wgrad: 16-bit dtypes only"));
+    c->num_sms = prop.multiProcessorCount; c->device = dev; c->cfg.compute_dtype = dtype; c->esize = 2; c->wgrad_splits = splits;
+    int r = get_encode_fn(c);
+    if (r) return fin(r);
+    cudaStream_t s = nullptr;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < iters + 2 && r == TIM_OK; ++i) {
+        if (i == 2) cudaEventRecord(e0, s);
+        r = dtype == TIM_BF16 ? run_wgrad<__nv_bfloat16>(c, dY16, N, X16, K, dW, K, M, N, K, s) : run_wgrad<__half>(c, dY16, N, X16, K, dW, K, M, N, K, s);
+    }
+    cudaEventRecord(e1, s);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (r) return fin(r);
+    if (e != cudaSuccess) return fin(c->fail(TIM_ERR_CUDA, "tim_bench_wgrad: %s", cudaGetErrorString(e)));
+    if (ms_per_iter) *ms_per_iter = ms / (iters > 0 ? iters : 1);
+    return TIM_OK;
+}
+
+// attention backward over a two-stream qkv buffer: qkv [(B*Ft + B*Qt), 3*H*hd], dO [.., H*hd] -> dqkv [.., 3*H*hd], all fp32 on the
+// device (16-bit paths cast on the device, run the mma kernels and widen the result on the host). qscale: see attention_bwd.cu.
+int tim_test_attention_bwd(int dtype, const float* qkv, const float* dO, float* dqkv, int B, int Ft, int Qt, int H, int hd, float qscale,
+                           void* stream) {
+    TmpCtx t;
+    tim_ctx* c = &t.c;
+    auto fin = [&](int r) { g_create_error = c->err; return r; };
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t M = static_cast<size_t>(B) * (Ft + Qt), E = static_cast<size_t>(H) * hd;
+    cudaError_t e = cudaSuccess;
+    if (dtype == TIM_FP32) {
+        e = cudaMemsetAsync(dqkv, 0, M * 3 * E * sizeof(float), s);
+        if (e == cudaSuccess) e = launch_attention_bwd_simt(qkv, dO, dqkv, B, Ft, Qt, H, hd, qscale, s);
+    } else {
+        void *q16 = nullptr, *d16 = nullptr, *o16 = nullptr, *st = nullptr;
+        if (t.alloc(&q16, M * 3 * E * 2) != cudaSuccess || t.alloc(&d16, M * E * 2) != cudaSuccess || t.alloc(&o16, M * 3 * E * 2) != cudaSuccess ||
+            t.alloc(&st, attention_bwd_stats_bytes(B, Ft, Qt, H)) != cudaSuccess)
+            return fin(c->fail(TIM_ERR_NOMEM, "alloc"));
+        cudaMemsetAsync(o16, 0, M * 3 * E * 2, s);
+        if (dtype == TIM_BF16) {
+            launch_cast<__nv_bfloat16>(qkv, static_cast<__nv_bfloat16*>(q16), M, 3 * E, 0, 1.0f, s);
+            launch_cast<__nv_bfloat16>(dO, static_cast<__nv_bfloat16*>(d16), M, E, 0, 1.0f, s);
+            e = launch_attention_bwd<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(q16), static_cast<const __nv_bfloat16*>(d16),
+                                                    static_cast<__nv_bfloat16*>(o16), st, B, Ft, Qt, H, hd, qscale, s);
+        } else {
+            launch_cast<__half>(qkv, static_cast<__half*>(q16), M, 3 * E, 0, 1.0f, s);
+            launch_cast<__half>(dO, static_cast<__half*>(d16), M, E, 0, 1.0f, s);
+            e = launch_attention_bwd<__half>(static_cast<const __half*>(q16), static_cast<const __half*>(d16), static_cast<__half*>(o16), st, B, Ft,
+                                             Qt, H, hd, qscale, s);
+        }
+        if (e == cudaSuccess) {
+            std::vector<uint16_t> h(M * 3 * E);
+            e = cudaStreamSynchronize(s);
+            if (e == cudaSuccess) e = cudaMemcpy(h.data(), o16, M * 3 * E * 2, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess) {
+                std::vector<float> f(M * 3 * E);
+                for (size_t i = 0; i < M * 3 * E; ++i) {
+                    if (dtype == TIM_BF16) { uint32_t u = static_cast<uint32_t>(h[i]) << 16; std::memcpy(&f[i], &u, 4); }
+                    else { __half_raw hr; hr.x = h[i]; f[i] = __half2float(__half(hr)); }
+                }
+                e = cudaMemcpy(dqkv, f.data(), M * 3 * E * 4, cudaMemcpyHostToDevice);
+            }
+        }
+    }
+    if (e != cudaSuccess) return fin(c->fail(TIM_ERR_CUDA, "tim_test_attention_bwd: %s", cudaGetErrorString(e)));
+    e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return fin(c->fail(TIM_ERR_CUDA, "tim_test_attention_bwd: %s", cudaGetErrorString(e)));
     return TIM_OK;
 }
 

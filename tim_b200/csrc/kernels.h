@@ -196,4 +196,70 @@ template <typename T>
 cudaError_t launch_reg_final(const T* h, int ldh, const float* W, const float* b, float* out, int rows, int K,
                              cudaStream_t s);
 
+// =====================================================================================================================
+// training leg (backward kernels)
+// =====================================================================================================================
+// ---- weight gradient: dW[N, K] += dY[M, N]^T * X[M, K] (gemm_wgrad.cu) ----
+struct WgradParams {
+    CUtensorMap tmA;      // dY: 2-D (N, M) 16-bit, box (64, 64), SWIZZLE_128B
+    CUtensorMap tmB;      // X : 2-D (K, M) 16-bit, box (64, 64), SWIZZLE_128B
+    CUtensorMap tmOut;    // dW: 2-D (K, N) fp32,   box (32, 32), SWIZZLE_128B (TMA reduce-add target)
+    int M, N, K;
+    int tiles_n, tiles_k, splits, kb_per_split;      // filled by the launcher (splits <= 0: chosen by wgrad_pick_splits)
+};
+bool wgrad_umma_supported(int M, int N, int K, int ldy, int ldx, int ldw);
+int wgrad_pick_splits(int M, int N, int K, int num_sms);
+template <typename T>
+cudaError_t launch_wgrad_umma(WgradParams p, int num_sms, cudaStream_t s);
+// CUDA-core version (fp32 parity mode: TA = float; also any shape the tensor-core kernel does not take)
+template <typename TA>
+cudaError_t launch_wgrad_simt(const TA* dY, int ldy, const TA* X, int ldx, float* dW, int ldw, int M, int N, int K, cudaStream_t s);
+
+// ---- attention backward over the two-stream layout (attention_bwd.cu); qscale: see the file header ----
+size_t attention_bwd_stats_bytes(int B, int Ft, int Qt, int H);
+template <typename T>
+cudaError_t launch_attention_bwd(const T* qkv, const T* dO, T* dqkv, void* stats, int B, int Ft, int Qt, int H, int hd, float qscale,
+                                 cudaStream_t s);
+size_t attention_bwd_simt_smem(int Ft, int hd);
+cudaError_t launch_attention_bwd_simt(const float* qkv, const float* dO, float* dqkv, int B, int Ft, int Qt, int H, int hd, float qscale,
+                                      cudaStream_t s);
+
+// ---- row / elementwise kernels (train_rows.cu) ----
+// LayerNorm backward; dy is overwritten by dz, dz16 (optional) receives its operand copy; dgamma / dbeta / dbias accumulate (+=)
+template <typename T>
+cudaError_t launch_ln_bwd(float* dy, int ldd, const float* z, int ldz, const float* gamma, T* dz16, int ld16, float* dgamma, float* dbeta,
+                          float* dbias, int M, int n, cudaStream_t s);
+// out = d * f'(a); mode 0: erf-GELU, a = pre-activation; mode 1: ReLU, a = post-activation. dbias (optional) += column sums of out
+template <typename TD, typename TA, typename TO>
+cudaError_t launch_act_bwd(int mode, const TD* d, const TA* a, TO* out, int rows, int cols, float* dbias, cudaStream_t s);
+template <typename T>
+cudaError_t launch_gelu_fwd(const T* u, T* h, size_t n, cudaStream_t s);
+// out[c] += sum_{g < G, r < R} x[(g * group_rows + row_off + r) * ld + col_off + c],  c < ncols
+template <typename T>
+cudaError_t launch_colsum(const T* x, int ld, int G, int group_rows, int row_off, int R, int col_off, int ncols, float* out, cudaStream_t s);
+// Wt[k, n] = T(W[n, k]) (n < N), 0 for N <= n < Np
+template <typename T>
+cudaError_t launch_transpose_pack(const float* W, T* Wt, int N, int K, int Np, cudaStream_t s);
+template <typename T>
+cudaError_t launch_cast_pad(const float* in, T* out, size_t rows, int C, int Cp, cudaStream_t s);
+template <typename T>
+cudaError_t launch_gather_group(const T* x, T* out, int B, int Qt, int off, int Q, int E, cudaStream_t s);
+cudaError_t launch_scatter_add_group(const float* in, float* dx, int B, int Qt, int off, int Q, int E, cudaStream_t s);
+struct AssembleBwdParams {
+    int B, d, T, Fv, Fa, Qt;
+    const float* dtok;       // [B*Ft + B*Qt, E] gradient w.r.t. the assembled tokens (two-stream layout)
+    float* dte;              // [B, T, d] gradient w.r.t. the time encodings (written, not accumulated)
+    float* demb_v;           // [B*Fv, d] gradient w.r.t. LayerNorm(GELU(embedder)) rows
+    float* demb_a;           // [B*Fa, d]
+    int n_groups;
+    TokenGroup groups[4];
+};
+cudaError_t launch_assemble_bwd(const AssembleBwdParams& p, cudaStream_t s);
+template <typename T>
+cudaError_t launch_time_l0_bwd(const T* d1, const float* times, float* dW0, int M, int d, cudaStream_t s);
+template <typename T>
+cudaError_t launch_reg_final_bwd(const float* dout, const float* y, const T* h, const float* W4, float* dW4, float* db4, T* dh, float* db2,
+                                 int rows, int K, cudaStream_t s);
+cudaError_t launch_axpy(float* y, const float* x, size_t n, cudaStream_t s);
+
 }  // namespace tim

@@ -96,6 +96,27 @@ class FlatGrads:
             lo, cnt = self.offsets[n]
             p.grad = self.buffer[lo:lo + cnt].view_as(p)
 
+    def reattach(self) -> int:
+        """Both reference train loops call optimizer.zero_grad() (recognition/scripts/train.py:354, detection/scripts/train.py:372),
+        which by default sets param.grad to None: the next backward would then allocate fresh gradients OUTSIDE the flat buffer and
+        all_reduce() would exchange stale data. Call this before every backward (patch_model does): a parameter whose .grad is no
+        longer its view is re-attached - a detached gradient counts as zero, a foreign one is copied in. Returns how many were
+        re-attached."""
+        n = 0
+        for name, p in self._params:
+            lo, cnt = self.offsets[name]
+            view = self.buffer[lo:lo + cnt].view_as(p)
+            g = p.grad
+            if g is not None and g.data_ptr() == view.data_ptr():
+                continue
+            if g is None:
+                view.zero_()
+            else:
+                view.copy_(g)
+            p.grad = view
+            n += 1
+        return n
+
     def zero_(self) -> None:
         self.buffer.zero_()
 
@@ -103,6 +124,7 @@ class FlatGrads:
         """The one data-path collective of a training step: NCCL on GPUs (NVLink / NVSwitch), gloo in the CPU tests."""
         if not (dist.is_available() and dist.is_initialized()):
             return
+        self.reattach()
         dist.all_reduce(self.buffer, op=dist.ReduceOp.SUM, group=group)
         if average:
             self.buffer.div_(dist.get_world_size(group))

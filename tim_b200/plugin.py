@@ -184,6 +184,92 @@ class TIMEngine:
                                                         C.byref(co), self._stream()), self._ctx)
         return out
 
+    # ------------------------------------------------------------------ training leg
+    def enable_training(self) -> None:
+        """Allocates the transposed weight copies of the input-gradient GEMMs; weights must be (re-)set afterwards."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tim_train_enable(self._ctx), self._ctx)
+
+    def bind_grad(self, key: str, grad: torch.Tensor) -> None:
+        """The backward accumulates d loss / d <key> into `grad` (fp32, contiguous, on this device)."""
+        if grad.device != self.device or grad.dtype != torch.float32 or not grad.is_contiguous():
+            raise ValueError(f"gradient buffer of '{key}' must be a contiguous fp32 tensor on {self.device}")
+        _lib.check(self.lib.tim_bind_grad(self._ctx, key.encode(), _ptr(grad)), self._ctx)
+
+    def time_mlp_train(self, times: torch.Tensor) -> torch.Tensor:
+        B, T = int(times.shape[0]), int(times.shape[1])
+        times = self._check_in(times, "times", (B, T, 2))
+        with torch.cuda.device(self.device):
+            out = torch.empty((B, T, self.cfg.d_model), device=self.device, dtype=torch.float32)
+            _lib.check(self.lib.tim_time_mlp_fwd_train(self._ctx, _ptr(times), _ptr(out), B, T, self._stream()), self._ctx)
+        return out
+
+    def time_mlp_bwd(self, d_out: torch.Tensor) -> None:
+        d_out = d_out.to(device=self.device, dtype=torch.float32).contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tim_time_mlp_bwd(self._ctx, _ptr(d_out), self._stream()), self._ctx)
+        d_out.record_stream(torch.cuda.current_stream(self.device))
+
+    def encoder_train(self, vis, aud, time_enc: torch.Tensor, Qv: int, Qa: int) -> Dict[str, Optional[torch.Tensor]]:
+        cfg = self.cfg
+        B, T = int(time_enc.shape[0]), int(time_enc.shape[1])
+        Qv, Qa = int(Qv or 0), int(Qa or 0)
+        time_enc = self._check_in(time_enc, "time_encodings", (B, T, cfg.d_model))
+        if cfg.has_visual_input:
+            vis = self._check_in(vis, "visual input", (B, cfg.num_feats, cfg.visual_input_dim))
+        if cfg.has_audio_input:
+            aud = self._check_in(aud, "audio input", (B, cfg.num_feats, cfg.audio_input_dim))
+        with torch.cuda.device(self.device):
+            out, co = self._alloc_outputs(B, Qv, Qa, pinned=False, want_feats=True)
+            _lib.check(self.lib.tim_encoder_fwd_train(self._ctx, _ptr(vis if cfg.has_visual_input else None),
+                                                      _ptr(aud if cfg.has_audio_input else None), _ptr(time_enc),
+                                                      B, T, Qv, Qa, C.byref(co), self._stream()), self._ctx)
+        self._train_shape = (B, T)
+        return out
+
+    def encoder_bwd(self, grads: Mapping[str, Optional[torch.Tensor]]) -> torch.Tensor:
+        """grads: gradients of the encoder_train outputs (None where the loss does not reach one). Returns d loss / d time_enc."""
+        B, T = self._train_shape
+        keep = {}
+        for k in ("verb", "noun", "action", "audio", "reg_v", "reg_a", "feats"):
+            g = grads.get(k)
+            keep[k] = g.to(device=self.device, dtype=torch.float32).contiguous() if g is not None else None
+        go = _lib.tim_outputs(verb=_ptr(keep["verb"]), noun=_ptr(keep["noun"]), action=_ptr(keep["action"]), audio=_ptr(keep["audio"]),
+                              reg_visual=_ptr(keep["reg_v"]), reg_audio=_ptr(keep["reg_a"]), feats=_ptr(keep["feats"]))
+        with torch.cuda.device(self.device):
+            d_te = torch.empty((B, T, self.cfg.d_model), device=self.device, dtype=torch.float32)
+            _lib.check(self.lib.tim_encoder_bwd(self._ctx, C.byref(go), _ptr(d_te), self._stream()), self._ctx)
+            st = torch.cuda.current_stream(self.device)
+            for g in keep.values():
+                if g is not None:
+                    g.record_stream(st)
+        return d_te
+
+    def comm_init(self, group=None) -> None:
+        """One NCCL communicator of the library's own over the ranks of `group` (the id travels through torch.distributed)."""
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        buf = (C.c_char * 128)()
+        if rank == 0:
+            _lib.check(self.lib.tim_comm_unique_id(buf), None)
+        obj = [bytes(buf) if rank == 0 else None]
+        dist.broadcast_object_list(obj, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        idbuf = C.create_string_buffer(obj[0], 128)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tim_comm_init(self._ctx, idbuf, rank, world), self._ctx)
+        self._comm_world = world
+
+    def allreduce(self, flat: torch.Tensor) -> None:
+        """The one data-path collective of a training step: average `flat` (fp32, contiguous) over the ranks, in place."""
+        if flat.device != self.device or flat.dtype != torch.float32 or not flat.is_contiguous():
+            raise ValueError("allreduce needs a contiguous fp32 tensor on the engine's device")
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tim_allreduce_grads(self._ctx, _ptr(flat), flat.numel(), self._stream()), self._ctx)
+
+    @property
+    def tape_bytes(self) -> int:
+        return int(self.lib.tim_train_tape_bytes(self._ctx))
+
     # ------------------------------------------------------------------ forward (host tensors, end to end)
     def forward_host(self, vis, aud, times: torch.Tensor, Qv: int, Qa: int, clips_per_chunk: int = 0,
                      want_feats: bool = True, out=None):
@@ -232,7 +318,8 @@ class TIMEngine:
                                                       self._stream()), None)
         return out
 
-    PROFILE_CLASSES = ("gemm_other", "attention", "layernorm", "assemble", "other", "gemm_in_proj_linear1", "gemm_out_proj_linear2")
+    PROFILE_CLASSES = ("gemm_other", "attention", "layernorm", "assemble", "other", "gemm_in_proj_linear1", "gemm_out_proj_linear2",
+                       "gemm_dgrad", "gemm_wgrad", "attention_bwd")
 
     def profile_begin(self) -> None:
         _lib.check(self.lib.tim_profile_begin(self._ctx), self._ctx)
@@ -244,7 +331,7 @@ class TIMEngine:
         _lib.check(self.lib.tim_profile_end(self._ctx, ms, fl, cnt, n), self._ctx)
         out = {name: {"ms": ms[i], "flops": fl[i], "launches": int(cnt[i])} for i, name in enumerate(self.PROFILE_CLASSES)}
         # "gemm" = every dense contraction of the step (the three GEMM classes together)
-        parts = [out[k] for k in ("gemm_other", "gemm_in_proj_linear1", "gemm_out_proj_linear2")]
+        parts = [out[k] for k in ("gemm_other", "gemm_in_proj_linear1", "gemm_out_proj_linear2", "gemm_dgrad", "gemm_wgrad")]
         out["gemm"] = {k: sum(p[k] for p in parts) for k in ("ms", "flops", "launches")}
         return out
 
@@ -285,6 +372,7 @@ class _Binding:
         self.engine = engine
         self.versions: Dict[str, tuple] = {}
         self.model = model
+        self.training_ready = False
 
     def sync(self):
         sd = {k: v for k, v in self.model.named_parameters()}
@@ -295,17 +383,119 @@ class _Binding:
                 self.engine.set_weight(k, p)
                 self.versions[k] = tag
 
+    # ---- training leg -------------------------------------------------------------------------------------------
+    def enable_training(self):
+        """First training-mode call: transposed weight copies in the library (weights are re-packed), ONE flat fp32 gradient buffer
+        holding every parameter's .grad (tim_b200.dist.FlatGrads), an autograd anchor, and - when torch.distributed is up - the
+        library's NCCL communicator for the single gradient all-reduce that replaces DDP's buckets (models/build.py:58-63)."""
+        if self.training_ready:
+            return
+        import torch.distributed as dist
+        from .dist import FlatGrads
+        bad = [n for n, m in self.model.named_modules()
+               if (isinstance(m, torch.nn.Dropout) and m.p > 0) or (isinstance(m, torch.nn.MultiheadAttention) and m.dropout > 0)]
+        if bad:
+            raise NotImplementedError("tim_b200: the training leg has no dropout kernels; construct the model with all dropout "
+                                      f"probabilities 0 (non-zero in: {', '.join(bad[:4])}{' ...' if len(bad) > 4 else ''})")
+        self.engine.enable_training()
+        self.versions.clear()                       # every weight is packed again, now with its transposed copy
+        self.flat = FlatGrads(self.model.named_parameters())
+        dev = self.engine.device
+        self.anchor = torch.zeros(1, device=dev, requires_grad=True)
+        self.bound = {}
+        self.distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        if self.distributed:
+            self.engine.comm_init()
+        self.callback_queued = False
+        self.training_ready = True
+
+    def attach_grads(self):
+        """param.grad must be the flat buffer's views when the backward runs (optimizer.zero_grad() sets them to None by default):
+        re-attach (a detached gradient counts as zero) and (re-)bind the library's destinations."""
+        params = dict(self.model.named_parameters())
+        self.flat.reattach()
+        for k in self.engine._keys:
+            v = self.flat.view(k).view_as(params[k])
+            if self.bound.get(k) != v.data_ptr():
+                self.engine.bind_grad(k, v)
+                self.bound[k] = v.data_ptr()
+
+    def queue_allreduce(self):
+        """Runs once, after the WHOLE backward pass (the callback mechanism DDP's reducer uses): the single all-reduce over the flat
+        gradient buffer, enqueued on the current stream behind the last gradient kernel."""
+        if not self.distributed or self.callback_queued:
+            return
+        self.callback_queued = True
+
+        def _cb():
+            self.callback_queued = False
+            self.engine.allreduce(self.flat.buffer)
+        torch.autograd.Variable._execution_engine.queue_callback(_cb)
+
+
+class _TimeMLPFn(torch.autograd.Function):
+    """forward_type == "time_mlp" in training mode: tim_time_mlp_fwd_train / tim_time_mlp_bwd."""
+
+    @staticmethod
+    def forward(ctx, binding, times, anchor):
+        ctx.binding = binding
+        return binding.engine.time_mlp_train(times)
+
+    @staticmethod
+    def backward(ctx, d_out):
+        b = ctx.binding
+        b.queue_allreduce()
+        b.engine.time_mlp_bwd(d_out)
+        return None, None, None
+
+
+class _EncoderFn(torch.autograd.Function):
+    """forward_type == "encoder" in training mode: tim_encoder_fwd_train / tim_encoder_bwd. Parameter gradients do not travel through
+    autograd: the library accumulates them straight into param.grad (views of the flat buffer)."""
+    KEYS = ("verb", "noun", "action", "audio", "reg_v", "reg_a", "feats")
+
+    @staticmethod
+    def forward(ctx, binding, vis, aud, time_enc, Qv, Qa, anchor):
+        o = binding.engine.encoder_train(vis, aud, time_enc, Qv, Qa)
+        ctx.binding = binding
+        return tuple(o[k] for k in _EncoderFn.KEYS)          # None where the reference returns None (non-tensor outputs pass through)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        b = ctx.binding
+        b.queue_allreduce()
+        d_te = b.engine.encoder_bwd(dict(zip(_EncoderFn.KEYS, grads)))
+        return None, None, None, d_te, None, None, None
+
+
+def _encoder_train(b: "_Binding", vis, aud, time_enc, Qv, Qa):
+    b.enable_training()
+    b.sync()
+    b.attach_grads()
+    outs = _EncoderFn.apply(b, vis, aud, time_enc, int(Qv or 0), int(Qa or 0), b.anchor)
+    return dict(zip(_EncoderFn.KEYS, outs))
+
 
 def _forward_recognition(self, inputs, forward_type, time_encodings=None, num_v_queries=None, num_a_queries=None):
     """Same signature / returns as recognition/.../models/tim.py:174-191."""
     b: _Binding = self._tim_b200
     if forward_type == "drloc_mlp":                        # loss-side helper, stays in PyTorch (SURVEY §8a)
         return self.drloc_mlp(inputs).squeeze(2)
-    if torch.is_grad_enabled() and self.training:
-        raise NotImplementedError("tim_b200: the training (backward) leg is not built yet; call under "
-                                  "model.eval() / torch.no_grad()")
     if getattr(self, "pool_features", False):
         raise NotImplementedError("tim_b200: AVGA feature pooling (AVE-only) is outside the hot path")
+    if forward_type not in ("time_mlp", "encoder"):
+        raise ValueError(f"unknown forward_type {forward_type!r}")
+    if self.training:
+        # the reference applies dropout whenever the module is in train() mode, with or without autograd (helpers/transformers.py:
+        # 73-82, encodings.py:141,149,177): the training leg below refuses non-zero dropout probabilities instead of diverging
+        b.enable_training()
+        if torch.is_grad_enabled():
+            if forward_type == "time_mlp":
+                b.sync()
+                b.attach_grads()
+                return _TimeMLPFn.apply(b, inputs, b.anchor)
+            o = _encoder_train(b, inputs[0], inputs[1], time_encodings, num_v_queries, num_a_queries)
+            return (o["verb"], o["noun"], o["action"], o["audio"]), o["feats"]
     b.sync()
     if forward_type == "time_mlp":
         return b.engine.time_mlp(inputs)
@@ -347,7 +537,7 @@ def _forward_detection(self, inputs, forward_type, feature_times=None, target=No
     if forward_type != "encoder":
         raise ValueError(f"unknown forward_type {forward_type!r}")
     if self.training:
-        raise NotImplementedError("tim_b200: the detection training leg (forward_train + backward) is not built yet")
+        return _forward_detection_train(self, inputs, feature_times, target)
     b.sync()
     cfg = b.engine.cfg
     dev = feature_times.device
@@ -373,6 +563,47 @@ def _forward_detection(self, inputs, forward_type, feature_times=None, target=No
         a_queries = torch.flatten(a_queries, 0, 1)
     te = b.engine.time_mlp(all_times)
     o = b.engine.encoder(inputs[0], inputs[1], te, nv, na)
+    cls = (o["verb"], o["noun"], o["action"], o["audio"])
+    reg = (o["reg_v"], o["reg_a"])
+    return (cls, reg, o["feats"]), (v_offsets, a_offsets), (v_labels, a_labels), (v_queries, a_queries), (v_ious, a_ious)
+
+
+def _forward_detection_train(self, inputs, feature_times, target):
+    """detection/.../models/tim.py:272-337 (forward_train): queries drawn from the train pool with the CPU global RNG exactly as the
+    reference does (torch.randperm, one draw per modality), labelled on the device, then time_mlp + encoder through the library."""
+    b: _Binding = self._tim_b200
+    b.enable_training()
+    cfg = b.engine.cfg
+    dev = feature_times.device
+    v_offsets = a_offsets = torch.empty(0, 2)
+    v_labels = a_labels = torch.empty(0, 4)
+    nv = na = 0
+    v_queries = a_queries = v_ious = a_ious = None
+    all_times = feature_times
+    B = all_times.shape[0]
+    if "visual" in cfg.data_modality:
+        idx = torch.randperm(self.train_pool.shape[1])[:self.num_queries]
+        v_queries = self.train_pool[:, idx.long()].repeat(B, 1, 1).to(device=dev)
+        nv = v_queries.shape[1]
+        v_offsets, v_labels, v_ious = _label_queries_device(self, b.engine, v_queries, target, "visual")
+        all_times = torch.cat([all_times, v_queries], dim=1)
+        v_queries = torch.flatten(v_queries, 0, 1)
+    if "audio" in cfg.data_modality:
+        idx = torch.randperm(self.train_pool.shape[1])[:self.num_queries]
+        a_queries = self.train_pool[:, idx.long()].repeat(B, 1, 1).to(device=dev)
+        na = a_queries.shape[1]
+        a_offsets, a_labels, a_ious = _label_queries_device(self, b.engine, a_queries, target, "audio")
+        all_times = torch.cat([all_times, a_queries], dim=1)
+        a_queries = torch.flatten(a_queries, 0, 1)
+    if torch.is_grad_enabled():
+        b.sync()
+        b.attach_grads()
+        te = _TimeMLPFn.apply(b, all_times, b.anchor)
+        o = _encoder_train(b, inputs[0], inputs[1], te, nv, na)
+    else:
+        b.sync()
+        te = b.engine.time_mlp(all_times)
+        o = b.engine.encoder(inputs[0], inputs[1], te, nv, na)
     cls = (o["verb"], o["noun"], o["action"], o["audio"])
     reg = (o["reg_v"], o["reg_a"])
     return (cls, reg, o["feats"]), (v_offsets, a_offsets), (v_labels, a_labels), (v_queries, a_queries), (v_ious, a_ious)
