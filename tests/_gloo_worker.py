@@ -49,6 +49,23 @@ def main():
         dist.all_gather(parts, mine[n])
         assert torch.allclose(p.grad, sum(parts) / world, rtol=1e-6, atol=1e-7), n
         assert p.grad.data_ptr() == flat.view(n).data_ptr()
+    # optimizer.zero_grad() (set_to_none=True, what both reference train loops call) detaches param.grad from the flat buffer:
+    # (a) reattach() before the backward (what patch_model does) makes autograd accumulate into the views again;
+    # (b) a backward WITHOUT it leaves foreign gradients, which all_reduce() copies in and re-binds before the collective.
+    opt = torch.optim.SGD(net.parameters(), lr=0.1)
+    for variant in ("reattach_before_backward", "foreign_grads"):
+        opt.zero_grad()
+        assert all(p.grad is None for p in net.parameters())
+        if variant == "reattach_before_backward":
+            assert flat.reattach() == len(list(net.parameters())) and float(flat.buffer.abs().sum()) == 0.0
+        net(x).square().sum().backward()
+        mine = {n: p.grad.clone() for n, p in net.named_parameters()}
+        flat.all_reduce()
+        for n, p in net.named_parameters():
+            parts = [torch.zeros_like(mine[n]) for _ in range(world)]
+            dist.all_gather(parts, mine[n])
+            assert torch.allclose(p.grad, sum(parts) / world, rtol=1e-6, atol=1e-7), (variant, n)
+            assert p.grad.data_ptr() == flat.view(n).data_ptr(), (variant, n)
     if rank == 0:
         print("GLOO_FLATGRAD_OK")
     dist.destroy_process_group()

@@ -144,6 +144,18 @@ def main():
             loss = sum((v * cotangent(name, k, v.shape, dev)).sum() for k, v in out.items() if v is not None)
             loss.backward()
             ref_g = {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+            # yardstick: the reference's OWN mixed precision (fp16 autocast, as its training loop runs it, train.py:197) against
+            # its fp32 run - gradients behind a ReLU gate move by the same order in any 16-bit implementation
+            model.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.float16):
+                out_ac = run_model(model, cfg, t, Qv, Qa, train=True)
+                loss_ac = sum((v.float() * cotangent(name, k, v.shape, dev)).sum() for k, v in out_ac.items() if v is not None)
+            loss_ac.backward()
+            for k, g in ref_g.items():
+                pg = dict(model.named_parameters())[k].grad
+                if pg is not None and not (k.startswith("drloc_mlp") or k.startswith("pool")):
+                    rec[f"ref_autocast_fp16/{k}"] = {"rel_l2": rel(pg, g)}
+            model.zero_grad(set_to_none=True)
             for dt in ("fp32", "fp16"):
                 m2 = build_reference(cfg).to(dev)
                 m2.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)

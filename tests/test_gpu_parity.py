@@ -309,11 +309,16 @@ def test_patch_model_dropin(lib, name, dt):
     sd2[key] = sd[key] * np.float32(1.5)
     check(run(), sd2)
     assert set(model.state_dict().keys()) >= set(sd.keys())                  # the module tree / checkpoint layout is untouched
-    model.train()
-    with pytest.raises(NotImplementedError):
-        model([vis, aud], "encoder", times, Qv, Qa) if cfg.variant == "recognition" else model([vis, aud], "encoder", times[:, :cfg.F_tot])
     with pytest.raises(ValueError):
         model.eval()(times, "no_such_forward_type")
+    # train() mode: a module that would apply dropout is refused (the training leg has no dropout kernels) instead of being run
+    # without it - also under no_grad, where the reference still applies dropout (helpers/transformers.py:73-82)
+    if cfg.variant == "recognition":
+        m2 = FakeTIM(cfg, sd).to(dev)
+        m2.add_module("extra_dropout", torch.nn.Dropout(0.5))
+        m2 = patch_model(m2.train(), compute_dtype=dt)
+        with pytest.raises(NotImplementedError), torch.no_grad():
+            m2(times, "time_mlp")
 
 
 @pytest.mark.parametrize("name", ["vn", "act", "aud"])

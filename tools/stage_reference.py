@@ -6,7 +6,7 @@
 baseline/_ref/ is git-ignored (never enters history) but NOT gpurun-ignored, exactly like oracle/_ref/: the snapshot that goes to
 the GPU box carries it. Only what `from time_interval_machine.models.tim import TIM` needs is copied, byte for byte, per variant
 (both variants use the same package name, so each lives under its own root and is imported in its own process):
-    <variant>/time_interval_machine/__init__.py, models/** (tim.py, build.py, helpers/*), utils/{__init__,logging,distributed}.py
+    <variant>/time_interval_machine/__init__.py, models/** (tim.py, build.py, helpers/*), utils/** (utils/__init__.py imports all of it)
 Users: tests/test_real_reference_gpu.py (patch_model on the real nn.Module, on a B200, against the same module run un-patched in
 fp32) and bench.py's gpu_eager_baseline leg (the reference's own eager-PyTorch forward on the same GPU). Nothing under tim_b200/
 imports it.
@@ -22,7 +22,6 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = "/root/reference"
 DST = os.path.join(ROOT, "baseline", "_ref")
-UTILS = ("__init__.py", "logging.py", "distributed.py")
 
 
 def stage() -> str:
@@ -34,12 +33,10 @@ def stage() -> str:
         pkg_dst = os.path.join(DST, variant, "time_interval_machine")
         if os.path.isdir(pkg_dst):
             shutil.rmtree(pkg_dst)
-        os.makedirs(os.path.join(pkg_dst, "utils"), exist_ok=True)
+        os.makedirs(pkg_dst, exist_ok=True)
         shutil.copy2(os.path.join(pkg_src, "__init__.py"), os.path.join(pkg_dst, "__init__.py"))
-        shutil.copytree(os.path.join(pkg_src, "models"), os.path.join(pkg_dst, "models"),
-                        ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
-        for f in UTILS:
-            shutil.copy2(os.path.join(pkg_src, "utils", f), os.path.join(pkg_dst, "utils", f))
+        for sub in ("models", "utils"):       # utils/__init__.py imports every utils module, so the whole directory travels
+            shutil.copytree(os.path.join(pkg_src, sub), os.path.join(pkg_dst, sub), ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
         for dp, _, fs in os.walk(pkg_dst):
             for f in fs:
                 p = os.path.join(dp, f)
