@@ -188,25 +188,31 @@ def time_steps(X: Ctx, fn, steps, warmup):
     return X.max_ranks(e0.elapsed_time(e1) / steps)
 
 
-def measure_e2e(X: Ctx, eng, cfg, vis, aud, times, B, Qv, Qa, chunk, steps):
+def measure_e2e(X: Ctx, eng, cfg, vis, aud, times, B, Qv, Qa, chunk, steps, feat_dtype=None, out_dtype=None):
+    """End to end through the plugin call on pinned HOST buffers. feat_dtype: dtype of the host feature bank (fp32 as the reference's
+    loader holds it, or the engine's 16-bit operand type - bit-identical results on the 16-bit paths, tests/test_gpu_parity.py::
+    test_host_path_16bit_io); out_dtype: dtype of the logits brought back."""
     torch = X.torch
-    hv = vis.cpu().pin_memory() if vis is not None else None
-    ha = aud.cpu().pin_memory() if aud is not None else None
+    feat_dtype = feat_dtype or torch.float32
+    out_dtype = out_dtype or torch.float32
+    hv = vis.to(feat_dtype).cpu().pin_memory() if vis is not None else None
+    ha = aud.to(feat_dtype).cpu().pin_memory() if aud is not None else None
     ht = times.cpu().pin_memory()
     # what the reference's eval loop brings back to the host: the logits / regression outputs (recognition/scripts/test.py:
     # 106-131 reads output[0] only); the feature rows output[1] feed the drloc loss in training and stay on the device
-    hout = eng._alloc_outputs(B, Qv, Qa, pinned=True, want_feats=False)
+    hout = eng._alloc_outputs(B, Qv, Qa, pinned=True, want_feats=False, dtype=out_dtype)
     for _ in range(2):
-        _, up, down = eng.forward_host(hv, ha, ht, Qv, Qa, clips_per_chunk=chunk, out=hout)
+        _, up, down = eng.forward_host(hv, ha, ht, Qv, Qa, clips_per_chunk=chunk, out=hout, out_dtype=out_dtype)
     X.barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
-        eng.forward_host(hv, ha, ht, Qv, Qa, clips_per_chunk=chunk, out=hout)
+        eng.forward_host(hv, ha, ht, Qv, Qa, clips_per_chunk=chunk, out=hout, out_dtype=out_dtype)
     torch.cuda.synchronize()
     s = X.max_ranks((time.perf_counter() - t0) / steps)
     X.barrier()
     return {"value": X.world * B * (Qv + Qa) / s, "unit": UNIT, "h2d_bytes_per_step": up, "d2h_bytes_per_step": down,
             "ms_per_step": s * 1e3, "clips_per_chunk": chunk,
+            "host_io": f"features {str(feat_dtype).replace('torch.', '')} (pinned host bank), interval times fp32, logits back as {str(out_dtype).replace('torch.', '')}",
             "d2h": "logits / regression outputs (what the reference eval loop reads, test.py:106-131); feature rows stay on device",
             "timing": "host wall clock around the blocking plugin call (outputs are in pinned host memory when it returns), "
                       "device synchronised on both sides, max over ranks"}, (hv, ha, ht, hout)
@@ -522,7 +528,20 @@ def main():
     # tiles (tim_forward_host). B // 3 measured best on cfg2
     chunk = args.chunk or max(1, B // 3)
     e2e_steps = max(3, args.steps // 4)
-    e2e, (hv, ha, ht, hout) = measure_e2e(X, eng, cfg, vis, aud, times, B, Qv, Qa, chunk, e2e_steps)
+    # headline e2e: the host feature bank kept in the operand type of the 16-bit paths (the kernels round the features to it before
+    # the embedder GEMM anyway: bit-identical outputs, half the H2D bytes, no cast pass), logits back in fp32. Next to it: the fp32
+    # host bank exactly as the reference's loader holds it (`e2e_fp32_io`, the r01 definition) and fp16 logits (`e2e_fp16_logits`).
+    op_dt = {"fp16": torch.float16, "bf16": torch.bfloat16}.get(args.dtype)
+    e2e_fp32, _k = measure_e2e(X, eng, cfg, vis, aud, times, B, Qv, Qa, chunk, e2e_steps)
+    del _k
+    e2e_16out = None
+    if op_dt is not None:
+        e2e, (hv, ha, ht, hout) = measure_e2e(X, eng, cfg, vis, aud, times, B, Qv, Qa, chunk, e2e_steps, feat_dtype=op_dt)
+        if not args.no_extras:
+            e2e_16out, _k = measure_e2e(X, eng, cfg, vis, aud, times, B, Qv, Qa, chunk, e2e_steps, feat_dtype=op_dt, out_dtype=torch.float16)
+            del _k
+    else:
+        e2e, (hv, ha, ht, hout) = measure_e2e(X, eng, cfg, vis, aud, times, B, Qv, Qa, chunk, e2e_steps)
     e2e["host_numa_node_of_rank0"] = numa_node
     down = e2e["d2h_bytes_per_step"]
 
@@ -587,7 +606,7 @@ def main():
             e4.load_state_dict(synth_state_dict(c4, 0, "trained"))
             v4, a4, t4 = synth_device_inputs(X, c4, B4, q4v, q4a)
             ms4 = time_steps(X, lambda: e4.encoder(v4, a4, e4.time_mlp(t4), q4v, q4a), max(5, args.steps // 4), 3)
-            e2e4, _keep = measure_e2e(X, e4, c4, v4, a4, t4, B4, q4v, q4a, max(1, B4 // 3), 3)
+            e2e4, _keep = measure_e2e(X, e4, c4, v4, a4, t4, B4, q4v, q4a, max(1, B4 // 3), 3, feat_dtype=op_dt)
             f4 = c4.flops_fwd_per_clip(q4v, q4a) * B4
             cfg4 = {"config": line_config("cfg4", args.dtype, B4, q4v, q4a, world), "value": world * B4 * (q4v + q4a) / (ms4 * 1e-3), "unit": UNIT,
                     "ms_per_step": ms4, "clips_per_sec": world * B4 / (ms4 * 1e-3), "path_tflops": f4 / (ms4 * 1e-3) / 1e12,
@@ -614,7 +633,7 @@ def main():
                 "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
                 "data": "synthetic", "config": conf, "input_bytes_per_step": in_bytes,
                 "clips_per_sec": world * B / (ms * 1e-3), "tokens_per_sec": world * B * cfg.seq_len(Qv, Qa) / (ms * 1e-3),
-                "gpu_launches": int(launches), "e2e": e2e, "e2e_resident_bank": e2e_bank, "roofline": roofline, "cpu_baseline": cb, "clocks": clocks,
+                "gpu_launches": int(launches), "e2e": e2e, "e2e_fp32_io": e2e_fp32, "e2e_fp16_logits": e2e_16out, "e2e_resident_bank": e2e_bank, "roofline": roofline, "cpu_baseline": cb, "clocks": clocks,
                 "parity": parity, "train": train, "cfg4": cfg4, "sweep_cfg5": sweep, "gpu_eager_baseline": eager}
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:

@@ -118,6 +118,18 @@ int tim_encoder_fwd_indexed(tim_ctx* ctx, const tim_feature_bank* bank, const fl
  * h2d_bytes / d2h_bytes (optional) receive the bytes moved. */
 int tim_forward_host(tim_ctx* ctx, const float* vis, const float* aud, const float* times, int B, int T, int Qv, int Qa,
                      const tim_outputs* host_outs, int clips_per_chunk, uint64_t* h2d_bytes, uint64_t* d2h_bytes);
+/* The same call with the host-side formats and the ordering made explicit:
+ *  in_dtype   TIM_FP32, or the context's 16-bit compute dtype: vis / aud then point to a 16-bit HOST feature bank slice. The
+ *             16-bit paths round the features to the operand type before the embedder GEMM anyway, so results are bit-identical
+ *             to the fp32 call while half the bytes cross PCIe and the cast pass disappears.
+ *  out_dtype  TIM_FP32, or TIM_FP16: every output buffer of host_outs is then __half (logits rounded once, on the device).
+ *  stream     the caller's stream (torch.cuda.current_stream): work enqueued there before the call (weight packing, an earlier
+ *             forward) is waited for through an event; nothing else on the device is synchronised.
+ * The precision guard of the folded-LayerNorm flow acts inside the call: if a chunk flags rows outside the folded path's error
+ * bound, the context switches to the un-folded flow and the whole call is recomputed before it returns. */
+int tim_forward_host_ex(tim_ctx* ctx, const void* vis, const void* aud, const float* times, int B, int T, int Qv, int Qa,
+                        const tim_outputs* host_outs, int clips_per_chunk, int in_dtype, int out_dtype, void* stream,
+                        uint64_t* h2d_bytes, uint64_t* d2h_bytes);
 
 /* The chunk sizes tim_forward_host uses for a batch of B clips (pure host arithmetic, no device needed): writes up to max_out
  * sizes to out and returns the number of chunks (negative tim_status on bad arguments). rows_per_clip = token rows per clip
@@ -132,6 +144,11 @@ int tim_seq_len(const tim_config* cfg, int Qv, int Qa); /* S = F_tot + query tok
  * un-folded flow is in use: fp32 mode, shapes the CTA-pair GEMM does not cover, TIM_B200_FOLD=0, or after the precision
  * guard saw residual-stream rows with |mean| > 8 std in an earlier forward of this context. */
 int tim_fold_active(const tim_ctx* ctx);
+/* Device entry points never synchronise, so the guard's verdict on a forward is known only after it ran: tim_fold_check blocks until
+ * the most recent tim_encoder_fwd / _indexed of this context has finished its check and returns 1 if that forward took the folded
+ * flow AND flagged such rows - its outputs should be recomputed by calling the forward again (the context has switched to the
+ * un-folded flow) - else 0. tim_forward_host(_ex) does this internally. */
+int tim_fold_check(tim_ctx* ctx);
 
 /* Detection query labelling (detection/time_interval_machine/models/tim.py:186-270 get_query_ious + label_queries): for every
  * query [B, Nq, 2] the ground-truth segment [B, Na, 2] of maximal IoU (first maximum; computed after the reference's shift by

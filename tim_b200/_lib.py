@@ -74,6 +74,10 @@ SYMBOLS = {
                                       C.POINTER(C.c_float)]),
     "tim_test_attention": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                      C.c_void_p]),
+    "tim_forward_host_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(tim_outputs), C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint64),
+                                      C.POINTER(C.c_uint64)]),
+    "tim_fold_check": (C.c_int, [C.c_void_p]),
     "tim_train_enable": (C.c_int, [C.c_void_p]),
     "tim_bind_grad": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p]),
     "tim_time_mlp_fwd_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
@@ -125,6 +129,13 @@ def load() -> C.CDLL:
         raise RuntimeError(f"libtim_b200 ABI version {v} != binding {ABI_VERSION}; rebuild the library")
     _lib = lib
     return lib
+
+
+def check_nonneg(status: int, ctx=None) -> int:
+    """for entry points that return a count / flag (>= 0) or a negative tim_status"""
+    if status < 0:
+        check(status, ctx)
+    return status
 
 
 def check(status: int, ctx=None) -> None:

@@ -106,6 +106,9 @@ struct tim_ctx {
     int* fold_alarm_dev = nullptr;
     volatile int* fold_alarm_host = nullptr;
     bool fold_tripped = false;
+    bool last_folded = false;           // the most recent encoder forward took the folded flow
+    cudaEvent_t fold_event = nullptr;   // recorded behind the alarm's D2H copy of that forward (tim_fold_check waits on it)
+    std::vector<cudaEvent_t> host_events;   // reused by tim_forward_host_ex (three per chunk) + one for the caller's stream
 
     // optional live profiling: CUDA-event pairs around every launch, accumulated per kernel class
     bool profiling = false;
@@ -620,7 +623,7 @@ int plan_queries(tim_ctx* c, int T_, int Qv, int Qa, QueryPlan* qp) {
 template <typename T>
 int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te, int B, int T_, int Qv, int Qa,
                  const tim_outputs* o, cudaStream_t s, uint8_t* ws_base, size_t* ws_need, const tim_feature_bank* fb = nullptr,
-                 bool ws_indexed = false) {
+                 bool ws_indexed = false, bool in16 = false) {
     constexpr bool f32 = std::is_same<T, float>::value;
     const tim_config& g = c->cfg;
     const int d = c->d, E = c->E, FF = c->FF;
@@ -664,7 +667,8 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
             A = vis16;
         } else {
             if (!vis) return c->fail(TIM_ERR_INVALID, "visual input is NULL");
-            if constexpr (!f32) { LAUNCH(c, launch_cast<T>(vis, vis16, Mv, g.vis_dim, 0, 1.0f, s)); A = vis16; }
+            // in16: the caller's rows already are in the operand type (16-bit host feature bank of tim_forward_host_ex): no cast pass
+            if constexpr (!f32) { if (!in16) { LAUNCH(c, launch_cast<T>(vis, vis16, Mv, g.vis_dim, 0, 1.0f, s)); A = vis16; } }
         }
         TIM_TRY(run_linear<T>(c, A, g.vis_dim, c->emb_v, plain_rows(Mv), epi(embv, d, true, ACT_GELU), s));
     }
@@ -677,7 +681,7 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
             A = aud16;
         } else {
             if (!aud) return c->fail(TIM_ERR_INVALID, "audio input is NULL");
-            if constexpr (!f32) { LAUNCH(c, launch_cast<T>(aud, aud16, Ma, g.aud_dim, 0, 1.0f, s)); A = aud16; }
+            if constexpr (!f32) { if (!in16) { LAUNCH(c, launch_cast<T>(aud, aud16, Ma, g.aud_dim, 0, 1.0f, s)); A = aud16; } }
         }
         TIM_TRY(run_linear<T>(c, A, g.aud_dim, c->emb_a, plain_rows(Ma), epi(emba, d, true, ACT_GELU), s));
     }
@@ -823,7 +827,12 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
         }
     }
     if (o->feats && Mf && !feats_done) CU_OK(c, cudaMemcpyAsync(o->feats, feats_src, Mf * E * sizeof(float), cudaMemcpyDeviceToDevice, s));
-    if (folded) CU_OK(c, cudaMemcpyAsync(const_cast<int*>(c->fold_alarm_host), c->fold_alarm_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+    c->last_folded = folded;
+    if (folded) {
+        CU_OK(c, cudaMemcpyAsync(const_cast<int*>(c->fold_alarm_host), c->fold_alarm_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (!c->fold_event) CU_OK(c, cudaEventCreateWithFlags(&c->fold_event, cudaEventDisableTiming));
+        CU_OK(c, cudaEventRecord(c->fold_event, s));
+    }
     return TIM_OK;
 }
 
@@ -944,6 +953,8 @@ void tim_destroy(tim_ctx* c) {
     for (void* p : c->allocs) cudaFree(p);
     if (c->ws) cudaFree(c->ws);
     if (c->fold_alarm_host) cudaFreeHost(const_cast<int*>(c->fold_alarm_host));
+    if (c->fold_event) cudaEventDestroy(c->fold_event);
+    for (cudaEvent_t e : c->host_events) cudaEventDestroy(e);
     if (c->train) {
         if (c->train->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->train->nccl_comm);
         if (c->train->mem) cudaFree(c->train->mem);
@@ -1097,52 +1108,49 @@ int tim_host_chunk_schedule(int B, int clips_per_chunk, int rows_per_clip, int E
     return static_cast<int>(v.size());
 }
 
-int tim_forward_host(tim_ctx* c, const float* vis, const float* aud, const float* times, int B, int T_, int Qv, int Qa,
-                     const tim_outputs* ho, int cpc, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+int tim_forward_host_ex(tim_ctx* c, const void* vis, const void* aud, const float* times, int B, int T_, int Qv, int Qa,
+                        const tim_outputs* ho, int cpc, int in_dtype, int out_dtype, void* stream, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
     if (!c) return TIM_ERR_INVALID;
     if (!times || !ho || B <= 0 || T_ <= 0) return c->fail(TIM_ERR_INVALID, "tim_forward_host: bad arguments");
+    const tim_config& g = c->cfg;
+    const bool in16 = in_dtype != TIM_FP32;
+    if (in16 && in_dtype != g.compute_dtype) return c->fail(TIM_ERR_INVALID, "tim_forward_host_ex: 16-bit host features must be in the context's compute dtype");
+    if (out_dtype != TIM_FP32 && out_dtype != TIM_FP16) return c->fail(TIM_ERR_INVALID, "tim_forward_host_ex: out_dtype must be TIM_FP32 or TIM_FP16");
+    const bool out16 = out_dtype == TIM_FP16;
     TIM_TRY(check_ready(c));
     CU_OK(c, cudaSetDevice(c->device));
-    const tim_config& g = c->cfg;
     if (cpc <= 0 || cpc > B) cpc = B;
     QueryPlan qp;
     TIM_TRY(plan_queries(c, T_, Qv, Qa, &qp));
-    // This call runs on the context's own non-blocking streams and blocks until the results are on the host. Work the caller
-    // enqueued earlier on ITS stream (tim_set_weight packing, a previous device-path forward) is not ordered against those
-    // streams, so settle the device first - a blocking API can afford it.
-    CU_OK(c, cudaDeviceSynchronize());
     if (!c->s_h2d) {
         CU_OK(c, cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
         CU_OK(c, cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
         CU_OK(c, cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
     }
-    // per-clip sizes (floats)
+    // per-clip sizes (elements)
+    const size_t isz = in16 ? 2 : 4, osz = out16 ? 2 : 4;
     const size_t n_vis = static_cast<size_t>(c->Fv) * g.vis_dim, n_aud = static_cast<size_t>(c->Fa) * g.aud_dim;
     const size_t n_times = static_cast<size_t>(T_) * 2, n_te = static_cast<size_t>(T_) * c->d;
     const size_t n_verb = ho->verb ? static_cast<size_t>(qp.Qv) * g.n_verb : 0, n_noun = ho->noun ? static_cast<size_t>(qp.Qv) * g.n_noun : 0;
     const size_t n_act = ho->action ? static_cast<size_t>(qp.Qv) * g.n_action : 0, n_au = ho->audio ? static_cast<size_t>(qp.Qa) * g.n_audio : 0;
     const size_t n_rv = ho->reg_visual ? static_cast<size_t>(qp.Qv) * 2 : 0, n_ra = ho->reg_audio ? static_cast<size_t>(qp.Qa) * 2 : 0;
     const size_t n_feats = ho->feats ? static_cast<size_t>(c->Ft) * c->E : 0;
+    const size_t n_out[7] = {n_verb, n_noun, n_act, n_au, n_rv, n_ra, n_feats};
     // two staging sets (double buffering across chunks)
-    struct Set { float *vis, *aud, *times, *te, *verb, *noun, *act, *au, *rv, *ra, *feats; };
+    struct Set { uint8_t *vis, *aud; float *times, *te; float* out[7]; __half* out16[7]; };
     Set st[2];
-    size_t io_need = 0;
     for (int pass = 0; pass < 2; ++pass) {
         Arena a{pass ? c->io : nullptr};
         for (int k = 0; k < 2; ++k) {
-            a.take(&st[k].vis, cpc * n_vis * 4); a.take(&st[k].aud, cpc * n_aud * 4); a.take(&st[k].times, cpc * n_times * 4);
-            a.take(&st[k].te, cpc * n_te * 4); a.take(&st[k].verb, cpc * n_verb * 4); a.take(&st[k].noun, cpc * n_noun * 4);
-            a.take(&st[k].act, cpc * n_act * 4); a.take(&st[k].au, cpc * n_au * 4); a.take(&st[k].rv, cpc * n_rv * 4);
-            a.take(&st[k].ra, cpc * n_ra * 4); a.take(&st[k].feats, cpc * n_feats * 4);
+            a.take(&st[k].vis, cpc * n_vis * isz); a.take(&st[k].aud, cpc * n_aud * isz); a.take(&st[k].times, cpc * n_times * 4);
+            a.take(&st[k].te, cpc * n_te * 4);
+            for (int j = 0; j < 7; ++j) { a.take(&st[k].out[j], cpc * n_out[j] * 4); a.take(&st[k].out16[j], out16 ? cpc * n_out[j] * 2 : 0); }
         }
-        if (!pass) {
-            io_need = a.off;
-            if (io_need > c->io_bytes) {
-                if (c->io) { cudaDeviceSynchronize(); cudaFree(c->io); c->io = nullptr; c->io_bytes = 0; }
-                cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->io), io_need);
-                if (e != cudaSuccess) return c->fail(TIM_ERR_NOMEM, "staging cudaMalloc(%zu) failed: %s", io_need, cudaGetErrorString(e));
-                c->io_bytes = io_need;
-            }
+        if (!pass && a.off > c->io_bytes) {
+            if (c->io) { cudaDeviceSynchronize(); cudaFree(c->io); c->io = nullptr; c->io_bytes = 0; }
+            cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&c->io), a.off);
+            if (e != cudaSuccess) return c->fail(TIM_ERR_NOMEM, "staging cudaMalloc(%zu) failed: %s", a.off, cudaGetErrorString(e));
+            c->io_bytes = a.off;
         }
     }
     size_t need_t = 0, need_e = 0;
@@ -1152,75 +1160,123 @@ int tim_forward_host(tim_ctx* c, const float* vis, const float* aud, const float
 
     // chunk schedule: full chunks of about cpc clips with tapered ends (a quarter, a half ... a half, a quarter) so that the
     // un-overlapped H2D of the first chunk and D2H of the last chunk are short. On the 16-bit path chunk sizes are aligned to
-    // whole WAVES of GEMM tiles: the encoder GEMMs run 256-row tiles on num_sms persistent CTAs, so a chunk whose row-tile count
-    // is a multiple of num_sms / gcd(num_sms, E / 256) fills every wave of all four of them (E = 1024 on 148 SMs: 37 row tiles
-    // = 47 clips of 200 tokens); a 64-clip chunk would leave out_proj / linear2 at 1.35 waves = 68 % occupancy.
+    // whole WAVES of GEMM tiles (see chunk_schedule).
     std::vector<int> chunk_b0, chunk_nb = chunk_schedule(B, cpc, c->Ft + qp.Qt, c->E, c->num_sms, g.compute_dtype != TIM_FP32);
     {
         int b0 = 0;
         for (int n : chunk_nb) { chunk_b0.push_back(b0); b0 += n; }
     }
     const int nchunks = static_cast<int>(chunk_nb.size());
-    struct EventSet {                                   // destroyed on every exit path
-        std::vector<cudaEvent_t> ev;
-        ~EventSet() { for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e); }
-    } events;
-    events.ev.assign(3 * static_cast<size_t>(nchunks), nullptr);
-    cudaEvent_t* ev_in = events.ev.data();
+    // events live in the context and are reused call after call (3 per chunk + 1 for the caller's stream)
+    while (c->host_events.size() < 3 * static_cast<size_t>(nchunks) + 1) {
+        cudaEvent_t e = nullptr;
+        CU_OK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->host_events.push_back(e);
+    }
+    cudaEvent_t* ev_in = c->host_events.data();
     cudaEvent_t* ev_comp = ev_in + nchunks;
     cudaEvent_t* ev_out = ev_comp + nchunks;
-    for (int i = 0; i < 3 * nchunks; ++i) CU_OK(c, cudaEventCreateWithFlags(&events.ev[i], cudaEventDisableTiming));
+    cudaEvent_t ev_caller = c->host_events[3 * static_cast<size_t>(nchunks)];
+    // Work the caller enqueued earlier on ITS stream (tim_set_weight packing, a previous device-path forward) must be complete
+    // before the context's own streams read weights / reuse the workspace: an event on that stream, waited for by the H2D and
+    // compute streams. No device-wide synchronisation: other streams and contexts of the device keep running.
+    CU_OK(c, cudaEventRecord(ev_caller, static_cast<cudaStream_t>(stream)));
+    CU_OK(c, cudaStreamWaitEvent(c->s_h2d, ev_caller, 0));
+    CU_OK(c, cudaStreamWaitEvent(c->s_comp, ev_caller, 0));
+
+    const bool was_folded_ctx = c->fold_ln && !c->fold_tripped;
     uint64_t up = 0, down = 0;
     int rc = TIM_OK;
-    auto h2d = [&](float* dst, const float* src, size_t n) -> cudaError_t {
-        if (!n) return cudaSuccess;
-        up += n * 4;
-        return cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyHostToDevice, c->s_h2d);
+    cudaError_t ce = cudaSuccess;
+#define HOST_CU(expr) do { if (ce == cudaSuccess) ce = (expr); } while (0)
+    auto h2d = [&](void* dst, const void* src, size_t bytes) {
+        if (!bytes) return;
+        up += bytes;
+        HOST_CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->s_h2d));
     };
-    auto d2h = [&](float* dst, const float* src, size_t n) -> cudaError_t {
-        if (!n) return cudaSuccess;
-        down += n * 4;
-        return cudaMemcpyAsync(dst, src, n * 4, cudaMemcpyDeviceToHost, c->s_d2h);
-    };
-    for (int i = 0; i < nchunks && rc == TIM_OK; ++i) {
+    void* const hdst[7] = {ho->verb, ho->noun, ho->action, ho->audio, ho->reg_visual, ho->reg_audio, ho->feats};
+    for (int i = 0; i < nchunks && rc == TIM_OK && ce == cudaSuccess; ++i) {
         const size_t b0 = static_cast<size_t>(chunk_b0[i]);
         const int nb = chunk_nb[i];
         Set& s = st[i & 1];
         // inputs of chunk i may overwrite set (i&1) once chunk i-2 has been computed
-        if (i >= 2) CU_OK(c, cudaStreamWaitEvent(c->s_h2d, ev_comp[i - 2], 0));
-        if (c->Fv) CU_OK(c, h2d(s.vis, vis + b0 * n_vis, nb * n_vis));
-        if (c->Fa) CU_OK(c, h2d(s.aud, aud + b0 * n_aud, nb * n_aud));
-        CU_OK(c, h2d(s.times, times + b0 * n_times, nb * n_times));
-        CU_OK(c, cudaEventRecord(ev_in[i], c->s_h2d));
+        if (i >= 2) HOST_CU(cudaStreamWaitEvent(c->s_h2d, ev_comp[i - 2], 0));
+        if (c->Fv) h2d(s.vis, static_cast<const uint8_t*>(vis) + b0 * n_vis * isz, nb * n_vis * isz);
+        if (c->Fa) h2d(s.aud, static_cast<const uint8_t*>(aud) + b0 * n_aud * isz, nb * n_aud * isz);
+        h2d(s.times, times + b0 * n_times, nb * n_times * 4);
+        HOST_CU(cudaEventRecord(ev_in[i], c->s_h2d));
         // compute: needs its inputs, and its output set free (chunk i-2 copied out)
-        CU_OK(c, cudaStreamWaitEvent(c->s_comp, ev_in[i], 0));
-        if (i >= 2) CU_OK(c, cudaStreamWaitEvent(c->s_comp, ev_out[i - 2], 0));
+        HOST_CU(cudaStreamWaitEvent(c->s_comp, ev_in[i], 0));
+        if (i >= 2) HOST_CU(cudaStreamWaitEvent(c->s_comp, ev_out[i - 2], 0));
+        if (ce != cudaSuccess) break;
         rc = dispatch_dtype(c, [&](auto tag) { return time_mlp_impl<decltype(tag)>(c, s.times, s.te, nb, T_, c->s_comp, c->ws, nullptr); });
         if (rc != TIM_OK) break;
         tim_outputs dout;
-        dout.verb = n_verb ? s.verb : nullptr; dout.noun = n_noun ? s.noun : nullptr; dout.action = n_act ? s.act : nullptr;
-        dout.audio = n_au ? s.au : nullptr; dout.reg_visual = n_rv ? s.rv : nullptr; dout.reg_audio = n_ra ? s.ra : nullptr;
-        dout.feats = n_feats ? s.feats : nullptr;
-        rc = dispatch_dtype(c, [&](auto tag) { return encoder_impl<decltype(tag)>(c, s.vis, s.aud, s.te, nb, T_, Qv, Qa, &dout, c->s_comp, c->ws, nullptr); });
+        dout.verb = n_verb ? s.out[0] : nullptr; dout.noun = n_noun ? s.out[1] : nullptr; dout.action = n_act ? s.out[2] : nullptr;
+        dout.audio = n_au ? s.out[3] : nullptr; dout.reg_visual = n_rv ? s.out[4] : nullptr; dout.reg_audio = n_ra ? s.out[5] : nullptr;
+        dout.feats = n_feats ? s.out[6] : nullptr;
+        rc = dispatch_dtype(c, [&](auto tag) {
+            return encoder_impl<decltype(tag)>(c, reinterpret_cast<const float*>(s.vis), reinterpret_cast<const float*>(s.aud), s.te, nb, T_, Qv, Qa, &dout,
+                                               c->s_comp, c->ws, nullptr, nullptr, false, in16);
+        });
         if (rc != TIM_OK) break;
-        CU_OK(c, cudaEventRecord(ev_comp[i], c->s_comp));
-        CU_OK(c, cudaStreamWaitEvent(c->s_d2h, ev_comp[i], 0));
-        if (n_verb) CU_OK(c, d2h(ho->verb + b0 * n_verb, s.verb, nb * n_verb));
-        if (n_noun) CU_OK(c, d2h(ho->noun + b0 * n_noun, s.noun, nb * n_noun));
-        if (n_act) CU_OK(c, d2h(ho->action + b0 * n_act, s.act, nb * n_act));
-        if (n_au) CU_OK(c, d2h(ho->audio + b0 * n_au, s.au, nb * n_au));
-        if (n_rv) CU_OK(c, d2h(ho->reg_visual + b0 * n_rv, s.rv, nb * n_rv));
-        if (n_ra) CU_OK(c, d2h(ho->reg_audio + b0 * n_ra, s.ra, nb * n_ra));
-        if (n_feats) CU_OK(c, d2h(ho->feats + b0 * n_feats, s.feats, nb * n_feats));
-        CU_OK(c, cudaEventRecord(ev_out[i], c->s_d2h));
+        if (out16)
+            for (int j = 0; j < 7; ++j)
+                if (n_out[j]) { HOST_CU(launch_cast<__half>(s.out[j], s.out16[j], nb * n_out[j], 1, 0, 1.0f, c->s_comp)); c->launches++; }
+        HOST_CU(cudaEventRecord(ev_comp[i], c->s_comp));
+        HOST_CU(cudaStreamWaitEvent(c->s_d2h, ev_comp[i], 0));
+        for (int j = 0; j < 7; ++j) {
+            if (!n_out[j]) continue;
+            const size_t bytes = nb * n_out[j] * osz;
+            down += bytes;
+            HOST_CU(cudaMemcpyAsync(static_cast<uint8_t*>(hdst[j]) + b0 * n_out[j] * osz, out16 ? static_cast<const void*>(s.out16[j]) : static_cast<const void*>(s.out[j]),
+                                    bytes, cudaMemcpyDeviceToHost, c->s_d2h));
+        }
+        HOST_CU(cudaEventRecord(ev_out[i], c->s_d2h));
     }
+#undef HOST_CU
+    // always settle the three streams before returning - also on an error path: the async copies target caller-owned host buffers
     cudaError_t e1 = cudaStreamSynchronize(c->s_h2d), e2 = cudaStreamSynchronize(c->s_comp), e3 = cudaStreamSynchronize(c->s_d2h);
     if (rc != TIM_OK) return rc;
+    if (ce != cudaSuccess) return c->fail(TIM_ERR_CUDA, "tim_forward_host: %s", cudaGetErrorString(ce));
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
         return c->fail(TIM_ERR_CUDA, "tim_forward_host: stream sync failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3)));
+    // precision guard of the folded LayerNorm flow, applied WITHIN this call: if a chunk raised the alarm (rows with |mean| > 8 std),
+    // the results already in the caller's buffers came from the folded path - switch the context to the un-folded flow and redo
+    if (was_folded_ctx && *c->fold_alarm_host) {
+        c->fold_tripped = true;
+        std::fprintf(stderr, "[tim_b200] rows with |mean| > 8 std seen in the residual stream: LayerNorm folding is switched off for this context; "
+                             "this call is recomputed with the un-folded flow\n");
+        return tim_forward_host_ex(c, vis, aud, times, B, T_, Qv, Qa, ho, cpc, in_dtype, out_dtype, stream, h2d_bytes, d2h_bytes);
+    }
     if (h2d_bytes) *h2d_bytes = up;
     if (d2h_bytes) *d2h_bytes = down;
     return TIM_OK;
+}
+
+int tim_forward_host(tim_ctx* c, const float* vis, const float* aud, const float* times, int B, int T_, int Qv, int Qa,
+                     const tim_outputs* ho, int cpc, uint64_t* h2d_bytes, uint64_t* d2h_bytes) {
+    if (!c) return TIM_ERR_INVALID;
+    // no caller stream in this signature: settle the device first (a blocking API can afford it)
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    return tim_forward_host_ex(c, vis, aud, times, B, T_, Qv, Qa, ho, cpc, TIM_FP32, TIM_FP32, nullptr, h2d_bytes, d2h_bytes);
+}
+
+// Blocks until the most recent encoder forward of this context has finished its precision check. Returns 1 if that forward ran
+// with the LayerNorms folded AND saw rows that break the folded path's error bound (its outputs should be recomputed: the context
+// has switched to the un-folded flow, so calling the forward again does that), 0 otherwise.
+int tim_fold_check(tim_ctx* c) {
+    if (!c) return TIM_ERR_INVALID;
+    if (!c->fold_ln || c->fold_tripped || !c->last_folded || !c->fold_event) return 0;
+    CU_OK(c, cudaSetDevice(c->device));
+    CU_OK(c, cudaEventSynchronize(c->fold_event));
+    if (*c->fold_alarm_host) {
+        c->fold_tripped = true;
+        std::fprintf(stderr, "[tim_b200] rows with |mean| > 8 std seen in the residual stream: LayerNorm folding is switched off for this context\n");
+        return 1;
+    }
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------- training leg

@@ -107,12 +107,12 @@ class TIMEngine:
             _lib.check(self.lib.tim_time_mlp_fwd(self._ctx, _ptr(times), _ptr(out), B, T, self._stream()), self._ctx)
         return out
 
-    def _alloc_outputs(self, B: int, Qv: int, Qa: int, *, pinned: bool, want_feats: bool = True):
+    def _alloc_outputs(self, B: int, Qv: int, Qa: int, *, pinned: bool, want_feats: bool = True, dtype=torch.float32):
         cfg = self.cfg
         hc = cfg.head_classes()
         qv = Qv if "visual" in cfg.data_modality else 0
         qa = Qa if "audio" in cfg.data_modality else 0
-        kw = dict(dtype=torch.float32, device="cpu", pin_memory=True) if pinned else dict(dtype=torch.float32, device=self.device)
+        kw = dict(dtype=dtype, device="cpu", pin_memory=True) if pinned else dict(dtype=dtype, device=self.device)
         out: Dict[str, Optional[torch.Tensor]] = {k: None for k in ("verb", "noun", "action", "audio", "reg_v", "reg_a", "feats")}
         if "visual" in cfg.data_modality:
             if hc["verb"]:
@@ -272,24 +272,46 @@ class TIMEngine:
 
     # ------------------------------------------------------------------ forward (host tensors, end to end)
     def forward_host(self, vis, aud, times: torch.Tensor, Qv: int, Qa: int, clips_per_chunk: int = 0,
-                     want_feats: bool = True, out=None):
+                     want_feats: bool = True, out=None, out_dtype=torch.float32):
         """time_mlp + encoder on HOST tensors (pinned for full copy bandwidth); H2D/D2H copies are inside the call.
+        vis / aud: fp32, or the engine's 16-bit operand dtype (a 16-bit host feature bank: bit-identical results on the 16-bit
+        paths, half the H2D bytes, no cast pass). out_dtype: torch.float32 or torch.float16 (logits rounded once on the device).
         Returns (outputs dict of pinned host tensors, h2d_bytes, d2h_bytes)."""
         cfg = self.cfg
         B, T = int(times.shape[0]), int(times.shape[1])
-        for name, t in (("vis", vis), ("aud", aud), ("times", times)):
-            if t is not None and (t.device.type != "cpu" or t.dtype != torch.float32 or not t.is_contiguous()):
-                raise ValueError(f"{name} must be a contiguous fp32 CPU tensor")
+        op = {"fp16": torch.float16, "bf16": torch.bfloat16}.get(self.compute_dtype)
+        feat_dt = None
+        for name, t in (("vis", vis), ("aud", aud)):
+            if t is None:
+                continue
+            if t.device.type != "cpu" or not t.is_contiguous() or t.dtype not in (torch.float32, op):
+                raise ValueError(f"{name} must be a contiguous CPU tensor, fp32 or the engine's 16-bit operand dtype")
+            if feat_dt is not None and t.dtype != feat_dt:
+                raise ValueError("vis and aud must have the same dtype")
+            feat_dt = t.dtype
+        if times.device.type != "cpu" or times.dtype != torch.float32 or not times.is_contiguous():
+            raise ValueError("times must be a contiguous fp32 CPU tensor")
+        if out_dtype not in (torch.float32, torch.float16):
+            raise ValueError("out_dtype must be torch.float32 or torch.float16")
         if out is None:
-            out = self._alloc_outputs(B, Qv, Qa, pinned=True, want_feats=want_feats)
+            out = self._alloc_outputs(B, Qv, Qa, pinned=True, want_feats=want_feats, dtype=out_dtype)
         outs, co = out
+        for v in outs.values():
+            if v is not None and v.dtype != out_dtype:
+                raise ValueError("preallocated outputs do not match out_dtype")
+        in_code = DTYPE_CODES["fp32"] if feat_dt in (None, torch.float32) else DTYPE_CODES[self.compute_dtype]
+        out_code = DTYPE_CODES["fp32"] if out_dtype == torch.float32 else DTYPE_CODES["fp16"]
         up, down = C.c_uint64(0), C.c_uint64(0)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.tim_forward_host(self._ctx, _ptr(vis if cfg.has_visual_input else None),
-                                                 _ptr(aud if cfg.has_audio_input else None), _ptr(times), B, T,
-                                                 int(Qv or 0), int(Qa or 0), C.byref(co), int(clips_per_chunk),
-                                                 C.byref(up), C.byref(down)), self._ctx)
+            _lib.check(self.lib.tim_forward_host_ex(self._ctx, _ptr(vis if cfg.has_visual_input else None),
+                                                    _ptr(aud if cfg.has_audio_input else None), _ptr(times), B, T,
+                                                    int(Qv or 0), int(Qa or 0), C.byref(co), int(clips_per_chunk), in_code, out_code,
+                                                    self._stream(), C.byref(up), C.byref(down)), self._ctx)
         return outs, int(up.value), int(down.value)
+
+    def fold_check(self) -> bool:
+        """Blocks until the last encoder forward's precision check is known; True = recompute it (see tim_fold_check)."""
+        return bool(_lib.check_nonneg(self.lib.tim_fold_check(self._ctx), self._ctx))
 
     # ------------------------------------------------------------------ detection query labelling (SURVEY.md §8f row 2)
     def label_queries(self, queries: torch.Tensor, gt_segs: torch.Tensor, gt_labels: torch.Tensor, iou_threshold: float):
@@ -501,6 +523,8 @@ def _forward_recognition(self, inputs, forward_type, time_encodings=None, num_v_
         return b.engine.time_mlp(inputs)
     if forward_type == "encoder":
         o = b.engine.encoder(inputs[0], inputs[1], time_encodings, num_v_queries, num_a_queries)
+        if b.engine.fold_check():           # the folded-LayerNorm precision guard fired: redo with the un-folded flow, now
+            o = b.engine.encoder(inputs[0], inputs[1], time_encodings, num_v_queries, num_a_queries)
         return (o["verb"], o["noun"], o["action"], o["audio"]), o["feats"]
     raise ValueError(f"unknown forward_type {forward_type!r}")
 
@@ -563,6 +587,8 @@ def _forward_detection(self, inputs, forward_type, feature_times=None, target=No
         a_queries = torch.flatten(a_queries, 0, 1)
     te = b.engine.time_mlp(all_times)
     o = b.engine.encoder(inputs[0], inputs[1], te, nv, na)
+    if b.engine.fold_check():
+        o = b.engine.encoder(inputs[0], inputs[1], te, nv, na)
     cls = (o["verb"], o["noun"], o["action"], o["audio"])
     reg = (o["reg_v"], o["reg_a"])
     return (cls, reg, o["feats"]), (v_offsets, a_offsets), (v_labels, a_labels), (v_queries, a_queries), (v_ious, a_ious)
