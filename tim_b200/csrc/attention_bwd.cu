@@ -40,7 +40,7 @@ template <int HD> struct SwzB {
 // kernel 1: dQ (+ own-key / own-value gradients of query rows, + softmax statistics)
 // ------------------------------------------------------------------------------------------------------------------
 template <typename T, int HD>
-__global__ void __launch_bounds__(AB_WARPS * 32, 1) attn_bwd_dq_kernel(const T* __restrict__ qkv, const T* __restrict__ dO, T* __restrict__ dqkv,
+__global__ void __launch_bounds__(AB_WARPS * 32, 2) attn_bwd_dq_kernel(const T* __restrict__ qkv, const T* __restrict__ dO, T* __restrict__ dqkv,
                                                                        float4* __restrict__ stats, int B, int Ft, int Qt, int H, int tiles_f,
                                                                        int tiles_q, int tiles_per_cta, float qscale) {
     constexpr int CH = HD / 8;
@@ -53,8 +53,10 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) attn_bwd_dq_kernel(const T* 
     uint8_t* sV = sK + Fp * HD * 2;                      // [Fp][HD]
     uint8_t* sQ = sV + Fp * HD * 2;                      // [64][HD]  (reused as the dQ staging tile)
     uint8_t* sD = sQ + AB_BM * HD * 2;                   // [64][HD]  dO tile
-    uint8_t* sKq = sD + AB_BM * HD * 2;                  // [64][HD]  own keys of a query tile
-    uint8_t* sVq = sKq + AB_BM * HD * 2;                 // [64][HD]  own values of a query tile
+    // The own key / value rows of a query tile are NOT staged: they are only used element-wise, in exactly the (row, column) pattern
+    // of this thread's A / C fragments, so each thread reads its 4-byte pieces straight from global memory (every 32-byte sector
+    // is consumed whole by the four lanes of a quad). That keeps the CTA at 2 K/V + 2 tile buffers: two CTAs per SM instead of one
+    // (the first version staged them: 120 KB, 4 warps per SM, 5.9 % warps active, profiles/r02b_ncu_full_attnbwd.csv).
 
     const int item = blockIdx.x;
     const int b = item / H, h = item - b * H;
@@ -93,17 +95,9 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) attn_bwd_dq_kernel(const T* 
                 const T* src = qkv + (tile_base + r) * ld + h * HD + c * 8;
                 cp_async_16(smem_u32(sQ + SW::off(r, c)), src);
                 cp_async_16(smem_u32(sD + SW::off(r, c)), dO + (tile_base + r) * E + h * HD + c * 8);
-                if (qtile) {
-                    cp_async_16(smem_u32(sKq + SW::off(r, c)), src + E);
-                    cp_async_16(smem_u32(sVq + SW::off(r, c)), src + 2 * E);
-                }
             } else {
                 *reinterpret_cast<uint4*>(sQ + SW::off(r, c)) = make_uint4(0, 0, 0, 0);
                 *reinterpret_cast<uint4*>(sD + SW::off(r, c)) = make_uint4(0, 0, 0, 0);
-                if (qtile) {
-                    *reinterpret_cast<uint4*>(sKq + SW::off(r, c)) = make_uint4(0, 0, 0, 0);
-                    *reinterpret_cast<uint4*>(sVq + SW::off(r, c)) = make_uint4(0, 0, 0, 0);
-                }
             }
         }
         cp_async_commit();
@@ -115,6 +109,10 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) attn_bwd_dq_kernel(const T* 
             const int g = lane >> 2, tq = lane & 3;
             const int nt = Fp / 8;
             const int lm = lane >> 3, lr = lane & 7;
+            const int r_lo = wr0 + g, r_hi = wr0 + g + 8;
+            // this thread's own-key / own-value pieces: rows r_lo / r_hi (clamped inside the tile; results of padded rows are unused)
+            const T* own_lo = qkv + (tile_base + min(r_lo, nrows - 1)) * ld + E + h * HD + tq * 2;
+            const T* own_hi = qkv + (tile_base + min(r_hi, nrows - 1)) * ld + E + h * HD + tq * 2;
 
             // ---- S = Q K_f^T and dP = dO V_f^T (+ the own-key score q.k_own and dP_self = dO.v_own of query tiles) ----
             float sc[NT_MAX][4], dp[NT_MAX][4];
@@ -131,9 +129,16 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) attn_bwd_dq_kernel(const T* 
                 ldmatrix_x4(smem_u32(sQ + SW::off(arow, achunk)), a[0], a[1], a[2], a[3]);
                 ldmatrix_x4(smem_u32(sD + SW::off(arow, achunk)), ad[0], ad[1], ad[2], ad[3]);
                 if (qtile) {
+                    // same element pattern as the A fragments: [0] (r_lo, 16kk + 2tq), [1] (r_hi, ..), [2] (r_lo, 16kk + 8 + 2tq), [3] (r_hi, ..)
                     uint32_t kq[4], vq[4];
-                    ldmatrix_x4(smem_u32(sKq + SW::off(arow, achunk)), kq[0], kq[1], kq[2], kq[3]);
-                    ldmatrix_x4(smem_u32(sVq + SW::off(arow, achunk)), vq[0], vq[1], vq[2], vq[3]);
+                    kq[0] = __ldg(reinterpret_cast<const unsigned int*>(own_lo + 16 * kk));
+                    kq[1] = __ldg(reinterpret_cast<const unsigned int*>(own_hi + 16 * kk));
+                    kq[2] = __ldg(reinterpret_cast<const unsigned int*>(own_lo + 16 * kk + 8));
+                    kq[3] = __ldg(reinterpret_cast<const unsigned int*>(own_hi + 16 * kk + 8));
+                    vq[0] = __ldg(reinterpret_cast<const unsigned int*>(own_lo + E + 16 * kk));
+                    vq[1] = __ldg(reinterpret_cast<const unsigned int*>(own_hi + E + 16 * kk));
+                    vq[2] = __ldg(reinterpret_cast<const unsigned int*>(own_lo + E + 16 * kk + 8));
+                    vq[3] = __ldg(reinterpret_cast<const unsigned int*>(own_hi + E + 16 * kk + 8));
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float2 qa = unpack2<T>(a[i]), ka = unpack2<T>(kq[i]);
@@ -212,7 +217,6 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) attn_bwd_dq_kernel(const T* 
                 }
             }
             const float dss0 = ps0 * (dps0 - D0), dss1 = ps1 * (dps1 - D1);      // own-key dS of query rows
-            const int r_lo = wr0 + g, r_hi = wr0 + g + 8;
             if (tq == 0) {
                 if (r_lo < nrows) stats[static_cast<size_t>(h) * Mtot + tile_base + r_lo] = make_float4(m0, inv0, D0, 0.0f);
                 if (r_hi < nrows) stats[static_cast<size_t>(h) * Mtot + tile_base + r_hi] = make_float4(m1, inv1, D1, 0.0f);
@@ -260,8 +264,8 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 1) attn_bwd_dq_kernel(const T* 
                     float* o = half ? o1 : o0;
                     const int chunk = jn + half;
                     if (qtile) {
-                        const float2 klo = unpack2<T>(*reinterpret_cast<const uint32_t*>(sKq + SW::off(r_lo, chunk) + tq * 4));
-                        const float2 khi = unpack2<T>(*reinterpret_cast<const uint32_t*>(sKq + SW::off(r_hi, chunk) + tq * 4));
+                        const float2 klo = unpack2<T>(__ldg(reinterpret_cast<const unsigned int*>(own_lo + 8 * chunk)));     // L1 / L2 hit: read above
+                        const float2 khi = unpack2<T>(__ldg(reinterpret_cast<const unsigned int*>(own_hi + 8 * chunk)));
                         o[0] += dss0 * klo.x; o[1] += dss0 * klo.y;
                         o[2] += dss1 * khi.x; o[3] += dss1 * khi.y;
                     }
@@ -411,7 +415,7 @@ __device__ __forceinline__ void dkv_pass(const T* __restrict__ qkv, const T* __r
 }
 
 template <typename T, int HD>
-__global__ void __launch_bounds__(KV_WARPS * 32, 1) attn_bwd_dkv_kernel(const T* __restrict__ qkv, const T* __restrict__ dO, T* __restrict__ dqkv,
+__global__ void __launch_bounds__(KV_WARPS * 32, 2) attn_bwd_dkv_kernel(const T* __restrict__ qkv, const T* __restrict__ dO, T* __restrict__ dqkv,
                                                                         const float4* __restrict__ stats, int B, int Ft, int Qt, int H) {
     constexpr int CH = HD / 8;
     using SW = SwzB<HD>;
@@ -437,12 +441,11 @@ __global__ void __launch_bounds__(KV_WARPS * 32, 1) attn_bwd_dkv_kernel(const T*
         }
     }
     // (the first chunk's cp.async group waits for these as well)
-    if constexpr (HD <= 128) {
-        dkv_pass<T, HD, true, true>(qkv, dO, dqkv, stats, sK, sV, sQc, sDc, sSt, B, Ft, Qt, H, b, h, Fp);
-    } else {
-        dkv_pass<T, HD, false, true>(qkv, dO, dqkv, stats, sK, sV, sQc, sDc, sSt, B, Ft, Qt, H, b, h, Fp);
-        dkv_pass<T, HD, true, false>(qkv, dO, dqkv, stats, sK, sV, sQc, sDc, sSt, B, Ft, Qt, H, b, h, Fp);
-    }
+    // dV_f and dK_f are produced by DIFFERENT CTAs (blockIdx.y): with both accumulators in one thread the kernel needed 255
+    // registers and ran one CTA (8 warps) per SM at 30 % tensor-pipe (profiles/r02b_ncu_full_attnbwd.csv); one accumulator set fits
+    // 128 registers, two CTAs per SM, and the two passes of a (clip, head) run concurrently. Cost: S^T is computed twice.
+    if (blockIdx.y == 0) dkv_pass<T, HD, false, true>(qkv, dO, dqkv, stats, sK, sV, sQc, sDc, sSt, B, Ft, Qt, H, b, h, Fp);
+    else dkv_pass<T, HD, true, false>(qkv, dO, dqkv, stats, sK, sV, sQc, sDc, sSt, B, Ft, Qt, H, b, h, Fp);
 }
 
 template <typename T, int HD>
@@ -452,14 +455,14 @@ cudaError_t launch_bwd_hd(const T* qkv, const T* dO, T* dqkv, float4* stats, int
     if (items <= 0) return cudaSuccess;
     if (items > 0x7fffffffLL) return cudaErrorInvalidValue;
     {
-        const size_t smem = static_cast<size_t>(2 * Fp + 4 * AB_BM) * HD * 2;
+        const size_t smem = static_cast<size_t>(2 * Fp + 2 * AB_BM) * HD * 2;
         if (smem > 227 * 1024) return cudaErrorInvalidValue;
         auto kern = attn_bwd_dq_kernel<T, HD>;
         static SmemAttrCache cache;
         if (cudaError_t e = ensure_dynamic_smem(kern, smem, cache); e != cudaSuccess) return e;
         const int tiles_f = (Ft + AB_BM - 1) / AB_BM, tiles_q = (Qt + AB_BM - 1) / AB_BM;
         const int tiles = tiles_f + tiles_q;
-        int nsplit = static_cast<int>((148LL * 4 + items - 1) / items);
+        int nsplit = static_cast<int>((148LL * 2 * 4 + items - 1) / items);
         if (nsplit < 1) nsplit = 1;
         if (nsplit > tiles) nsplit = tiles;
         const int tiles_per_cta = (tiles + nsplit - 1) / nsplit;
@@ -473,7 +476,7 @@ cudaError_t launch_bwd_hd(const T* qkv, const T* dO, T* dqkv, float4* stats, int
         auto kern = attn_bwd_dkv_kernel<T, HD>;
         static SmemAttrCache cache;
         if (cudaError_t e = ensure_dynamic_smem(kern, smem, cache); e != cudaSuccess) return e;
-        kern<<<static_cast<unsigned>(items), KV_WARPS * 32, smem, s>>>(qkv, dO, dqkv, stats, B, Ft, Qt, H);
+        kern<<<dim3(static_cast<unsigned>(items), 2), KV_WARPS * 32, smem, s>>>(qkv, dO, dqkv, stats, B, Ft, Qt, H);
     }
     return cudaGetLastError();
 }

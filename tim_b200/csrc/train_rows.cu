@@ -6,6 +6,8 @@
 // What they replace: the autograd nodes torch records for  nn.LayerNorm / nn.GELU / nn.ReLU / torch.cat / expand / bias adds  of
 //   recognition/.../models/tim.py:66-74, helpers/encodings.py:140-251, helpers/transformers.py:92-111, helpers/head.py
 // when recognition/scripts/train.py:354-366 (detection/scripts/train.py:372-384) runs backward().
+#include <type_traits>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -16,9 +18,27 @@ constexpr int RW = 8;                      // warps (rows in flight) per CTA
 constexpr float kInvSqrt2 = 0.70710678118654752440f;
 constexpr float kInvSqrt2Pi = 0.39894228040143267794f;
 
-__device__ __forceinline__ float gelu_grad(float x) {          // d/dx [x Phi(x)] = Phi(x) + x phi(x)
+__device__ __forceinline__ float gelu_grad(float x) {          // d/dx [x Phi(x)] = Phi(x) + x phi(x)   (fp32 parity path)
     const float cdf = 0.5f * (1.0f + erff(x * kInvSqrt2));
     return fmaf(x * kInvSqrt2Pi, __expf(-0.5f * x * x), cdf);
+}
+// 16-bit paths: Phi(x) from the same degree-6 fit of log2 erfc(|x| / sqrt2) the forward's gelu_erf_fast uses (ptx.cuh; relative
+// error 3e-5 of erfc), phi(x) = 2^(-x^2 log2(e) / 2) / sqrt(2 pi): two MUFU.EX2 and ~16 FMAs, no erff() / expf() call sequences - the
+// first version of act_bwd_kernel was instruction-bound on those (781 us for 2.5 GB, profiles/r02b_launches_train_cfg2.csv).
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+    const float ax = fabsf(x);
+    const float u = fminf(ax, 5.656854249f);
+    float p = 2.513894565e-05f;
+    p = fmaf(p, u, -6.454259847e-04f);
+    p = fmaf(p, u, 7.399560496e-03f);
+    p = fmaf(p, u, -5.173896880e-02f);
+    p = fmaf(p, u, -4.605998700e-01f);
+    p = fmaf(p, u, -1.150469307e+00f);
+    p = fmaf(p, u, -4.401278411e-05f);
+    const float h = 0.5f * ex2_approx(p);                      // 0.5 erfc(|x| / sqrt2) = Phi(-|x|)
+    const float cdf = x >= 0.0f ? 1.0f - h : h;
+    const float pdf = kInvSqrt2Pi * ex2_approx(-0.72134752044448170368f * x * x);
+    return fmaf(x, pdf, cdf);
 }
 
 template <typename T> __device__ __forceinline__ void load4(const T* p, float (&v)[4]);
@@ -159,7 +179,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const TD* __restrict__ d, 
         load4<TD>(d + off, dv); load4<TA>(a + off, av);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            o[j] = MODE == 0 ? dv[j] * gelu_grad(av[j]) : (av[j] > 0.0f ? dv[j] : 0.0f);
+            o[j] = MODE == 0 ? dv[j] * (sizeof(TA) == 2 ? gelu_grad_fast(av[j]) : gelu_grad(av[j])) : (av[j] > 0.0f ? dv[j] : 0.0f);
             if (sizeof(TO) == 2) o[j] = to_float<TO>(from_float<TO>(o[j]));     // the bias gradient sums what the GEMMs will see
             acc[j] += o[j];
         }
@@ -168,6 +188,36 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const TD* __restrict__ d, 
     if (dbias) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) atomicAdd(dbias + c + j, acc[j]);
+    }
+}
+
+// all-16-bit version (the FFN's GELU backward, [M, FF]): 8 columns = 16 bytes per thread and row, two rows in flight
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) act_bwd16_kernel(const T* __restrict__ d, const T* __restrict__ a, T* __restrict__ out, int rows, int cols,
+                                                        float* __restrict__ dbias) {
+    const int c = (blockIdx.x * 256 + threadIdx.x) * 8;
+    if (c >= cols) return;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+        const size_t off = static_cast<size_t>(r) * cols + c;
+        const uint4 dq = *reinterpret_cast<const uint4*>(d + off);
+        const uint4 aq = *reinterpret_cast<const uint4*>(a + off);
+        const uint32_t dw[4] = {dq.x, dq.y, dq.z, dq.w}, aw[4] = {aq.x, aq.y, aq.z, aq.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 dv = unpack2<T>(dw[j]), av = unpack2<T>(aw[j]);
+            const float o0 = MODE == 0 ? dv.x * gelu_grad_fast(av.x) : (av.x > 0.0f ? dv.x : 0.0f);
+            const float o1 = MODE == 0 ? dv.y * gelu_grad_fast(av.y) : (av.y > 0.0f ? dv.y : 0.0f);
+            ow[j] = pack2<T>(o0, o1);
+            const float2 q = unpack2<T>(ow[j]);                 // the bias gradient sums what the GEMMs will see
+            acc[2 * j] += q.x; acc[2 * j + 1] += q.y;
+        }
+        *reinterpret_cast<uint4*>(out + off) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+    if (dbias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(dbias + c + j, acc[j]);
     }
 }
 
@@ -202,6 +252,24 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, in
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) atomicAdd(out + c + j, acc[j]);
+}
+
+// plain [rows, ncols] 16-bit matrix (the in_proj bias gradient over dqkv): 8 columns = 16 bytes per thread and row, no index
+// arithmetic in the loop (the generic kernel above spends a 64-bit division per row: 62 % issue-active at 2.2 TB/s)
+template <typename T>
+__global__ void __launch_bounds__(256) colsum16_kernel(const T* __restrict__ x, int ld, int rows, int ncols, float* __restrict__ out) {
+    const int c = (blockIdx.x * 256 + threadIdx.x) * 8;
+    if (c >= ncols) return;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const T* p = x + static_cast<size_t>(blockIdx.y) * ld + c;
+    const size_t step = static_cast<size_t>(gridDim.y) * ld;
+    for (int r = blockIdx.y; r < rows; r += gridDim.y, p += step) {
+        const uint4 q = *reinterpret_cast<const uint4*>(p);
+        const float2 a = unpack2<T>(q.x), b = unpack2<T>(q.y), c2 = unpack2<T>(q.z), d2 = unpack2<T>(q.w);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c2.x; acc[5] += c2.y; acc[6] += d2.x; acc[7] += d2.y;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(out + c + j, acc[j]);
 }
 
 // scalar version for rows whose width / pitch is not a multiple of 4 (class counts such as 97 or 3806): one thread per column
@@ -425,6 +493,17 @@ template <typename TD, typename TA, typename TO>
 cudaError_t launch_act_bwd(int mode, const TD* d, const TA* a, TO* out, int rows, int cols, float* dbias, cudaStream_t s) {
     if (rows <= 0 || cols <= 0) return cudaSuccess;
     if (cols & 3) return cudaErrorInvalidValue;
+    if constexpr (std::is_same<TD, TA>::value && std::is_same<TD, TO>::value && sizeof(TD) == 2) {
+        if ((cols & 7) == 0 && ((reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+            const int gx = (cols + 2047) / 2048;
+            long long gy = (148 * 8 + gx - 1) / gx;
+            if (gy > rows) gy = rows;
+            const dim3 grid(gx, static_cast<unsigned>(gy));
+            if (mode == 0) act_bwd16_kernel<TD, 0><<<grid, 256, 0, s>>>(d, a, out, rows, cols, dbias);
+            else act_bwd16_kernel<TD, 1><<<grid, 256, 0, s>>>(d, a, out, rows, cols, dbias);
+            return cudaGetLastError();
+        }
+    }
     const dim3 grid = col_grid(cols, rows);
     if (mode == 0) act_bwd_kernel<TD, TA, TO, 0><<<grid, 256, 0, s>>>(d, a, out, rows, cols, dbias);
     else act_bwd_kernel<TD, TA, TO, 1><<<grid, 256, 0, s>>>(d, a, out, rows, cols, dbias);
@@ -459,6 +538,15 @@ cudaError_t launch_colsum(const T* x, int ld, int G, int group_rows, int row_off
         if (gy > R) gy = R;
         colsum_scalar_kernel<T><<<dim3(gx, static_cast<unsigned>(gy)), 256, 0, s>>>(x + static_cast<size_t>(row_off) * ld + col_off, ld, R, ncols, out);
         return cudaGetLastError();
+    }
+    if constexpr (sizeof(T) == 2) {
+        if (G == 1 && (ncols & 7) == 0 && (ld & 7) == 0 && (col_off & 7) == 0) {
+            const int gx = (ncols + 2047) / 2048;
+            long long gy = (148 * 8 + gx - 1) / gx;
+            if (gy > R) gy = R;
+            colsum16_kernel<T><<<dim3(gx, static_cast<unsigned>(gy)), 256, 0, s>>>(x + static_cast<size_t>(row_off) * ld + col_off, ld, R, ncols, out);
+            return cudaGetLastError();
+        }
     }
     colsum_kernel<T><<<col_grid(ncols, static_cast<long long>(G) * R), 256, 0, s>>>(x, ld, G, group_rows, row_off, R, col_off, ncols, out);
     return cudaGetLastError();
