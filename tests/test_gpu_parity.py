@@ -25,6 +25,24 @@ TOL = {"fp32": 1e-5, "fp16": 1e-3, "bf16": 1e-2}
 # few-class heads on tiny widths have small-norm logits; their fp16 bound is looser (cancellation, not kernel error)
 TOL_SMALL = {"fp32": 1e-5, "fp16": 3e-3, "bf16": 2e-2}
 DT = {"fp32": 0, "bf16": 1, "fp16": 2}
+REAL_WIDTH_CASES = ("recog_cfg1", "recog_cfg2", "det_cfg4")
+
+
+def _record_forward(tag, errs):
+    """measured per-case errors -> gpurun_out/forward_parity.json (copied into profiles/ by hand)"""
+    import json
+    import os
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if not os.path.isdir(d):
+        return
+    p = os.path.join(d, "forward_parity.json")
+    try:
+        blob = json.load(open(p))
+    except Exception:
+        blob = {}
+    blob[tag] = {"worst_rel_l2": max(v["rel_l2"] for v in errs.values()), "worst_row_centered": max(v["worst_row_centered"] for v in errs.values()),
+                 "per_tensor": {k: round(v["rel_l2"], 9) for k, v in errs.items()}}
+    json.dump(blob, open(p, "w"), indent=1, sort_keys=True)
 
 
 @pytest.fixture(scope="module")
@@ -66,13 +84,23 @@ def engine_run(cfg, sd, inp, Qv, Qa, dt, host=False, chunks=0):
 def test_golden_vectors(lib, name, dt):
     cfg, sd, inp, gold, c = load_case(name)
     res = engine_run(cfg, sd, inp, c["Qv"], c["Qa"], dt)
-    tol = TOL if name == "recog_cfg1" else TOL_SMALL
+    # the real-width cases (BASELINE.json configs[0], [1], [3]) are held to the stated tolerance; the d_model = 64 models sum few
+    # terms per output, so their 16-bit bound is looser (measured per case: profiles/*_forward_parity.json)
+    tol = TOL if name in REAL_WIDTH_CASES else TOL_SMALL
     for k in ("verb", "noun", "action", "audio", "reg_v", "reg_a"):
         assert (res[k] is None) == (k not in gold), k
+    errs = {}
     for k, g in gold.items():
         assert res[k].shape == g.shape, (k, res[k].shape, g.shape)
         e = rel_l2(res[k], g)
+        # per-row check (a constant logit bias must not hide errors of single query rows): worst row, centred
+        a2, g2 = res[k].reshape(-1, g.shape[-1]).astype(np.float64), g.reshape(-1, g.shape[-1]).astype(np.float64)
+        den = np.maximum(np.linalg.norm(g2 - g2.mean(1, keepdims=True), axis=1), 1e-12 + 1e-6 * np.linalg.norm(g2, axis=1))
+        row = float((np.linalg.norm(a2 - g2, axis=1) / den).max()) if g.shape[-1] > 2 else e
+        errs[k] = {"rel_l2": e, "worst_row_centered": row}
         assert e <= tol[dt], f"{name}/{k} [{dt}]: rel-L2 {e:.3e} > {tol[dt]:.0e}"
+        assert row <= 8 * tol[dt], f"{name}/{k} [{dt}]: worst row {row:.3e} > {8 * tol[dt]:.0e}"
+    _record_forward(f"{name}/{dt}", errs)
 
 
 @pytest.mark.parametrize("name", ["recog_cfg1", "recog_av_small", "det_av"])
