@@ -188,13 +188,13 @@ __global__ void __launch_bounds__(AB_WARPS * 32, 2) attn_bwd_dq_kernel(const T* 
 #pragma unroll
             for (int j = 0; j < NT_MAX; ++j) {
                 if (j < nt) {
-                    sc[j][0] = exp2f(sc[j][0] - m0); sc[j][1] = exp2f(sc[j][1] - m0);
-                    sc[j][2] = exp2f(sc[j][2] - m1); sc[j][3] = exp2f(sc[j][3] - m1);
+                    sc[j][0] = ex2_approx(sc[j][0] - m0); sc[j][1] = ex2_approx(sc[j][1] - m0);
+                    sc[j][2] = ex2_approx(sc[j][2] - m1); sc[j][3] = ex2_approx(sc[j][3] - m1);
                     l0 += sc[j][0] + sc[j][1]; l1 += sc[j][2] + sc[j][3];
                 }
             }
             l0 = quad_sum(l0); l1 = quad_sum(l1);
-            float ps0 = qtile ? exp2f(self0 - m0) : 0.0f, ps1 = qtile ? exp2f(self1 - m1) : 0.0f;
+            float ps0 = qtile ? ex2_approx(self0 - m0) : 0.0f, ps1 = qtile ? ex2_approx(self1 - m1) : 0.0f;
             const float inv0 = 1.0f / (l0 + ps0), inv1 = 1.0f / (l1 + ps1);
             ps0 *= inv0; ps1 *= inv1;
             // ---- D = sum_j P_ij dP_ij (+ own key), dS = P o (dP - D) ----
@@ -365,8 +365,8 @@ __device__ __forceinline__ void dkv_pass(const T* __restrict__ qkv, const T* __r
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             const float4 s0 = sSt[8 * j + 2 * tq], s1 = sSt[8 * j + 2 * tq + 1];     // (max, 1 / l, D) of the two rows this thread holds
-            const float p00 = klo_ok ? exp2f(st[j][0] - s0.x) * s0.y : 0.0f, p01 = klo_ok ? exp2f(st[j][1] - s1.x) * s1.y : 0.0f;
-            const float p10 = khi_ok ? exp2f(st[j][2] - s0.x) * s0.y : 0.0f, p11 = khi_ok ? exp2f(st[j][3] - s1.x) * s1.y : 0.0f;
+            const float p00 = klo_ok ? ex2_approx(st[j][0] - s0.x) * s0.y : 0.0f, p01 = klo_ok ? ex2_approx(st[j][1] - s1.x) * s1.y : 0.0f;
+            const float p10 = khi_ok ? ex2_approx(st[j][2] - s0.x) * s0.y : 0.0f, p11 = khi_ok ? ex2_approx(st[j][3] - s1.x) * s1.y : 0.0f;
             if (DO_V) {
                 pT[j >> 1][(j & 1) * 2 + 0] = pack2<T>(p00, p01);
                 pT[j >> 1][(j & 1) * 2 + 1] = pack2<T>(p10, p11);
