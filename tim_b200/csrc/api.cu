@@ -100,6 +100,7 @@ struct tim_ctx {
     int attn_version = 2;       // 2: tcgen05 attention where the shape allows, 1: warp-MMA attention only (TIM_B200_ATTN=1)
     bool fold_ln = false;       // encoder LayerNorms folded into the GEMMs around them (16-bit path, CTA-pair kernel shapes; TIM_B200_FOLD=0 disables)
     bool fold_dirty = true;     // a weight changed since the folded copies were made
+    bool planes = true;         // folded flow keeps the residual stream as two 16-bit planes (mode 7); TIM_B200_PLANES=0: fp32 + 16-bit copy (mode 5)
     // precision guard of the folded path: the finalize kernel flags rows with |mean| > 8 std (relative error of the folded
     // operand x8); the flag is copied to pinned host memory at the end of every forward and read, without a synchronisation,
     // at the start of the next one - from then on this context takes the un-folded flow.
@@ -236,6 +237,19 @@ int make_tmap_2d(tim_ctx* c, CUtensorMap* tm, const void* base, CUtensorMapDataT
     if (r != CUDA_SUCCESS)
         return c->fail(TIM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) inner=%lld rows=%lld pitch=%lld box=(%d,%d)", static_cast<int>(r),
                        inner, rows, pitch_bytes, box_inner, box_rows);
+    return TIM_OK;
+}
+// 16-bit plane tile map of the two-plane residual stream: box (32 columns = 64 bytes, 32 rows), 64-byte swizzle
+int make_tmap_plane(tim_ctx* c, CUtensorMap* tm, const void* base, CUtensorMapDataType dt, long long inner, long long rows, long long pitch_bytes) {
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (pitch_bytes & 15) != 0)
+        return c->fail(TIM_ERR_INVALID, "TMA map: base / pitch must be 16-byte aligned");
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(inner), static_cast<cuuint64_t>(rows)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(pitch_bytes)};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = c->encode(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return c->fail(TIM_ERR_CUDA, "cuTensorMapEncodeTiled(plane) failed (%d) inner=%lld rows=%lld", static_cast<int>(r), inner, rows);
     return TIM_OK;
 }
 // 3-D map (inner elements, rows of a group, groups) with explicit pitches; 16-bit elements, box (64, box_rows, 1), 128-byte swizzle.
@@ -378,6 +392,7 @@ int build_weights(tim_ctx* c) {
     c->fold_ln = g.compute_dtype != TIM_FP32 && c->gemm_version >= 2 && c->L > 0 && E <= 2048 && umma2_supported(1, 3 * E, E) &&
                  umma2_supported(1, E, E) && umma2_supported(1, FF, E) && umma2_supported(1, E, FF);
     if (const char* fv = std::getenv("TIM_B200_FOLD")) if (std::atoi(fv) == 0) c->fold_ln = false;
+    if (const char* pv = std::getenv("TIM_B200_PLANES")) c->planes = std::atoi(pv) != 0;
     if (c->fold_ln) {
         TIM_TRY(dev_alloc(c, reinterpret_cast<void**>(&c->fold_alarm_dev), sizeof(int)));
         if (cudaMemset(c->fold_alarm_dev, 0, sizeof(int)) != cudaSuccess ||
@@ -543,15 +558,23 @@ int refold_weights(tim_ctx* c, cudaStream_t s) {
 //   mode 5 (producer): out32 [M,N] fp32 = A W^T + bias + R(resid), out16 = its 16-bit copy, opart = its partial row sums;
 //                      R = LayerNorm-on-read with (rstats, rgamma, rbeta) or the identity when rstats == nullptr
 //   mode 6 (consumer): out16 [M,N] = act(rstd * (A Wf^T - mean * cs) + bwf) with (mean, rstd) = rstats[row]
+//   mode 7 (producer, two-plane residual stream): (out16, out_lo) = planes of  A W^T + bias + R(res_hi + res_lo); opart as mode 5
 template <typename T>
 int run_fold_gemm(tim_ctx* c, int mode, int act, const void* A, int M, int N, int K, const CUtensorMap& tmB, const float* bias,
                   float* out32, void* out16, const float* resid, const float2* rstats, const float* rgamma, const float* rbeta,
-                  float2* opart, const float* cs, cudaStream_t s) {
+                  float2* opart, const float* cs, cudaStream_t s, const void* res_hi = nullptr, const void* res_lo = nullptr,
+                  void* out_lo = nullptr) {
     Umma2Params q;
     std::memset(&q, 0, sizeof(q));
     TIM_TRY(make_tmap_2d(c, &q.tmA, A, op_dtype(c), 2, K, M, static_cast<long long>(K) * 2, 64, 128));
     q.tmB = tmB;
-    if (mode == 5) {
+    if (mode == 7) {
+        const long long pitch = static_cast<long long>(N) * 2;
+        TIM_TRY(make_tmap_plane(c, &q.tmOut, out16, op_dtype(c), N, M, pitch));
+        TIM_TRY(make_tmap_plane(c, &q.tmOutLo, out_lo, op_dtype(c), N, M, pitch));
+        TIM_TRY(make_tmap_plane(c, &q.tmRes, res_hi, op_dtype(c), N, M, pitch));
+        TIM_TRY(make_tmap_plane(c, &q.tmResLo, res_lo, op_dtype(c), N, M, pitch));
+    } else if (mode == 5) {
         TIM_TRY(make_tmap_2d(c, &q.tmOut, out32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, N, M, static_cast<long long>(N) * 4, 32, 32));
         TIM_TRY(make_tmap_2d(c, &q.tmRes, resid, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, N, M, static_cast<long long>(N) * 4, 32, 32));
         TIM_TRY(make_tmap_2d(c, &q.tmOut16, out16, op_dtype(c), 2, N, M, static_cast<long long>(N) * 2, 64, 32));
@@ -563,6 +586,7 @@ int run_fold_gemm(tim_ctx* c, int mode, int act, const void* A, int M, int N, in
     LAUNCH_C(c, mode == 6 ? 5 : 6, 2.0 * M * N * K, s, launch_linear_umma2<T>(q, mode, act, c->num_sms, s));
     return TIM_OK;
 }
+static_assert(sizeof(Umma2Params) <= 4000, "kernel parameter space");
 
 template <typename T>
 int time_mlp_impl(tim_ctx* c, const float* times, float* out, int B, int T_, cudaStream_t s, uint8_t* ws_base, size_t* ws_need) {
@@ -650,6 +674,12 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
     const size_t regrows = static_cast<size_t>(B) * (qp.Qv > qp.Qa ? qp.Qv : qp.Qa);
     a.take(&r1, g.variant == TIM_DETECTION ? regrows * (E / 2) * sizeof(T) : 0);
     a.take(&r2, g.variant == TIM_DETECTION ? regrows * (E / 2) * sizeof(T) : 0);
+    // two-plane residual stream of the folded flow: (x16, xlo) = tokens / z2, (zhi, zlo) = z1
+    T *xlo, *zhi, *zlo;
+    const bool planes_ws = !f32 && c->fold_ln && c->planes;
+    a.take(&xlo, planes_ws ? M * E * sizeof(T) : 0);
+    a.take(&zhi, planes_ws ? M * E * sizeof(T) : 0);
+    a.take(&zlo, planes_ws ? M * E * sizeof(T) : 0);
     float2 *stats, *part;
     a.take(&stats, f32 ? 0 : M * sizeof(float2));
     const size_t nparts = 2 * static_cast<size_t>((E + 255) / 256);       // per-tile partial row sums of the folded-LayerNorm GEMMs
@@ -696,6 +726,17 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
     ap.te = te; ap.n_groups = qp.n_groups;
     for (int i = 0; i < qp.n_groups; ++i) ap.groups[i] = qp.groups[i];
     ap.Qt = Qt; ap.x32 = x32; ap.x16 = f32 ? nullptr : x16;
+    bool folded = false;
+    if constexpr (!f32) {
+        if (c->fold_ln && !c->fold_tripped && *c->fold_alarm_host) {
+            c->fold_tripped = true;
+            std::fprintf(stderr, "[tim_b200] rows with |mean| > 8 std seen in the residual stream: LayerNorm folding is switched off "
+                                 "for this context (un-folded LayerNorm-on-read flow from now on)\n");
+        }
+        folded = c->fold_ln && !c->fold_tripped;
+    }
+    const bool planes = folded && planes_ws;
+    ap.xlo = planes ? xlo : nullptr;
     LAUNCH_C(c, 3, 0.0, s, launch_assemble<T>(ap, s));
 
     // ---- encoder layers (post-LN): x = LN1(x + out_proj(attn(in_proj(x)))); x = LN2(x + W2 gelu(W1 x)) ----
@@ -707,14 +748,7 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
     AttnUmmaParams attn_p;
     bool attn_umma = false;
     if constexpr (!f32) TIM_TRY(prepare_attention<T>(c, &attn_p, &attn_umma, qkv, att, B, Ft, Qt));
-    bool folded = false;
     if constexpr (!f32) {
-        if (c->fold_ln && !c->fold_tripped && *c->fold_alarm_host) {
-            c->fold_tripped = true;
-            std::fprintf(stderr, "[tim_b200] rows with |mean| > 8 std seen in the residual stream: LayerNorm folding is switched off "
-                                 "for this context (un-folded LayerNorm-on-read flow from now on)\n");
-        }
-        folded = c->fold_ln && !c->fold_tripped;
         if (folded && c->fold_dirty) TIM_TRY(refold_weights<T>(c, s));
     }
     for (int l = 0; l < c->L; ++l) {
@@ -750,6 +784,21 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
             TIM_TRY(run_linear<T>(c, xin, E, ly.lin1, plain_rows(Mi), epi(hid, FF, f32, ACT_GELU), s));
             TIM_TRY(run_linear<T>(c, hid, FF, ly.lin2, plain_rows(Mi), epi(z, E, true, ACT_NONE, x32, E), s));
             LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(z, E, ly.n2g, ly.n2b, x32, E, x16o, E, Mi, E, s));
+        } else if (planes) {
+            // the folded flow on the two-plane residual stream (mode 7): (x16, xlo) hold the tokens / z2 of the previous layer,
+            // (zhi, zlo) receive z1; the hi planes are the A operands of the consumer GEMMs. Same statistics protocol as below.
+            TIM_TRY(run_fold_gemm<T>(c, 7, ACT_NONE, att, Mi, E, E, ly.out_proj.tmB2, ly.out_proj.bias, nullptr, zhi, nullptr, l > 0 ? stats : nullptr,
+                                     l > 0 ? c->layers[l - 1].n2g : nullptr, l > 0 ? c->layers[l - 1].n2b : nullptr, part, nullptr, s, x16, xlo, zlo));
+            LAUNCH_C(c, 2, 0.0, s, launch_row_stats_finalize(part, static_cast<int>(nparts), E, stats, Mi, 64.0f, c->fold_alarm_dev, s));
+            TIM_TRY(run_fold_gemm<T>(c, 6, ACT_GELU, zhi, Mi, FF, E, ly.lin1.tmB2f, ly.lin1.bwf, nullptr, hid, nullptr, stats, nullptr, nullptr,
+                                     nullptr, ly.lin1.cs, s));
+            TIM_TRY(run_fold_gemm<T>(c, 7, ACT_NONE, hid, Mi, E, FF, ly.lin2.tmB2, ly.lin2.bias, nullptr, x16, nullptr, stats, ly.n1g, ly.n1b, part, nullptr, s,
+                                     zhi, zlo, xlo));
+            if (l < c->L - 1) LAUNCH_C(c, 2, 0.0, s, launch_row_stats_finalize(part, static_cast<int>(nparts), E, stats, Mi, 64.0f, c->fold_alarm_dev, s));
+            // the last layer's norm2 feeds the heads: over the query rows only, in place on the hi plane (each row is read whole first)
+            if (l == c->L - 1 && Mq)
+                LAUNCH_C(c, 2, 0.0, s, launch_layernorm_planes<T>(x16 + Mf * E, xlo + Mf * E, E, ly.n2g, ly.n2b, nullptr, 0, x16 + Mf * E, E,
+                                                                  static_cast<int>(Mq), E, s));
         } else if (folded) {
             // `stats` holds (mean, rstd) of the rows whose LayerNorm is pending: z2 of the previous layer here ...
             // z1 = att Wo^T + bo + LN2_prev(z2_prev)   -> z (fp32), x16 (16-bit copy), partial sums
@@ -786,7 +835,8 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
     if constexpr (!f32) {
         if (c->L > 0 && o->feats && Mf) {
             Layer& ly = c->layers[c->L - 1];
-            LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(x32, E, ly.n2g, ly.n2b, o->feats, E, static_cast<T*>(nullptr), 0, static_cast<int>(Mf), E, s));
+            if (planes) LAUNCH_C(c, 2, 0.0, s, launch_layernorm_planes<T>(x16, xlo, E, ly.n2g, ly.n2b, o->feats, E, static_cast<T*>(nullptr), 0, static_cast<int>(Mf), E, s));
+            else LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(x32, E, ly.n2g, ly.n2b, o->feats, E, static_cast<T*>(nullptr), 0, static_cast<int>(Mf), E, s));
             feats_done = true;
         }
     }

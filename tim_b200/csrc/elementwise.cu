@@ -169,6 +169,7 @@ __global__ void __launch_bounds__(ROWS_PER_CTA * 32) assemble_kernel(const Assem
     const float* te = p.te + (static_cast<size_t>(b) * p.T + te_row) * d;
     float* o32 = p.x32 + row * E;
     T* o16 = p.x16 ? reinterpret_cast<T*>(p.x16) + row * E : nullptr;
+    T* olo = p.xlo ? reinterpret_cast<T*>(p.xlo) + row * E : nullptr;
     for (int c = lane * 4; c < E; c += 128) {
         float4 v;
         if (c < d) {
@@ -188,6 +189,59 @@ __global__ void __launch_bounds__(ROWS_PER_CTA * 32) assemble_kernel(const Assem
         }
         store4<float>(o32 + c, v.x, v.y, v.z, v.w);
         if (o16) store4<T>(o16 + c, v.x, v.y, v.z, v.w);
+        if (olo) {
+            const float h0 = to_float<T>(from_float<T>(v.x)), h1 = to_float<T>(from_float<T>(v.y));
+            const float h2 = to_float<T>(from_float<T>(v.z)), h3 = to_float<T>(from_float<T>(v.w));
+            store4<T>(olo + c, v.x - h0, v.y - h1, v.z - h2, v.w - h3);
+        }
+    }
+}
+
+// LayerNorm of rows stored as two 16-bit planes (z = hi + lo): the row is read once into registers (so out16 may alias hi)
+template <typename T, int V>
+__global__ void __launch_bounds__(ROWS_PER_CTA * 32) layernorm_planes_kernel(const T* __restrict__ hi, const T* __restrict__ lo, int ldi,
+                                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                                             float* __restrict__ out32, int ld32, T* out16, int ld16, int M, int n) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const T* ph = hi + static_cast<size_t>(row) * ldi;
+    const T* pl = lo + static_cast<size_t>(row) * ldi;
+    float4 v[V];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const int c = lane * 4 + i * 128;
+        if (c < n) {
+            const uint2 a = *reinterpret_cast<const uint2*>(ph + c), b = *reinterpret_cast<const uint2*>(pl + c);
+            const float2 a0 = unpack2<T>(a.x), a1 = unpack2<T>(a.y), b0 = unpack2<T>(b.x), b1 = unpack2<T>(b.y);
+            v[i] = make_float4(a0.x + b0.x, a0.y + b0.y, a1.x + b1.x, a1.y + b1.y);
+        } else {
+            v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) / static_cast<float>(n);
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        if (lane * 4 + i * 128 < n) {
+            const float a = v[i].x - mean, b2 = v[i].y - mean, c2 = v[i].z - mean, d2 = v[i].w - mean;
+            q += (a * a + b2 * b2) + (c2 * c2 + d2 * d2);
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(n) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+        const int c = lane * 4 + i * 128;
+        if (c < n) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+            const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c));
+            const float y0 = (v[i].x - mean) * rstd * g.x + b.x, y1 = (v[i].y - mean) * rstd * g.y + b.y;
+            const float y2 = (v[i].z - mean) * rstd * g.z + b.z, y3 = (v[i].w - mean) * rstd * g.w + b.w;
+            if (out32) store4<float>(out32 + static_cast<size_t>(row) * ld32 + c, y0, y1, y2, y3);
+            if (out16) store4<T>(out16 + static_cast<size_t>(row) * ld16 + c, y0, y1, y2, y3);
+        }
     }
 }
 
@@ -336,6 +390,20 @@ cudaError_t launch_layernorm(const float* in, int ldi, const float* gamma, const
 template cudaError_t launch_layernorm<float>(const float*, int, const float*, const float*, float*, int, float*, int, int, int, cudaStream_t, float2*);
 template cudaError_t launch_layernorm<__half>(const float*, int, const float*, const float*, float*, int, __half*, int, int, int, cudaStream_t, float2*);
 template cudaError_t launch_layernorm<__nv_bfloat16>(const float*, int, const float*, const float*, float*, int, __nv_bfloat16*, int, int, int, cudaStream_t, float2*);
+
+template <typename T>
+cudaError_t launch_layernorm_planes(const T* hi, const T* lo, int ldi, const float* gamma, const float* beta, float* out32, int ld32, T* out16,
+                                    int ld16, int M, int n, cudaStream_t s) {
+    if (M <= 0) return cudaSuccess;
+    if ((n & 3) || (ldi & 3) || (out32 && (ld32 & 3)) || (out16 && (ld16 & 3)) || n > 2048) return cudaErrorInvalidValue;
+    const int grid = (M + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
+    if (n <= 512) layernorm_planes_kernel<T, 4><<<grid, ROWS_PER_CTA * 32, 0, s>>>(hi, lo, ldi, gamma, beta, out32, ld32, out16, ld16, M, n);
+    else if (n <= 1024) layernorm_planes_kernel<T, 8><<<grid, ROWS_PER_CTA * 32, 0, s>>>(hi, lo, ldi, gamma, beta, out32, ld32, out16, ld16, M, n);
+    else layernorm_planes_kernel<T, 16><<<grid, ROWS_PER_CTA * 32, 0, s>>>(hi, lo, ldi, gamma, beta, out32, ld32, out16, ld16, M, n);
+    return cudaGetLastError();
+}
+template cudaError_t launch_layernorm_planes<__half>(const __half*, const __half*, int, const float*, const float*, float*, int, __half*, int, int, int, cudaStream_t);
+template cudaError_t launch_layernorm_planes<__nv_bfloat16>(const __nv_bfloat16*, const __nv_bfloat16*, int, const float*, const float*, float*, int, __nv_bfloat16*, int, int, int, cudaStream_t);
 
 template <typename T>
 cudaError_t launch_assemble(const AssembleParams& p, cudaStream_t s) {

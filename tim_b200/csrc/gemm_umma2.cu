@@ -60,6 +60,11 @@ template <int ACT> __device__ __forceinline__ float apply_act(float v) {
 //    thread owns in the tile: p.opart[(2 tn + half) * M + row]  (row_stats_finalize_kernel turns them into (mean, rstd));
 // 6: consumer - A = the 16-bit copy of z, W pre-multiplied by gamma: out = T(act(rstd * (acc - mean * cs[n]) + bw[n])) with
 //    (mean, rstd) = p.rstats[row], cs[n] = sum_k W'[n,k], bw[n] = sum_k beta[k] W[n,k] + bias[n] (passed as p.bias),
+// 7: producer on a TWO-PLANE residual stream: z is kept as hi = T(z), lo = T(z - hi) (two 16-bit planes, ~22 significant bits with
+//    fp16; tools/residual_split_study.py: 5.9e-7 end to end) instead of fp32 + a 16-bit copy. The hi plane IS the A operand of the
+//    consumer GEMM, so a producer writes 4 bytes per element where mode 5 writes 6, reads the residual as two 16-bit tiles (TMA, box
+//    32 x 32, 64-byte swizzle) and overwrites them in shared memory with the output planes before the TMA stores. Per warp that is
+//    two 4 KB slots, the same as the plain modes - so mode 7 keeps all 5 pipeline stages where mode 5 gave one up.
 template <typename T, int MODE, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_umma2_kernel(const __grid_constant__ Umma2Params p) {
     // MODE 5 trades one pipeline stage for a third epilogue buffer per warp (the 16-bit copy); same total
@@ -93,8 +98,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
         tma_prefetch_desc(&p.tmOut);
-        if (MODE == 2 || MODE == 3 || MODE == 5) tma_prefetch_desc(&p.tmRes);
+        if (MODE == 2 || MODE == 3 || MODE == 5 || MODE == 7) tma_prefetch_desc(&p.tmRes);
         if (MODE == 5) tma_prefetch_desc(&p.tmOut16);
+        if (MODE == 7) { tma_prefetch_desc(&p.tmResLo); tma_prefetch_desc(&p.tmOutLo); }
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -176,9 +182,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
         const uint32_t swz = static_cast<uint32_t>(lane & 7);
         const uint32_t tempty_leader0 = mapa_shared(tempty_bar(0), 0), tempty_leader1 = mapa_shared(tempty_bar(1), 0);
         constexpr bool OUT16 = MODE == 0 || MODE == 6;
-        constexpr bool RES = MODE == 2 || MODE == 3 || MODE == 5;
+        constexpr bool RES = MODE == 2 || MODE == 3 || MODE == 5 || MODE == 7;
         constexpr bool DUAL = MODE == 5;
+        constexpr bool PLANES = MODE == 7;
         constexpr bool FOLD = MODE == 6;
+        const uint32_t sw64 = static_cast<uint32_t>((lane >> 1) & 3);      // 64-byte swizzle of the 32 x 32 16-bit plane tiles
         constexpr int COLS_PER_BLOCK = OUT16 ? 64 : 32;          // 128 B of output per row
         constexpr int BLOCKS = BN / COLS_PER_BLOCK;
         // column block handled in this warp's i-th step: every other block; MODE 5 takes adjacent PAIRS of 32-column blocks
@@ -199,7 +207,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
 
             // LayerNorm of the residual row on read: r -> (r * rstd - mean * rstd) * gamma + beta   (MODE 3, MODE 5 with rstats)
             float ln_rstd = 1.0f, ln_nmr = 0.0f;
-            const bool ln_res = MODE == 3 || (DUAL && p.rstats != nullptr);
+            const bool ln_res = MODE == 3 || ((DUAL || PLANES) && p.rstats != nullptr);
             if (ln_res && row_ok) {
                 const float2 st = p.rstats[row0 + lane];
                 ln_rstd = st.y; ln_nmr = -st.x * st.y;
@@ -218,6 +226,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
                     tma_store_wait_read<0>();             // that buffer's previous store has drained
                     mbar_arrive_expect_tx(epild_bar(e, b), EPI_BUF);
                     tma_load_2d(buf0 + b * EPI_BUF, &p.tmRes, epild_bar(e, b), n0 + block_of(0) * COLS_PER_BLOCK, row0);
+                    if (PLANES) tma_load_2d(buf0 + b * EPI_BUF + EPI_BUF / 2, &p.tmResLo, epild_bar(e, b), n0 + block_of(0) * COLS_PER_BLOCK, row0);
                 }
                 __syncwarp();
             }
@@ -236,6 +245,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
                             tma_store_wait_read<0>();
                             mbar_arrive_expect_tx(epild_bar(e, b ^ 1u), EPI_BUF);
                             tma_load_2d(buf0 + (b ^ 1u) * EPI_BUF, &p.tmRes, epild_bar(e, b ^ 1u), n0 + block_of(i + 1) * COLS_PER_BLOCK, row0);
+                            if (PLANES)
+                                tma_load_2d(buf0 + (b ^ 1u) * EPI_BUF + EPI_BUF / 2, &p.tmResLo, epild_bar(e, b ^ 1u), n0 + block_of(i + 1) * COLS_PER_BLOCK, row0);
                         }
                         __syncwarp();
                     }
@@ -277,6 +288,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
                             const uint32_t chunk = static_cast<uint32_t>(part * 4 + c);
                             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
                                          ::"r"(buf + my_row + ((chunk ^ swz) << 4)), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+                        }
+                    } else if (PLANES) {
+                        // residual = hi + lo (two 32 x 32 16-bit tiles, 64-byte rows, 64-byte swizzle); the output planes overwrite them
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const uint32_t a_hi = buf + static_cast<uint32_t>(lane) * 64u + ((static_cast<uint32_t>(c) ^ sw64) << 4);
+                            const uint32_t a_lo = a_hi + EPI_BUF / 2;
+                            const uint4 qh = lds_u128(a_hi), ql = lds_u128(a_lo);
+                            const uint32_t hw[4] = {qh.x, qh.y, qh.z, qh.w}, lw[4] = {ql.x, ql.y, ql.z, ql.w};
+                            uint32_t oh[4], ol[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 h2 = unpack2<T>(hw[j]), l2 = unpack2<T>(lw[j]);
+                                float r0 = h2.x + l2.x, r1 = h2.y + l2.y;
+                                const int col = n + 8 * c + 2 * j;
+                                if (ln_res) {
+                                    const float2 g2 = __ldg(reinterpret_cast<const float2*>(p.rgamma + col));
+                                    const float2 e2 = __ldg(reinterpret_cast<const float2*>(p.rbeta + col));
+                                    r0 = fmaf(fmaf(r0, ln_rstd, ln_nmr), g2.x, e2.x);
+                                    r1 = fmaf(fmaf(r1, ln_rstd, ln_nmr), g2.y, e2.y);
+                                }
+                                const float o0 = f[8 * c + 2 * j] + r0, o1 = f[8 * c + 2 * j + 1] + r1;
+                                oh[j] = pack2<T>(o0, o1);
+                                const float2 hb = unpack2<T>(oh[j]);
+                                ol[j] = pack2<T>(o0 - hb.x, o1 - hb.y);
+                                st_sum += o0 + o1; st_sq = fmaf(o0, o0, fmaf(o1, o1, st_sq));
+                            }
+                            sts_u128(a_hi, make_uint4(oh[0], oh[1], oh[2], oh[3]));
+                            sts_u128(a_lo, make_uint4(ol[0], ol[1], ol[2], ol[3]));
                         }
                     } else {
 #pragma unroll
@@ -320,11 +360,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
                 if (lane == 0) {
                     tma_store_2d(&p.tmOut, buf, col0, row0);
                     if (DUAL && (i & 1)) tma_store_2d(&p.tmOut16, buf16, col0 - 32, row0);
+                    if (PLANES) tma_store_2d(&p.tmOutLo, buf + EPI_BUF / 2, col0, row0);
                     tma_store_commit();
                 }
                 ++nbuf;
             }
-            if (DUAL && row_ok)                          // also when this half owns no column of a ragged last tile: (0, 0)
+            if ((DUAL || PLANES) && row_ok)              // also when this half owns no column of a ragged last tile: (0, 0)
                 p.opart[static_cast<size_t>(tn * 2 + half) * p.M + row0 + lane] = make_float2(st_sum, st_sq);
             // all of this warp's TMEM reads of the accumulator are done
             tc_fence_before();
@@ -372,6 +413,7 @@ cudaError_t launch_linear_umma2(Umma2Params p, int mode, int act, int num_sms, c
     TIM_U2(3, ACT_NONE)
     TIM_U2(5, ACT_NONE)
     TIM_U2(6, ACT_NONE) TIM_U2(6, ACT_GELU)
+    TIM_U2(7, ACT_NONE)
 #undef TIM_U2
     return cudaErrorInvalidValue;
 }

@@ -87,6 +87,9 @@ struct Umma2Params {
     const float* rbeta;
     // folded-LayerNorm pair (modes 5 / 6); rstats doubles as the statistics of the residual rows (5) / of the A rows (6)
     CUtensorMap tmOut16;  // mode 5: 16-bit copy of the output, (N, M), box (64, 32), SWIZZLE_128B
+    // mode 7 (two-plane residual stream): tmOut / tmRes are the HI planes, tmOutLo / tmResLo the LO planes; all four 16-bit (N, M),
+    // box (32, 32), SWIZZLE_64B
+    CUtensorMap tmOutLo, tmResLo;
     float2* opart;        // mode 5: [2 * tiles_n][M] partial (sum, sum of squares) of the rows written
     const float* cs;      // mode 6: [N] row sums of the gamma-folded 16-bit weight
     int M, N, K;
@@ -95,7 +98,7 @@ struct Umma2Params {
 bool umma2_supported(int M, int N, int K);
 // mode 0: out = T(act(acc + bias)); 1: out = float(act(acc + bias)); 2: out = float(act(acc + bias) + resid);
 // mode 3: out = float(act(acc + bias) + LayerNorm(resid)) with the row statistics given (Epilogue::rstats)
-// modes 5 / 6: the folded-LayerNorm producer / consumer pair, see gemm_umma2.cu
+// modes 5 / 6: the folded-LayerNorm producer / consumer pair, see gemm_umma2.cu; mode 7: producer on the two-plane residual stream
 template <typename T>
 cudaError_t launch_linear_umma2(Umma2Params p, int mode, int act, int num_sms, cudaStream_t s);
 
@@ -145,6 +148,11 @@ template <typename T>
 cudaError_t launch_layernorm(const float* in, int ldi, const float* gamma, const float* beta, float* out32, int ld32,
                              T* out16, int ld16, int M, int n, cudaStream_t s, float2* stats = nullptr);
 
+// LayerNorm over rows held as two 16-bit planes (z = hi + lo, the two-plane residual stream of gemm_umma2.cu mode 7); out16 may alias hi
+template <typename T>
+cudaError_t launch_layernorm_planes(const T* hi, const T* lo, int ldi, const float* gamma, const float* beta, float* out32, int ld32,
+                                    T* out16, int ld16, int M, int n, cudaStream_t s);
+
 // Token assembly (encodings.py forward): see elementwise.cu for the row plan
 struct TokenGroup {          // a run of `count` query tokens per clip
     const float* cls;        // [d] CLS parameter (left half)
@@ -166,6 +174,7 @@ struct AssembleParams {
     int Qt;                  // query tokens per clip = sum(groups.count)
     float* x32;              // [B*Ft + B*Qt, E] fp32 residual stream (two-stream layout)
     void* x16;               // same rows, operand dtype (nullptr in fp32 mode)
+    void* xlo;               // optional LO plane of the two-plane residual stream: T(x - float(T(x)))   (x16 is the HI plane)
 };
 template <typename T>
 cudaError_t launch_assemble(const AssembleParams& p, cudaStream_t s);
