@@ -109,7 +109,7 @@ def test_wgrad_kernel(lib, M, N, K, splits, dt):
 
 
 ATT_SHAPES = [(2, 12, 7, 2, 16), (3, 100, 100, 2, 128), (2, 128, 200, 1, 192), (2, 100, 0, 2, 64), (1, 50, 130, 4, 32), (2, 33, 65, 3, 64),
-              (1, 100, 300, 2, 128)]
+              (1, 100, 300, 2, 128), (2, 128, 129, 2, 128), (4, 16, 5, 1, 64), (37, 100, 100, 8, 128)]
 
 
 @pytest.mark.parametrize("dt", ["fp32", "fp16", "bf16"])

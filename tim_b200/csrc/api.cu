@@ -1800,17 +1800,29 @@ int tim_test_attention_bwd(int dtype, const float* qkv, const float* dO, float* 
             t.alloc(&st, attention_bwd_stats_bytes(B, Ft, Qt, H)) != cudaSuccess)
             return fin(c->fail(TIM_ERR_NOMEM, "alloc"));
         cudaMemsetAsync(o16, 0, M * 3 * E * 2, s);
+        int dev = 0;
+        cudaDeviceProp prop;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaGetDeviceProperties(&prop, dev) != cudaSuccess || prop.major != 10) {
+            g_create_error = "tim_test_attention_bwd: no sm_100 device";
+            return TIM_ERR_NO_DEVICE;
+        }
+        c->num_sms = prop.multiProcessorCount; c->device = dev; c->cfg.compute_dtype = dtype; c->esize = 2;
+        c->H = H; c->hd = hd; c->E = static_cast<int>(E);
+        int rc = get_encode_fn(c);
+        if (rc) return fin(rc);
+        // same dispatch as the training leg: tcgen05 kernel where the shape allows (TIM_B200_ATTN_BWD=1 forces the warp-MMA kernels)
         if (dtype == TIM_BF16) {
             launch_cast<__nv_bfloat16>(qkv, static_cast<__nv_bfloat16*>(q16), M, 3 * E, 0, 1.0f, s);
             launch_cast<__nv_bfloat16>(dO, static_cast<__nv_bfloat16*>(d16), M, E, 0, 1.0f, s);
-            e = launch_attention_bwd<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(q16), static_cast<const __nv_bfloat16*>(d16),
-                                                    static_cast<__nv_bfloat16*>(o16), st, B, Ft, Qt, H, hd, qscale, s);
+            rc = run_attention_bwd<__nv_bfloat16>(c, static_cast<const __nv_bfloat16*>(q16), static_cast<const __nv_bfloat16*>(d16),
+                                                  static_cast<__nv_bfloat16*>(o16), st, B, Ft, Qt, qscale, 0.0, s);
         } else {
             launch_cast<__half>(qkv, static_cast<__half*>(q16), M, 3 * E, 0, 1.0f, s);
             launch_cast<__half>(dO, static_cast<__half*>(d16), M, E, 0, 1.0f, s);
-            e = launch_attention_bwd<__half>(static_cast<const __half*>(q16), static_cast<const __half*>(d16), static_cast<__half*>(o16), st, B, Ft,
-                                             Qt, H, hd, qscale, s);
+            rc = run_attention_bwd<__half>(c, static_cast<const __half*>(q16), static_cast<const __half*>(d16), static_cast<__half*>(o16), st, B, Ft,
+                                           Qt, qscale, 0.0, s);
         }
+        if (rc) return fin(rc);
         if (e == cudaSuccess) {
             std::vector<uint16_t> h(M * 3 * E);
             e = cudaStreamSynchronize(s);

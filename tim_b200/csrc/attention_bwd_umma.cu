@@ -1,0 +1,453 @@
+// Backward of the mask-aware attention core on the 5th-generation tensor cores (tcgen05 + TMEM + TMA) - the training leg's
+// counterpart of attention_umma.cu. Math, scaling conventions and what it replaces in the reference: see attention_bwd.cu (the
+// warp-MMA version, which stays for head_dim 16 / 32 / 192 and as the A/B partner: TIM_B200_ATTN_BWD=1).
+//
+// Work unit = (clip b, head h). K_f / V_f ([Ft, hd]) are staged once per unit; the unit walks its 128-row tiles (tile 0 = the
+// clip's feature rows, tiles 1.. = its query rows). Per tile, five products on the tensor cores:
+//   S   = Q K_f^T          M=128 rows, N=Fp keys, K=hd     A, B K-major                         -> TMEM [0, Fp)
+//   dP  = dO V_f^T         same shapes                                                          -> TMEM [128, 128 + Fp)
+//   softmax warps (one thread per row): P, D = sum P dP (+ own key), dS = P o (dP - D); P and dS go to shared memory ONCE,
+//   in the K-major 128-byte-swizzled tile layout - which, read with the other descriptor, is also the MN-major layout:
+//   dQ  = dS K_f           M=128 rows, N=hd, K=Fp          A = dS K-major, B = K_f MN-major     -> TMEM [0, hd)   (S is consumed)
+//   dV_f += P^T dO         M=128 keys, N=hd, K=128 rows    A = P MN-major, B = dO MN-major      -> TMEM [256, 256 + hd), accumulates over the unit's tiles
+//   dK_f += dS^T Q         same                            A = dS MN-major, B = Q MN-major      -> TMEM [384, 384 + hd)
+// The own-key / own-value terms of query rows are element-wise per row and are done by the thread that owns the row.
+// No atomics, no P / dS in global memory; HBM traffic is the algorithmic 14 KB per token row (+ the own k / v rows once more).
+//
+// One persistent CTA per SM, 320 threads: warp 0 TMA producer, warp 1 MMA issuer (and TMEM allocation), warps 2-5 softmax
+// (TMEM lane quarter = warp % 4), warps 6-9 epilogue (dQ per tile; dK_f / dV_f per unit). Single-stage per tile (the 512 TMEM
+// columns and 227 KB of shared memory are both full at hd = 128): tiles of one SM run back to back, overlap comes from the
+// roles (the loads of tile t+1 start as soon as the products of tile t have retired, under its epilogue).
+#include <cstdlib>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace tim {
+namespace {
+
+constexpr int BU_THREADS = 320;
+constexpr int BU_BM = 128;
+constexpr float kLn2u = 0.69314718055994530942f;
+
+template <typename T> struct FmtOfB;
+template <> struct FmtOfB<__half> { static constexpr uint32_t v = 0; };
+template <> struct FmtOfB<__nv_bfloat16> { static constexpr uint32_t v = 1; };
+
+template <typename T, int HD>
+__global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const __grid_constant__ AttnBwdUmmaParams p) {
+    constexpr int KBOX = HD / 64;
+    constexpr int TILE_BYTES = KBOX * BU_BM * 128;          // Q / dO tile
+    constexpr int PS_BYTES = 2 * BU_BM * 128;               // P / dS tile: 128 rows x 128 keys
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int Fp = p.Fp, Ft = p.Ft, Qt = p.Qt;
+    const uint32_t box_kv = static_cast<uint32_t>(Fp) * 128u;
+    const uint32_t kv_bytes = KBOX * box_kv;
+    const uint32_t kv_pad = (kv_bytes + 1023u) & ~1023u;
+    const uint32_t sKF = base, sVF = base + kv_pad;
+    const uint32_t sQ = sVF + kv_pad, sDO = sQ + TILE_BYTES, sP = sDO + TILE_BYTES, sDS = sP + PS_BYTES;
+    const uint32_t stat_base = sDS + PS_BYTES;              // float [2][128]: own-key dS of query rows, double-buffered by tile parity
+    const uint32_t bar_base = stat_base + 1024;
+    const uint32_t kv_full = bar_base, kv_empty = bar_base + 8, q_full = bar_base + 16, s_full = bar_base + 24, p_full = bar_base + 32,
+                   o_full = bar_base + 40, dq_done = bar_base + 48, acc_empty = bar_base + 56, tmem_slot = bar_base + 64;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    const int E = p.H * HD;
+    const size_t ld = 3 * static_cast<size_t>(E);
+    const int tiles = 1 + p.tiles_q;
+    const T* qkv = static_cast<const T*>(p.qkv);
+    const T* dOp = static_cast<const T*>(p.dO);
+    T* dqkv = static_cast<T*>(p.dqkv);
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmKV); tma_prefetch_desc(&p.tmQf); tma_prefetch_desc(&p.tmQq);
+        tma_prefetch_desc(&p.tmDf); tma_prefetch_desc(&p.tmDq);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            mbar_init(kv_full, 1); mbar_init(kv_empty, 1); mbar_init(q_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 4);
+            mbar_init(o_full, 1); mbar_init(dq_done, 4); mbar_init(acc_empty, 4);
+            fence_mbar_init();
+        }
+        __syncwarp();
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        uint32_t g = 0, un = 0;
+        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++un) {
+            const int b = u / p.H, h = u - b * p.H;
+            mbar_wait(kv_empty, (un & 1u) ^ 1u);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(kv_full, 2 * kv_bytes);
+#pragma unroll
+                for (int j = 0; j < KBOX; ++j) {
+                    tma_load_3d(sKF + j * box_kv, &p.tmKV, kv_full, E + h * HD + 64 * j, 0, b);
+                    tma_load_3d(sVF + j * box_kv, &p.tmKV, kv_full, 2 * E + h * HD + 64 * j, 0, b);
+                }
+            }
+            for (int t = 0; t < tiles; ++t, ++g) {
+                if (g > 0) mbar_wait(o_full, (g - 1) & 1u);          // the previous tile's products have retired: Q / dO tiles are free
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(q_full, 2 * TILE_BYTES);
+#pragma unroll
+                    for (int j = 0; j < KBOX; ++j) {
+                        if (t == 0) {
+                            tma_load_3d(sQ + j * 16384, &p.tmQf, q_full, h * HD + 64 * j, 0, b);
+                            tma_load_3d(sDO + j * 16384, &p.tmDf, q_full, h * HD + 64 * j, 0, b);
+                        } else {
+                            tma_load_3d(sQ + j * 16384, &p.tmQq, q_full, h * HD + 64 * j, (t - 1) * BU_BM, b);
+                            tma_load_3d(sDO + j * 16384, &p.tmDq, q_full, h * HD + 64 * j, (t - 1) * BU_BM, b);
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc_s = umma_idesc_f16(FmtOfB<T>::v, BU_BM, static_cast<uint32_t>(Fp));
+        const uint32_t idesc_dq = umma_idesc_f16(FmtOfB<T>::v, BU_BM, HD) | (1u << 16);                 // B = K_f MN-major
+        const uint32_t idesc_kv = umma_idesc_f16(FmtOfB<T>::v, BU_BM, HD) | (1u << 15) | (1u << 16);   // A and B MN-major
+        const int ksteps_f = Fp / 16;
+        uint32_t g = 0, un = 0;
+        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++un) {
+            mbar_wait(kv_full, un & 1u);
+            for (int t = 0; t < tiles; ++t, ++g) {
+                mbar_wait(q_full, g & 1u);
+                if (g > 0) mbar_wait(dq_done, (g - 1) & 1u);        // dQ of the previous tile has been read out of [0, hd)
+                tc_fence_after();
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < HD / 16; ++k) {
+                        const uint64_t bq = umma_desc_sw128(sQ + (k >> 2) * 16384) + 2u * (k & 3);
+                        const uint64_t bd = umma_desc_sw128(sDO + (k >> 2) * 16384) + 2u * (k & 3);
+                        const uint64_t bk = umma_desc_sw128(sKF + (k >> 2) * box_kv) + 2u * (k & 3);
+                        const uint64_t bv = umma_desc_sw128(sVF + (k >> 2) * box_kv) + 2u * (k & 3);
+                        umma_f16_ss(tmem_base, bq, bk, idesc_s, k != 0 ? 1u : 0u);             // S
+                        umma_f16_ss(tmem_base + 128, bd, bv, idesc_s, k != 0 ? 1u : 0u);       // dP
+                    }
+                    umma_commit(s_full);
+                }
+                mbar_wait(p_full, g & 1u);                           // P and dS are in shared memory, S and dP consumed
+                if (t == 0 && un > 0) mbar_wait(acc_empty, (un - 1) & 1u);     // dK_f / dV_f of the previous unit have been read out
+                tc_fence_after();
+                if (elect_one()) {
+                    for (int k = 0; k < ksteps_f; ++k) {             // dQ = dS K_f
+                        const uint64_t a = umma_desc_sw128(sDS + (k >> 2) * 16384) + 2u * (k & 3);
+                        const uint64_t bdesc = umma_desc_mn_sw128(sKF + k * 2048, box_kv);
+                        umma_f16_ss(tmem_base, a, bdesc, idesc_dq, k != 0 ? 1u : 0u);
+                    }
+#pragma unroll
+                    for (int k = 0; k < BU_BM / 16; ++k) {           // dV_f += P^T dO,  dK_f += dS^T Q  (k runs over the tile's rows)
+                        const uint32_t acc = (t != 0 || k != 0) ? 1u : 0u;
+                        umma_f16_ss(tmem_base + 256, umma_desc_mn_sw128(sP + k * 2048, 16384), umma_desc_mn_sw128(sDO + k * 2048, 16384), idesc_kv, acc);
+                        umma_f16_ss(tmem_base + 384, umma_desc_mn_sw128(sDS + k * 2048, 16384), umma_desc_mn_sw128(sQ + k * 2048, 16384), idesc_kv, acc);
+                    }
+                    umma_commit(o_full);
+                    if (t == tiles - 1) umma_commit(kv_empty);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp < 6) {
+        // ===================== softmax / dS (warps 2..5): one thread per row =====================
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t swz = static_cast<uint32_t>(row & 7);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        const float qln2 = kLn2u;
+        uint32_t g = 0;
+        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+            const int b = u / p.H, h = u - b * p.H;
+            for (int t = 0; t < tiles; ++t, ++g) {
+                const bool qt = t > 0;
+                const int row0 = qt ? (t - 1) * BU_BM : 0;
+                const int nrows = min(BU_BM, (qt ? Qt : Ft) - row0);
+                const bool valid = row < nrows;
+                const size_t grow = qt ? static_cast<size_t>(p.B) * Ft + static_cast<size_t>(b) * Qt + row0 + row : static_cast<size_t>(b) * Ft + row;
+                // own key / value rows of a query row: element-wise terms only - read straight from global memory by the row's thread
+                float sself = -INFINITY, dps = 0.0f;
+                mbar_wait(q_full, g & 1u);                           // Q and dO tiles of this tile are in shared memory
+                if (qt && valid) {
+                    const T* own = qkv + grow * ld + h * HD;
+                    float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+                    for (int c = 0; c < HD / 8; ++c) {
+                        const uint4 kq = __ldg(reinterpret_cast<const uint4*>(own + E + 8 * c));
+                        const uint4 vq = __ldg(reinterpret_cast<const uint4*>(own + 2 * E + 8 * c));
+                        const uint32_t off = static_cast<uint32_t>(c >> 3) * 16384 + row * 128 + ((static_cast<uint32_t>(c & 7) ^ swz) << 4);
+                        const uint4 qq = lds_u128(sQ + off), dd = lds_u128(sDO + off);
+                        const uint32_t kw[4] = {kq.x, kq.y, kq.z, kq.w}, vw[4] = {vq.x, vq.y, vq.z, vq.w};
+                        const uint32_t qw[4] = {qq.x, qq.y, qq.z, qq.w}, dw[4] = {dd.x, dd.y, dd.z, dd.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 kf = unpack2<T>(kw[j]), vf = unpack2<T>(vw[j]), qf = unpack2<T>(qw[j]), df = unpack2<T>(dw[j]);
+                            a0 = fmaf(qf.x, kf.x, fmaf(qf.y, kf.y, a0));
+                            a1 = fmaf(df.x, vf.x, fmaf(df.y, vf.y, a1));
+                        }
+                    }
+                    sself = a0; dps = a1;
+                }
+                if (g > 0) mbar_wait(o_full, (g - 1) & 1u);          // P / dS tiles of the previous tile are no longer read by the tensor core
+                mbar_wait(s_full, g & 1u);
+                tc_fence_after();
+                // ---- P (whole row in registers), softmax statistics ----
+                float s[128];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c * 16 < Fp) {
+                        uint32_t v[16];
+                        tmem_ld_32x16(taddr + c * 16, v);
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) s[c * 16 + j] = __uint_as_float(v[j]);
+                    }
+                }
+                tmem_ld_wait();
+                float mx[4] = {sself, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c * 16 < Fp) {
+                        if (c * 16 + 16 > Ft) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (c * 16 + j >= Ft) s[c * 16 + j] = -INFINITY;
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) mx[j & 3] = fmaxf(mx[j & 3], s[c * 16 + j]);
+                    }
+                }
+                const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+                float ls[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c * 16 < Fp) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const float e = ex2_approx(s[c * 16 + j] - m);
+                            s[c * 16 + j] = e;
+                            ls[j & 3] += e;
+                        }
+                    }
+                }
+                float ps = qt ? ex2_approx(sself - m) : 0.0f;
+                const float inv = valid ? 1.0f / ((ls[0] + ls[1]) + (ls[2] + ls[3]) + ps) : 0.0f;      // padded rows: P = dS = 0
+                ps *= inv;
+                // ---- D = sum_j P_j dP_j (+ own key): first pass over dP ----
+                float dacc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c * 16 < Fp) {
+                        uint32_t v[16];
+                        tmem_ld_32x16(taddr + 128 + c * 16, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            s[c * 16 + j] *= inv;
+                            dacc[j & 3] = fmaf(s[c * 16 + j], __uint_as_float(v[j]), dacc[j & 3]);
+                        }
+                    }
+                }
+                const float D = (dacc[0] + dacc[1]) + (dacc[2] + dacc[3]) + ps * dps;
+                const float dss = ps * (dps - D);
+                // ---- second pass: dS = P o (dP - D); P and dS -> shared memory (K-major, 128-byte swizzle; 64-key blocks 16 KB apart) ----
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (c * 16 < Fp) {
+                        uint32_t v[16];
+                        tmem_ld_32x16(taddr + 128 + c * 16, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int h8 = 0; h8 < 2; ++h8) {
+                            const int c8 = c * 2 + h8;
+                            uint4 qp, qd;
+                            uint32_t* wp = reinterpret_cast<uint32_t*>(&qp);
+                            uint32_t* wd = reinterpret_cast<uint32_t*>(&qd);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float p0 = s[c8 * 8 + 2 * j], p1 = s[c8 * 8 + 2 * j + 1];
+                                wp[j] = pack2<T>(p0, p1);
+                                wd[j] = pack2<T>(p0 * (__uint_as_float(v[h8 * 8 + 2 * j]) - D), p1 * (__uint_as_float(v[h8 * 8 + 2 * j + 1]) - D));
+                            }
+                            const uint32_t off = static_cast<uint32_t>(c8 >> 3) * 16384 + row * 128 + ((static_cast<uint32_t>(c8 & 7) ^ swz) << 4);
+                            sts_u128(sP + off, qp);
+                            sts_u128(sDS + off, qd);
+                        }
+                    }
+                }
+                sts_f32(stat_base + static_cast<uint32_t>((g & 1u) * 512 + row * 4), dss);
+                tc_fence_before();
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full);
+                // ---- own-key / own-value gradients of query rows: dk_own = ln2 dss q~, dv_own = p_self dO ----
+                // (q~ and dO rows come from global memory here, an L2 hit: the shared-memory tiles may already be receiving the next
+                // tile - the producer reloads them as soon as this tile's products retire, which this thread no longer waits for)
+                if (qt && valid) {
+                    T* o = dqkv + grow * ld + h * HD;
+                    const T* qrow = qkv + grow * ld + h * HD;
+                    const T* drow = dOp + grow * static_cast<size_t>(E) + h * HD;
+                    const float kk = qln2 * dss;
+#pragma unroll
+                    for (int c = 0; c < HD / 8; ++c) {
+                        const uint4 qq = __ldg(reinterpret_cast<const uint4*>(qrow + 8 * c)), dd = __ldg(reinterpret_cast<const uint4*>(drow + 8 * c));
+                        const uint32_t qw[4] = {qq.x, qq.y, qq.z, qq.w}, dw[4] = {dd.x, dd.y, dd.z, dd.w};
+                        uint4 ok, ov;
+                        uint32_t* wk = reinterpret_cast<uint32_t*>(&ok);
+                        uint32_t* wv = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 qf = unpack2<T>(qw[j]), df = unpack2<T>(dw[j]);
+                            wk[j] = pack2<T>(kk * qf.x, kk * qf.y);
+                            wv[j] = pack2<T>(ps * df.x, ps * df.y);
+                        }
+                        *reinterpret_cast<uint4*>(o + E + 8 * c) = ok;
+                        *reinterpret_cast<uint4*>(o + 2 * E + 8 * c) = ov;
+                    }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 6..9): dQ per tile, dK_f / dV_f per unit =====================
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        uint32_t g = 0;
+        for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
+            const int b = u / p.H, h = u - b * p.H;
+            for (int t = 0; t < tiles; ++t, ++g) {
+                const bool qt = t > 0;
+                const int row0 = qt ? (t - 1) * BU_BM : 0;
+                const int nrows = min(BU_BM, (qt ? Qt : Ft) - row0);
+                const bool valid = row < nrows;
+                const size_t grow = qt ? static_cast<size_t>(p.B) * Ft + static_cast<size_t>(b) * Qt + row0 + row : static_cast<size_t>(b) * Ft + row;
+                mbar_wait(p_full, g & 1u);                           // the softmax warps' per-row statistics are in shared memory
+                mbar_wait(o_full, g & 1u);
+                tc_fence_after();
+                const float dss = qt ? lds_f32(stat_base + static_cast<uint32_t>((g & 1u) * 512 + row * 4)) : 0.0f;
+                const T* kown = qkv + (valid ? grow : 0) * ld + E + h * HD;
+                T* oq = dqkv + grow * ld + h * HD;
+#pragma unroll
+                for (int c = 0; c < HD / 16; ++c) {
+                    uint32_t v[16];
+                    tmem_ld_32x16(taddr + c * 16, v);
+                    tmem_ld_wait();
+                    if (valid) {
+                        float f[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+                        if (qt) {
+                            const uint4 k0 = __ldg(reinterpret_cast<const uint4*>(kown + 16 * c)), k1 = __ldg(reinterpret_cast<const uint4*>(kown + 16 * c + 8));
+                            const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float2 kf = unpack2<T>(kw[j]);
+                                f[2 * j] = fmaf(dss, kf.x, f[2 * j]); f[2 * j + 1] = fmaf(dss, kf.y, f[2 * j + 1]);
+                            }
+                        }
+                        uint4 o0, o1;
+                        o0.x = pack2<T>(f[0] * p.qscale, f[1] * p.qscale); o0.y = pack2<T>(f[2] * p.qscale, f[3] * p.qscale);
+                        o0.z = pack2<T>(f[4] * p.qscale, f[5] * p.qscale); o0.w = pack2<T>(f[6] * p.qscale, f[7] * p.qscale);
+                        o1.x = pack2<T>(f[8] * p.qscale, f[9] * p.qscale); o1.y = pack2<T>(f[10] * p.qscale, f[11] * p.qscale);
+                        o1.z = pack2<T>(f[12] * p.qscale, f[13] * p.qscale); o1.w = pack2<T>(f[14] * p.qscale, f[15] * p.qscale);
+                        *reinterpret_cast<uint4*>(oq + 16 * c) = o0;
+                        *reinterpret_cast<uint4*>(oq + 16 * c + 8) = o1;
+                    }
+                }
+                if (t == tiles - 1) {
+                    // the unit's accumulators are complete: this thread's TMEM lane is feature key `row`
+                    const bool kvalid = row < Ft;
+                    T* ok = dqkv + (static_cast<size_t>(b) * Ft + (kvalid ? row : 0)) * ld + E + h * HD;
+#pragma unroll
+                    for (int c = 0; c < HD / 16; ++c) {
+                        uint32_t vv[16], vk[16];
+                        tmem_ld_32x16(taddr + 256 + c * 16, vv);
+                        tmem_ld_32x16(taddr + 384 + c * 16, vk);
+                        tmem_ld_wait();
+                        if (kvalid) {
+                            uint4 a0, a1, b0, b1;
+                            uint32_t* w;
+                            w = reinterpret_cast<uint32_t*>(&a0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) w[j] = pack2<T>(kLn2u * __uint_as_float(vk[2 * j]), kLn2u * __uint_as_float(vk[2 * j + 1]));
+                            w = reinterpret_cast<uint32_t*>(&a1);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) w[j] = pack2<T>(kLn2u * __uint_as_float(vk[8 + 2 * j]), kLn2u * __uint_as_float(vk[8 + 2 * j + 1]));
+                            w = reinterpret_cast<uint32_t*>(&b0);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) w[j] = pack2<T>(__uint_as_float(vv[2 * j]), __uint_as_float(vv[2 * j + 1]));
+                            w = reinterpret_cast<uint32_t*>(&b1);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) w[j] = pack2<T>(__uint_as_float(vv[8 + 2 * j]), __uint_as_float(vv[8 + 2 * j + 1]));
+                            *reinterpret_cast<uint4*>(ok + 16 * c) = a0;
+                            *reinterpret_cast<uint4*>(ok + 16 * c + 8) = a1;
+                            *reinterpret_cast<uint4*>(ok + E + 16 * c) = b0;
+                            *reinterpret_cast<uint4*>(ok + E + 16 * c + 8) = b1;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(dq_done);
+                    if (t == tiles - 1) mbar_arrive(acc_empty);
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+template <int HD> size_t bwd_smem_for(int Fp) {
+    const size_t kv = ((static_cast<size_t>(HD / 64) * Fp * 128) + 1023) & ~static_cast<size_t>(1023);
+    return 1024 + 2 * kv + 2 * static_cast<size_t>(HD / 64) * BU_BM * 128 + 2 * 2 * BU_BM * 128 + 1024 + 256;
+}
+
+template <typename T, int HD>
+cudaError_t launch_bwd_umma_hd(const AttnBwdUmmaParams& p, int num_sms, cudaStream_t s) {
+    const size_t smem = bwd_smem_for<HD>(p.Fp);
+    if (smem > 227 * 1024) return cudaErrorInvalidValue;
+    auto kern = attention_bwd_umma_kernel<T, HD>;
+    static SmemAttrCache cache;
+    if (cudaError_t e = ensure_dynamic_smem(kern, smem > 120 * 1024 ? smem : 120 * 1024, cache); e != cudaSuccess) return e;
+    const int grid = p.num_units < num_sms ? p.num_units : num_sms;
+    kern<<<grid, BU_THREADS, smem > 120 * 1024 ? smem : 120 * 1024, s>>>(p);      // >= 120 KB: one CTA per SM (each allocates all of TMEM)
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+bool attention_bwd_umma_supported(int Ft, int hd) {
+    if (const char* e = std::getenv("TIM_B200_ATTN_BWD")) if (std::atoi(e) == 1) return false;
+    return Ft >= 1 && Ft <= 128 && (hd == 64 || hd == 128);
+}
+
+template <typename T>
+cudaError_t launch_attention_bwd_umma(AttnBwdUmmaParams p, int hd, int num_sms, cudaStream_t s) {
+    if (!attention_bwd_umma_supported(p.Ft, hd) || p.B <= 0 || p.H <= 0 || p.Qt < 0) return cudaErrorInvalidValue;
+    p.Fp = (p.Ft + 15) & ~15;
+    p.tiles_q = (p.Qt + BU_BM - 1) / BU_BM;
+    const long long units = 1LL * p.B * p.H;
+    if (units > 0x7fffffffLL) return cudaErrorInvalidValue;
+    p.num_units = static_cast<int>(units);
+    return hd == 64 ? launch_bwd_umma_hd<T, 64>(p, num_sms, s) : launch_bwd_umma_hd<T, 128>(p, num_sms, s);
+}
+template cudaError_t launch_attention_bwd_umma<__half>(AttnBwdUmmaParams, int, int, cudaStream_t);
+template cudaError_t launch_attention_bwd_umma<__nv_bfloat16>(AttnBwdUmmaParams, int, int, cudaStream_t);
+
+}  // namespace tim

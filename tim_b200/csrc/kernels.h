@@ -229,6 +229,22 @@ size_t attention_bwd_stats_bytes(int B, int Ft, int Qt, int H);
 template <typename T>
 cudaError_t launch_attention_bwd(const T* qkv, const T* dO, T* dqkv, void* stats, int B, int Ft, int Qt, int H, int hd, float qscale,
                                  cudaStream_t s);
+// tcgen05 version (head_dim 64 / 128, Ft <= 128), attention_bwd_umma.cu. All maps: 16-bit, 128-byte swizzle, 3-D (columns, rows of a clip, clips)
+struct AttnBwdUmmaParams {
+    CUtensorMap tmKV;     // qkv feature rows (3E, Ft, B), box (64, Fp, 1)   - K_f / V_f of one (clip, head)
+    CUtensorMap tmQf;     // qkv feature rows (3E, Ft, B), box (64, 128, 1)  - Q tile of the feature rows
+    CUtensorMap tmQq;     // qkv query rows   (3E, Qt, B), box (64, 128, 1)
+    CUtensorMap tmDf;     // dO feature rows  (E, Ft, B),  box (64, 128, 1)
+    CUtensorMap tmDq;     // dO query rows    (E, Qt, B),  box (64, 128, 1)
+    const void* qkv; const void* dO; void* dqkv;
+    int B, Ft, Qt, H;
+    int Fp, tiles_q, num_units;       // filled by the launcher
+    float qscale;
+};
+bool attention_bwd_umma_supported(int Ft, int hd);
+template <typename T>
+cudaError_t launch_attention_bwd_umma(AttnBwdUmmaParams p, int hd, int num_sms, cudaStream_t s);
+
 size_t attention_bwd_simt_smem(int Ft, int hd);
 cudaError_t launch_attention_bwd_simt(const float* qkv, const float* dO, float* dqkv, int B, int Ft, int Qt, int H, int hd, float qscale,
                                       cudaStream_t s);

@@ -119,6 +119,32 @@ int run_wgrad(tim_ctx* c, const void* dY, int ldy, const void* X, int ldx, float
     return TIM_OK;
 }
 
+// attention backward: tcgen05 kernel where it applies (head_dim 64 / 128, Ft <= 128), else the two warp-MMA kernels
+template <typename T>
+int run_attention_bwd(tim_ctx* c, const T* qkv, const T* dO, T* dqkv, void* stats, int B, int Ft, int Qt, float qscale, double flops, cudaStream_t s) {
+    if (attention_bwd_umma_supported(Ft, c->hd)) {
+        AttnBwdUmmaParams ap;
+        std::memset(&ap, 0, sizeof(ap));
+        const long long E = c->E, ld = 3LL * c->E;
+        const int Fp = (Ft + 15) & ~15;
+        TIM_TRY(make_tmap_3d16(c, &ap.tmKV, qkv, ld, Ft, B, ld * 2, ld * 2 * Ft, Fp));
+        TIM_TRY(make_tmap_3d16(c, &ap.tmQf, qkv, ld, Ft, B, ld * 2, ld * 2 * Ft, 128));
+        TIM_TRY(make_tmap_3d16(c, &ap.tmDf, dO, E, Ft, B, E * 2, E * 2 * Ft, 128));
+        if (Qt > 0) {
+            TIM_TRY(make_tmap_3d16(c, &ap.tmQq, qkv + static_cast<size_t>(B) * Ft * ld, ld, Qt, B, ld * 2, ld * 2 * Qt, 128));
+            TIM_TRY(make_tmap_3d16(c, &ap.tmDq, dO + static_cast<size_t>(B) * Ft * E, E, Qt, B, E * 2, E * 2 * Qt, 128));
+        } else {
+            ap.tmQq = ap.tmQf; ap.tmDq = ap.tmDf;
+        }
+        ap.qkv = qkv; ap.dO = dO; ap.dqkv = dqkv; ap.B = B; ap.Ft = Ft; ap.Qt = Qt; ap.H = c->H; ap.qscale = qscale;
+        LAUNCH_C(c, 9, flops, s, launch_attention_bwd_umma<T>(ap, c->hd, c->num_sms, s));
+    } else {
+        LAUNCH_C(c, 9, flops, s, launch_attention_bwd<T>(qkv, dO, dqkv, stats, B, Ft, Qt, c->H, c->hd, qscale, s));
+        c->launches++;      // two kernels per call
+    }
+    return TIM_OK;
+}
+
 // dgrad through the forward GEMM kernels; profiled as class 7
 template <typename T>
 int run_dgrad(tim_ctx* c, const void* dY, const LinearW& w, int rows, Epilogue ep, cudaStream_t s) {
@@ -522,8 +548,7 @@ int encoder_train_bwd(tim_ctx* c, const tim_outputs* go, float* d_te, cudaStream
             CU_OK(c, cudaMemsetAsync(dqkv, 0, M * 3 * E * sizeof(float), s));
             LAUNCH_C(c, 9, attn_bwd_flops, s, launch_attention_bwd_simt(static_cast<const float*>(t.qkv), da, dqkv, B, Ft, Qt, c->H, c->hd, qscale, s));
         } else {
-            LAUNCH_C(c, 9, attn_bwd_flops, s, launch_attention_bwd<T>(static_cast<const T*>(t.qkv), da, dqkv, astats, B, Ft, Qt, c->H, c->hd, qscale, s));
-            c->launches++;      // two kernels per call
+            TIM_TRY(run_attention_bwd<T>(c, static_cast<const T*>(t.qkv), da, dqkv, astats, B, Ft, Qt, qscale, attn_bwd_flops, s));
         }
         LAUNCH(c, launch_colsum<T>(dqkv, 3 * E, 1, 0, 0, Mi, 0, 3 * E, g_bi, s));
         TIM_TRY(run_wgrad<T>(c, dqkv, 3 * E, t.xin, E, g_wi, E, Mi, 3 * E, E, s));
