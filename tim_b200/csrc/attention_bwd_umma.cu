@@ -109,6 +109,25 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                             tma_load_3d(sDO + j * 16384, &p.tmDq, q_full, h * HD + 64 * j, (t - 1) * BU_BM, b);
                         }
                     }
+                    // the tile buffers are single: the NEXT tile's loads cannot start before this tile's products retire, so pull its
+                    // rows into L2 now - the shared-memory load then costs an L2 round trip instead of an HBM one on the critical path
+                    const int nu = u + static_cast<int>(gridDim.x);
+                    if (t + 1 < tiles) {
+#pragma unroll
+                        for (int j = 0; j < KBOX; ++j) {
+                            tma_prefetch_l2_3d(&p.tmQq, h * HD + 64 * j, t * BU_BM, b);
+                            tma_prefetch_l2_3d(&p.tmDq, h * HD + 64 * j, t * BU_BM, b);
+                        }
+                    } else if (nu < p.num_units) {
+                        const int nb = nu / p.H, nh = nu - nb * p.H;
+#pragma unroll
+                        for (int j = 0; j < KBOX; ++j) {
+                            tma_prefetch_l2_3d(&p.tmKV, E + nh * HD + 64 * j, 0, nb);
+                            tma_prefetch_l2_3d(&p.tmKV, 2 * E + nh * HD + 64 * j, 0, nb);
+                            tma_prefetch_l2_3d(&p.tmQf, nh * HD + 64 * j, 0, nb);
+                            tma_prefetch_l2_3d(&p.tmDf, nh * HD + 64 * j, 0, nb);
+                        }
+                    }
                 }
             }
         }
@@ -330,11 +349,16 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                 const int nrows = min(BU_BM, (qt ? Qt : Ft) - row0);
                 const bool valid = row < nrows;
                 const size_t grow = qt ? static_cast<size_t>(p.B) * Ft + static_cast<size_t>(b) * Qt + row0 + row : static_cast<size_t>(b) * Ft + row;
+                const T* kown = qkv + (valid ? grow : 0) * ld + E + h * HD;
+                uint4 kreg[HD / 8];                                  // own-key row (query tiles): fetched under the tile's products
+                if (qt && valid) {
+#pragma unroll
+                    for (int c = 0; c < HD / 8; ++c) kreg[c] = __ldg(reinterpret_cast<const uint4*>(kown + 8 * c));
+                }
                 mbar_wait(p_full, g & 1u);                           // the softmax warps' per-row statistics are in shared memory
                 mbar_wait(o_full, g & 1u);
                 tc_fence_after();
                 const float dss = qt ? lds_f32(stat_base + static_cast<uint32_t>((g & 1u) * 512 + row * 4)) : 0.0f;
-                const T* kown = qkv + (valid ? grow : 0) * ld + E + h * HD;
                 T* oq = dqkv + grow * ld + h * HD;
 #pragma unroll
                 for (int c = 0; c < HD / 16; ++c) {
@@ -346,7 +370,7 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
 #pragma unroll
                         for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
                         if (qt) {
-                            const uint4 k0 = __ldg(reinterpret_cast<const uint4*>(kown + 16 * c)), k1 = __ldg(reinterpret_cast<const uint4*>(kown + 16 * c + 8));
+                            const uint4 k0 = kreg[2 * c], k1 = kreg[2 * c + 1];
                             const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
