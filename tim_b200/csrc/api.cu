@@ -97,7 +97,7 @@ struct tim_ctx {
     uint64_t launches = 0;
     EncodeTiledFn encode = nullptr;
     int gemm_version = 2;       // 2: CTA-pair kernel where the shape allows, 1: single-CTA kernel only (TIM_B200_GEMM=1)
-    int attn_version = 2;       // 2: tcgen05 attention where the shape allows, 1: warp-MMA attention only (TIM_B200_ATTN=1)
+    int attn_version = 3;       // 3: tcgen05 attention, deeper pipeline (attention_umma3.cu); 2: the r01 tcgen05 kernel; 1: warp-MMA attention only (TIM_B200_ATTN)
     bool fold_ln = false;       // encoder LayerNorms folded into the GEMMs around them (16-bit path, CTA-pair kernel shapes; TIM_B200_FOLD=0 disables)
     bool fold_dirty = true;     // a weight changed since the folded copies were made
     bool planes = true;         // folded flow keeps the residual stream as two 16-bit planes (mode 7); TIM_B200_PLANES=0: fp32 + 16-bit copy (mode 5)
@@ -519,6 +519,12 @@ int prepare_attention(tim_ctx* c, AttnUmmaParams* ap, bool* use_umma, const T* q
     return TIM_OK;
 }
 
+// tcgen05 attention forward: the deeper-pipeline kernel (attention_umma3.cu) unless TIM_B200_ATTN=2 asks for the r01 form
+template <typename T>
+cudaError_t launch_attention_tc(const tim_ctx* c, const AttnUmmaParams& ap, cudaStream_t s) {
+    return c->attn_version >= 3 ? launch_attention_umma3<T>(ap, c->hd, c->num_sms, s) : launch_attention_umma<T>(ap, c->hd, c->num_sms, s);
+}
+
 inline Epilogue epi(void* out, int ldo, bool out_fp32, int act = ACT_NONE, const float* resid = nullptr, int ldr = 0) {
     Epilogue e;
     e.bias = nullptr; e.resid = resid; e.ldr = ldr; e.out = out; e.ldo = ldo; e.out_fp32 = out_fp32 ? 1 : 0; e.act = act;
@@ -773,7 +779,7 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
         if constexpr (f32) {
             LAUNCH_C(c, 1, attn_flops, s, launch_attention_simt(reinterpret_cast<const float*>(qkv), reinterpret_cast<float*>(att), B, Ft, Qt, c->H, c->hd, s));
         } else if (attn_umma) {
-            LAUNCH_C(c, 1, attn_flops, s, launch_attention_umma<T>(attn_p, c->hd, c->num_sms, s));
+            LAUNCH_C(c, 1, attn_flops, s, launch_attention_tc<T>(c, attn_p, s));
         } else {
             LAUNCH_C(c, 1, attn_flops, s, launch_attention_mma<T>(qkv, att, B, Ft, Qt, c->H, c->hd, s));
         }
@@ -972,7 +978,7 @@ int tim_create(tim_ctx** out, const tim_config* cfg, int device) {
     c->vn_tokens = g.variant == TIM_RECOGNITION && g.include_verb_noun && c->vis_data;
     c->esize = g.compute_dtype == TIM_FP32 ? 4 : 2;
     if (const char* gv = std::getenv("TIM_B200_GEMM")) c->gemm_version = std::atoi(gv) == 1 ? 1 : 2;
-    if (const char* av = std::getenv("TIM_B200_ATTN")) c->attn_version = std::atoi(av) == 1 ? 1 : 2;
+    if (const char* av = std::getenv("TIM_B200_ATTN")) { const int v = std::atoi(av); c->attn_version = v < 1 ? 1 : (v > 3 ? 3 : v); }
     if (const char* wv = std::getenv("TIM_B200_WGRAD_SPLITS")) c->wgrad_splits = std::atoi(wv);
     if (c->d % 4) return bail(c->fail(TIM_ERR_INVALID, "d_model must be a multiple of 4"));
     if (c->vis_data && !g.n_action) return bail(c->fail(TIM_ERR_INVALID, "visual data modality needs n_action > 0"));
@@ -1612,7 +1618,7 @@ int tim_bench_attention(int dtype, const void* qkv16, void* out16, int B, int Ft
     }
     if (dtype != TIM_BF16 && dtype != TIM_FP16) return fin(c->fail(TIM_ERR_INVALID, "tim_bench_attention: 16-bit dtypes only"));
     c->num_sms = prop.multiProcessorCount; c->device = dev; c->cfg.compute_dtype = dtype; c->esize = 2;
-    c->H = H; c->hd = hd; c->E = H * hd; c->attn_version = version == 1 ? 1 : 2;
+    c->H = H; c->hd = hd; c->E = H * hd; c->attn_version = version < 1 ? 1 : (version > 3 ? 3 : version);
     int r = get_encode_fn(c);
     if (r) return fin(r);
     cudaStream_t s = nullptr;
@@ -1626,7 +1632,7 @@ int tim_bench_attention(int dtype, const void* qkv16, void* out16, int B, int Ft
         TIM_TRY(prepare_attention<TT>(c, &ap, &use_umma, static_cast<const TT*>(qkv16), static_cast<TT*>(out16), B, Ft, Qt));
         for (int i = 0; i < iters + 2 && e == cudaSuccess; ++i) {
             if (i == 2) cudaEventRecord(e0, s);
-            e = use_umma ? launch_attention_umma<TT>(ap, hd, c->num_sms, s)
+            e = use_umma ? launch_attention_tc<TT>(c, ap, s)
                          : launch_attention_mma<TT>(static_cast<const TT*>(qkv16), static_cast<TT*>(out16), B, Ft, Qt, H, hd, s);
         }
         return TIM_OK;
@@ -1663,7 +1669,7 @@ int tim_test_attention(int dtype, const float* qkv, float* out, int B, int Ft, i
         }
         c->num_sms = prop.multiProcessorCount; c->device = dev; c->cfg.compute_dtype = dtype; c->esize = 2;
         c->H = H; c->hd = hd; c->E = static_cast<int>(E);
-        if (const char* av = std::getenv("TIM_B200_ATTN")) c->attn_version = std::atoi(av) == 1 ? 1 : 2;
+        if (const char* av = std::getenv("TIM_B200_ATTN")) { const int v = std::atoi(av); c->attn_version = v < 1 ? 1 : (v > 3 ? 3 : v); }
         int rc = get_encode_fn(c);
         if (rc) return fin(rc);
         // same dispatch as the forward: tcgen05 kernel where the shape allows, warp-MMA kernel otherwise
@@ -1672,7 +1678,7 @@ int tim_test_attention(int dtype, const float* qkv, float* out, int B, int Ft, i
             AttnUmmaParams ap;
             bool use_umma = false;
             if (prepare_attention<TT>(c, &ap, &use_umma, qp, op, B, Ft, Qt) != TIM_OK) return cudaErrorInvalidValue;
-            if (use_umma) return launch_attention_umma<TT>(ap, hd, c->num_sms, s);
+            if (use_umma) return launch_attention_tc<TT>(c, ap, s);
             return launch_attention_mma<TT>(qp, op, B, Ft, Qt, H, hd, s);
         };
         if (t.alloc(&q16, M * 3 * E * 2) != cudaSuccess || t.alloc(&o16, M * E * 2) != cudaSuccess) return fin(c->fail(TIM_ERR_NOMEM, "alloc"));

@@ -134,6 +134,11 @@ size_t attention_umma_smem(int Ft, int hd);
 template <typename T>
 cudaError_t launch_attention_umma(AttnUmmaParams p, int hd, int num_sms, cudaStream_t s);
 
+// deeper-pipeline form (attention_umma3.cu): one buffer and 128 TMEM columns per tile in flight, own-key / own-value terms by the
+// thread that owns the row; same parameter block and tensor maps
+template <typename T>
+cudaError_t launch_attention_umma3(AttnUmmaParams p, int hd, int num_sms, cudaStream_t s);
+
 cudaError_t launch_attention_simt(const float* qkv, float* out, int B, int Ft, int Qt, int H, int hd, cudaStream_t s);
 size_t attention_simt_smem(int Ft, int hd);
 

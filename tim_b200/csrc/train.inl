@@ -343,7 +343,7 @@ int encoder_train_fwd(tim_ctx* c, const float* vis, const float* aud, const floa
             AttnUmmaParams attn_p;
             bool attn_umma = false;
             TIM_TRY(prepare_attention<T>(c, &attn_p, &attn_umma, static_cast<const T*>(t.qkv), static_cast<T*>(t.att), B, Ft, Qt));
-            if (attn_umma) LAUNCH_C(c, 1, attn_flops, s, launch_attention_umma<T>(attn_p, c->hd, c->num_sms, s));
+            if (attn_umma) LAUNCH_C(c, 1, attn_flops, s, launch_attention_tc<T>(c, attn_p, s));
             else LAUNCH_C(c, 1, attn_flops, s, launch_attention_mma<T>(static_cast<const T*>(t.qkv), static_cast<T*>(t.att), B, Ft, Qt, c->H, c->hd, s));
         }
         if constexpr (f32) {

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Isolated timing of the attention kernels (C-ABI hook tim_bench_attention) on a B200.
 
-    python tools/attn_bench.py [--versions 1,2] [--dtype fp16] [--shapes cfg2,cfg3,cfg4]
+    python tools/attn_bench.py [--versions 1,2,3] [--dtype fp16] [--shapes cfg2,cfg3,cfg4]
 Reports ms per launch and achieved HBM GB/s on the algorithmic bytes (qkv read once + out written once = 8 * E bytes/row),
 and checks version 2 against version 1 on the same input.
 """
@@ -26,7 +26,7 @@ SHAPES = {  # name: (B, Ft, Qt, H, hd)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--versions", default="1,2")
+    ap.add_argument("--versions", default="1,2,3", help="1 warp-MMA, 2 tcgen05 (r01 form), 3 tcgen05 deeper pipeline")
     ap.add_argument("--dtype", default="fp16")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--shapes", default="cfg2,cfg3,cfg4")
@@ -53,9 +53,10 @@ def main():
             gbs = M * 8 * E / (ms.value * 1e-3) / 1e9
             outs[v] = out
             print(f"{name:6s} v{v} B={B} Ft={Ft} Qt={Qt} H={H} hd={hd}: {ms.value * 1e3:9.1f} us  {gbs:8.1f} GB/s algorithmic", flush=True)
-        if 1 in outs and 2 in outs:
-            d = (outs[1].float() - outs[2].float()).norm() / outs[1].float().norm()
-            print(f"{name:6s} v2 vs v1 rel-L2 {d.item():.2e}")
+        for v in (2, 3):
+            if 1 in outs and v in outs:
+                d = (outs[1].float() - outs[v].float()).norm() / outs[1].float().norm()
+                print(f"{name:6s} v{v} vs v1 rel-L2 {d.item():.2e}")
 
 
 if __name__ == "__main__":
