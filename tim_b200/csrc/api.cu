@@ -97,7 +97,7 @@ struct tim_ctx {
     uint64_t launches = 0;
     EncodeTiledFn encode = nullptr;
     int gemm_version = 2;       // 2: CTA-pair kernel where the shape allows, 1: single-CTA kernel only (TIM_B200_GEMM=1)
-    int attn_version = 3;       // 3: tcgen05 attention, deeper pipeline (attention_umma3.cu); 2: the r01 tcgen05 kernel; 1: warp-MMA attention only (TIM_B200_ATTN)
+    int attn_version = 2;       // 2: tcgen05 attention (attention_umma.cu, default); 3: the deeper-pipeline form (attention_umma3.cu: measured slower, kept for A/B); 1: warp-MMA attention only (TIM_B200_ATTN)
     bool fold_ln = false;       // encoder LayerNorms folded into the GEMMs around them (16-bit path, CTA-pair kernel shapes; TIM_B200_FOLD=0 disables)
     bool fold_dirty = true;     // a weight changed since the folded copies were made
     bool planes = true;         // folded flow keeps the residual stream as two 16-bit planes (mode 7); TIM_B200_PLANES=0: fp32 + 16-bit copy (mode 5)
@@ -519,7 +519,7 @@ int prepare_attention(tim_ctx* c, AttnUmmaParams* ap, bool* use_umma, const T* q
     return TIM_OK;
 }
 
-// tcgen05 attention forward: the deeper-pipeline kernel (attention_umma3.cu) unless TIM_B200_ATTN=2 asks for the r01 form
+// tcgen05 attention forward: attention_umma.cu; TIM_B200_ATTN=3 selects the deeper-pipeline form (attention_umma3.cu, measured slower)
 template <typename T>
 cudaError_t launch_attention_tc(const tim_ctx* c, const AttnUmmaParams& ap, cudaStream_t s) {
     return c->attn_version >= 3 ? launch_attention_umma3<T>(ap, c->hd, c->num_sms, s) : launch_attention_umma<T>(ap, c->hd, c->num_sms, s);

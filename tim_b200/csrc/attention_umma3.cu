@@ -11,6 +11,14 @@
 //   head_dim 64 / 128 : 4 tiles in flight (K_f / V_f 56 KB + 4 x 33 KB);  head_dim 192 : 2 (was 1).
 // HBM traffic is unchanged (qkv read once, out written once).
 //
+// MEASURED (profiles/r02g_attn_bench.txt, same visit, isolated launches): correct (equal to the warp-MMA kernel to 7e-6, 116 forward
+// tests green with it as the default) but SLOWER than attention_umma.cu - cfg2 538 us against 344 us, cfg4 766 against 404, head_dim
+// 192 717 against 689 - and the stage count does not matter (2 / 3 / 4 stages: 510 / 544 / 541 us). So the forward kernel was never
+// pipeline-depth-bound: its limit is the throughput of the four softmax warps (one thread per row, one warp per scheduler), and
+// moving the own-key dot product from the idle tensor core (the S_self trick) onto those warps costs more than the extra stages
+// give. NOT the default (TIM_B200_ATTN=3 selects it); kept as the measured A/B partner and for what it says about where to go next:
+// more threads per row in the softmax role, not more tiles in flight.
+//
 // One persistent CTA per SM, 320 threads: warp 0 TMA producer (+ L2 prefetch of the next tiles and of the own k / v rows),
 // warp 1 MMA issuer (S(t+1) is issued before O(t)), warps 2-5 softmax (one thread per row), warps 6-9 epilogue.
 #include <cstdio>

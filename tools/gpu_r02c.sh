@@ -22,7 +22,7 @@ if [ "$NG" -ge 2 ]; then
 import json
 try:
     d = json.load(open("$OUT/bench_${NG}gpu_$TAG.json"))
-    print("value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"], "e2e_fp32", d["e2e_fp32_io"]["value"], "e2e16", d["e2e_fp16_logits"]["value"])
+    print("value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"], "e2e_fp32", d["e2e_fp32_io"]["value"], "e2e16", d["e2e_fp32_logits"]["value"])
     t = d["train"]; print("train ms", t["ms_per_step"], t["breakdown_ms"], t["allreduce_bytes"])
     c = d["cfg4"]; print("cfg4", c["value"], c["ms_per_step"], "e2e", c["e2e"]["value"], "train", c["train"]["ms_per_step"], c["train"]["breakdown_ms"])
 except Exception as e:
@@ -34,7 +34,7 @@ else
 import json
 try:
     d = json.load(open("$OUT/bench_$TAG.json"))
-    print("value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"], "e2e_fp32", d["e2e_fp32_io"]["value"], "e2e16", d["e2e_fp16_logits"]["value"])
+    print("value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"]["value"], d["e2e"]["ms_per_step"], "e2e_fp32", d["e2e_fp32_io"]["value"], "e2e16", d["e2e_fp32_logits"]["value"])
     t = d["train"]; print("train ms", t["ms_per_step"], t["breakdown_ms"], t["class_ms_per_step"])
     c = d["cfg4"]; print("cfg4", c["value"], c["ms_per_step"], "e2e", c["e2e"]["value"], "train", c["train"]["ms_per_step"])
 except Exception as e:

@@ -13,7 +13,7 @@ echo "bench exit $?"; python - <<PY
 import json
 try:
     d = json.load(open("$OUT/bench_$TAG.json"))
-    print("fwd ms/step", d["ms_per_step"], "value", d["value"], "e2e", d["e2e"]["value"], "fp32io", d["e2e_fp32_io"]["value"], "fp16 logits", d["e2e_fp16_logits"]["value"], "bank", d["e2e_resident_bank"]["value"])
+    print("fwd ms/step", d["ms_per_step"], "value", d["value"], "e2e", d["e2e"]["value"], "fp32io", d["e2e_fp32_io"]["value"], "fp16 logits", d["e2e_fp32_logits"]["value"], "bank", d["e2e_resident_bank"]["value"])
     print("gemm frac", d["roofline"]["frac"], "path frac", d["roofline"]["path_frac"], d["roofline"]["class_ms_per_step"], "clocks", d["clocks"])
     t = d["train"]; print("train ms/step", t["ms_per_step"], t["breakdown_ms"], "path_frac", t["path_frac"], t["class_ms_per_step"])
     c = d["cfg4"]; print("cfg4 fwd ms", c["ms_per_step"], "value", c["value"], "e2e", c["e2e"]["value"], "train ms", c["train"]["ms_per_step"])
