@@ -202,8 +202,8 @@ int tim_det_emit(const float* preds, const double* proposals, int64_t R, int C, 
  * Training leg. Replaces what torch.autograd + DistributedDataParallel do for this path when the
  * reference trains: recognition/scripts/train.py:190-260 (forward under autocast), :354-366 (GradScaler.scale(loss).backward(),
  * optimizer step), recognition/time_interval_machine/models/build.py:58-63 (DDP bucketed gradient all-reduce),
- * detection/time_interval_machine/models/tim.py:272-337 (forward_train). Dropout is NOT applied (p = 0 semantics; the Python
- * drop-in refuses modules whose dropout probability is non-zero instead of silently diverging).
+ * detection/time_interval_machine/models/tim.py:272-337 (forward_train). Dropout: tim_set_dropout (all six nn.Dropout sites of the
+ * reference, statistically equivalent masks from a counter-based hash instead of torch's Philox stream).
  *
  *  tim_train_enable      allocates the transposed weight copies the input-gradient GEMMs read; every weight must be set (again)
  *                        with tim_set_weight afterwards.
@@ -224,6 +224,13 @@ int tim_det_emit(const float* preds, const double* proposals, int64_t R, int C, 
  * keep the reference's GradScaler (train.py:354-366) so that small gradients do not underflow. */
 int tim_train_enable(tim_ctx* ctx);
 int tim_bind_grad(tim_ctx* ctx, const char* key, float* dst);
+/* Dropout of the NEXT tim_encoder_fwd_train (and of its backward): p_feat = the embedders' input dropout (helpers/encodings.py:141,149),
+ * p_seq = dropout of the assembled token sequence (:177), p_enc = the transformer's four sites - attention probabilities, dropout1,
+ * the FFN's inner dropout, dropout2 (helpers/transformers.py:73-82, 102-108). No mask is stored: keep decisions are a pure function
+ * of (seed, site, layer, element) - one 32-bit hash per pair of elements, described next to DropSite in tim_b200/csrc/kernels.h -
+ * and are re-evaluated by the backward. Pass a fresh seed every step. All zero (the default) = no dropout. 16-bit modes need
+ * head_dim 64 or 128 for p_enc > 0 (the tcgen05 attention kernels carry the probability dropout). */
+int tim_set_dropout(tim_ctx* ctx, float p_feat, float p_seq, float p_enc, uint64_t seed);
 int tim_time_mlp_fwd_train(tim_ctx* ctx, const float* times, float* out, int B, int T, void* stream);
 int tim_time_mlp_bwd(tim_ctx* ctx, const float* d_out, void* stream);
 int tim_encoder_fwd_train(tim_ctx* ctx, const float* vis, const float* aud, const float* time_enc, int B, int T, int Qv, int Qa,

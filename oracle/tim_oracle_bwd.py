@@ -1,10 +1,13 @@
-"""CPU restatement (numpy) of the BACKWARD of the reference TIM forward - TEST INFRASTRUCTURE ONLY, groundwork for the training
-leg: no CUDA path uses or mirrors it yet. Same import rules as oracle/tim_oracle.py.
+"""CPU restatement (numpy) of the BACKWARD of the reference TIM forward - TEST INFRASTRUCTURE ONLY (SURVEY.md §8f row 1,
+DESIGN.md §9): the checker of the CUDA training leg, never on its path. Same import rules as oracle/tim_oracle.py.
 
 What it differentiates: exactly the graph oracle/tim_oracle.py restates (time MLP -> token assembly -> L post-LN encoder layers with
 dense masked attention -> CLS / regression heads, plus the feature rows returned for the drloc loss), i.e. what autograd records
-when the reference runs  recognition/.../models/tim.py:147-172  /  detection/.../models/tim.py:339-400  with dropout 0. The
-reference has no hand-written backward: gradients come from torch.autograd over
+when the reference runs  recognition/.../models/tim.py:147-172  /  detection/.../models/tim.py:339-400. Dropout: the
+reference's six nn.Dropout sites (helpers/encodings.py:141,149,177; helpers/transformers.py:73-82,102-108) take their masks from
+torch's RNG, which no other implementation can reproduce; with `dropout=` given, this oracle applies at the same six sites the
+masks of the library's counter-based hash (drop_mask below restates tim_b200/csrc/kernels.h: DropSite), so gradient parity is
+checked mask for mask. The reference has no hand-written backward: gradients come from torch.autograd over
   nn.Linear / ReLU / GELU(erf) / LayerNorm      (tim.py:66-74, helpers/encodings.py:140-153, helpers/transformers.py:75-111, helpers/head.py)
   F.multi_head_attention_forward                (q scaled before q.k^T, boolean mask -> -inf, softmax over keys)
   torch.cat / broadcast of the CLS parameters and modality encodings (helpers/encodings.py:181-251).
@@ -22,6 +25,56 @@ import numpy as np
 
 from oracle.tim_oracle import TIMOracle, _erf, _gelu, _relu
 from tim_b200.config import RECOGNITION
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the library's dropout masks (tim_b200/csrc/kernels.h: DropSite / make_drop_site, ptx.cuh: drop_hash)
+# ---------------------------------------------------------------------------------------------------------------------
+DROP_FEAT_VIS, DROP_FEAT_AUD, DROP_SEQ, DROP_ATTN, DROP_SUB1, DROP_FFN, DROP_SUB2 = 1, 2, 3, 4, 5, 6, 7
+DROP_ATTN_KW = 130
+
+
+def drop_mask(e, p: float, seed: int, site: int, layer: int = 0):
+    """Scaled keep mask (float64: 0 or 65536 / (65536 - thr)) of the elements with flat indices e (any shape, < 2^32)."""
+    e = np.asarray(e, np.uint64)
+    if p <= 0.0:
+        return np.ones(e.shape)
+    thr = min(int(np.float32(p) * np.float32(65536.0) + np.float32(0.5)), 65535)
+    scale = float(np.float32(65536.0) / np.float32(65536 - thr))
+    seed32 = (int(seed) ^ (int(seed) >> 32)) & 0xFFFFFFFF
+    key = (seed32 ^ (site * 0x9E3779B9) ^ (layer * 0x85EBCA6B)) & 0xFFFFFFFF
+    m32 = np.uint64(0xFFFFFFFF)
+    x = ((e >> np.uint64(1)) ^ np.uint64(key)) & m32
+    x ^= x >> np.uint64(16); x = (x * np.uint64(0x7FEB352D)) & m32
+    x ^= x >> np.uint64(15); x = (x * np.uint64(0x846CA68B)) & m32
+    x ^= x >> np.uint64(16)
+    bits = np.where((e & np.uint64(1)) != 0, x >> np.uint64(16), x & np.uint64(0xFFFF))
+    return np.where(bits >= np.uint64(thr), scale, 0.0)
+
+
+def two_stream_rows(B: int, S: int, Ft: int):
+    """[B, S] -> row of token (b, s) in the library's layout: the B*Ft feature rows first, then the B*(S-Ft) query rows."""
+    b = np.arange(B)[:, None]
+    sidx = np.arange(S)[None, :]
+    Qt = S - Ft
+    return np.where(sidx < Ft, b * Ft + sidx, B * Ft + b * Qt + (sidx - Ft))
+
+
+def row_drop_mask(B: int, S: int, Ft: int, width: int, p: float, seed: int, site: int, layer: int = 0):
+    """[B, S, width] mask of a token-row site (seq_drop, dropout1, the FFN's dropout, dropout2): element = library row * width + column."""
+    rows = two_stream_rows(B, S, Ft)
+    return drop_mask(rows[..., None] * width + np.arange(width), p, seed, site, layer)
+
+
+def attn_drop_mask(B: int, H: int, S: int, Ft: int, p: float, seed: int, layer: int):
+    """[B, H, S, S] mask of the attention probabilities: element = ((b H + h) S + row) * DROP_ATTN_KW + key index, where the key index
+    of feature key j is j and a query row's own key is Ft (the other entries are removed by the attention mask anyway)."""
+    kidx = np.broadcast_to(np.arange(S)[None, :], (S, S)).copy()
+    qrows = np.arange(S) >= Ft
+    kidx[qrows, np.arange(S)[qrows]] = Ft
+    kidx = np.minimum(kidx, DROP_ATTN_KW - 1)
+    base = ((np.arange(B)[:, None, None] * H + np.arange(H)[None, :, None]) * S + np.arange(S)[None, None, :]) * DROP_ATTN_KW
+    return drop_mask(base[..., None] + kidx[None, None], p, seed, DROP_ATTN, layer)
 
 
 def _ln_fwd(x, w, b, eps=1e-5):
@@ -57,9 +110,20 @@ class TIMOracleGrad(TIMOracle):
     """forward_backward(...) -> (outputs, grads): grads maps every reference state_dict key that receives a gradient, plus
     'input.vis' / 'input.aud', to d L / d tensor for L = sum_k <outputs[k], cot[k]>."""
 
-    def forward_backward(self, vis, aud, times, Qv: int, Qa: int, cot: Dict[str, np.ndarray]):
+    def forward_backward(self, vis, aud, times, Qv: int, Qa: int, cot: Dict[str, np.ndarray], dropout: Optional[dict] = None):
+        """dropout: None, or {"p_feat", "p_seq", "p_enc", "seed"} - the arguments of tim_set_dropout."""
         cfg, s, dt = self.cfg, self.sd, self.dt
         g: Dict[str, np.ndarray] = {}
+        dr = dropout or {}
+        p_feat, p_seq, p_enc, seed = dr.get("p_feat", 0.0), dr.get("p_seq", 0.0), dr.get("p_enc", 0.0), dr.get("seed", 0)
+        feat_mask = {}
+        if p_feat > 0.0:                                  # feat_drop: flat index over the [B, F, dim] input
+            if vis is not None:
+                feat_mask["visual"] = drop_mask(np.arange(np.size(vis)).reshape(np.shape(vis)), p_feat, seed, DROP_FEAT_VIS).astype(dt)
+                vis = np.asarray(vis, dt) * feat_mask["visual"]
+            if aud is not None:
+                feat_mask["audio"] = drop_mask(np.arange(np.size(aud)).reshape(np.shape(aud)), p_feat, seed, DROP_FEAT_AUD).astype(dt)
+                aud = np.asarray(aud, dt) * feat_mask["audio"]
 
         def acc(key, val):
             g[key] = g[key] + val if key in g else val
@@ -86,6 +150,18 @@ class TIMOracleGrad(TIMOracle):
         B, S, E = x.shape
         H, hd, d = cfg.nhead, cfg.head_dim, cfg.d_model
         mask = self.mask(S)
+        Ft = cfg.F_tot
+
+        def row_mask(width, p, site, layer=0):
+            return row_drop_mask(B, S, Ft, width, p, seed, site, layer).astype(dt)
+
+        def attn_mask(layer):
+            return attn_drop_mask(B, H, S, Ft, p_enc, seed, layer).astype(dt)
+
+        seq_m = None
+        if p_seq > 0.0:
+            seq_m = row_mask(E, p_seq, DROP_SEQ)
+            x = x * seq_m
         layers = []
         for l in range(cfg.num_layers):
             p = f"{cfg.encoder_prefix}.layers.{l}."
@@ -96,13 +172,24 @@ class TIMOracleGrad(TIMOracle):
             sc = np.where(mask[None, None], dt.type(-np.inf), q @ k.transpose(0, 1, 3, 2))
             pr = np.exp(sc - sc.max(axis=-1, keepdims=True))
             pr = pr / pr.sum(axis=-1, keepdims=True)
-            ctx = (pr @ v).transpose(0, 2, 1, 3).reshape(B, S, E)
+            dm = None
+            if p_enc > 0.0:
+                dm = (attn_mask(l), row_mask(E, p_enc, DROP_SUB1, l), row_mask(cfg.FF, p_enc, DROP_FFN, l), row_mask(E, p_enc, DROP_SUB2, l))
+            prd = pr * dm[0] if dm else pr                            # the probabilities that meet V (F.multi_head_attention_forward's dropout)
+            ctx = (prd @ v).transpose(0, 2, 1, 3).reshape(B, S, E)
             a = ctx @ s[p + "self_attn.out_proj.weight"].T + s[p + "self_attn.out_proj.bias"]
+            if dm:
+                a = a * dm[1]
             x1, ln1 = _ln_fwd(x + a, s[p + "norm1.weight"], s[p + "norm1.bias"])
             hpre = x1 @ s[p + "linear1.weight"].T + s[p + "linear1.bias"]
             hact = _gelu(hpre)
-            x2, ln2 = _ln_fwd(x1 + hact @ s[p + "linear2.weight"].T + s[p + "linear2.bias"], s[p + "norm2.weight"], s[p + "norm2.bias"])
-            layers.append((x, q, k, v, pr, ctx, ln1, x1, hpre, hact, ln2))
+            if dm:
+                hact = hact * dm[2]
+            f = hact @ s[p + "linear2.weight"].T + s[p + "linear2.bias"]
+            if dm:
+                f = f * dm[3]
+            x2, ln2 = _ln_fwd(x1 + f, s[p + "norm2.weight"], s[p + "norm2.bias"])
+            layers.append((x, q, k, v, pr, prd, dm, ctx, ln1, x1, hpre, hact, ln2))
             x = x2
         out = self.heads(x, Qv, Qa)
         out["feats"] = x[:, :cfg.F_tot]
@@ -167,18 +254,24 @@ class TIMOracleGrad(TIMOracle):
 
         for l in reversed(range(cfg.num_layers)):
             p = f"{cfg.encoder_prefix}.layers.{l}."
-            xin, q, k, v, pr, ctx, ln1, x1, hpre, hact, ln2 = layers[l]
+            xin, q, k, v, pr, prd, dm, ctx, ln1, x1, hpre, hact, ln2 = layers[l]
             dz2, dw, db = _ln_bwd(dx, ln2, s[p + "norm2.weight"]); acc(p + "norm2.weight", dw); acc(p + "norm2.bias", db)
-            dh, dw, db = _lin_bwd(dz2, hact, s[p + "linear2.weight"]); acc(p + "linear2.weight", dw); acc(p + "linear2.bias", db)
+            df = dz2 * dm[3] if dm else dz2
+            dh, dw, db = _lin_bwd(df, hact, s[p + "linear2.weight"]); acc(p + "linear2.weight", dw); acc(p + "linear2.bias", db)
+            if dm:
+                dh = dh * dm[2]
             dhp = _gelu_bwd(dh, hpre)
             dx1, dw, db = _lin_bwd(dhp, x1, s[p + "linear1.weight"]); acc(p + "linear1.weight", dw); acc(p + "linear1.bias", db)
             dx1 = dx1 + dz2
             dz1, dw, db = _ln_bwd(dx1, ln1, s[p + "norm1.weight"]); acc(p + "norm1.weight", dw); acc(p + "norm1.bias", db)
-            dctx, dw, db = _lin_bwd(dz1, ctx, s[p + "self_attn.out_proj.weight"])
+            da = dz1 * dm[1] if dm else dz1
+            dctx, dw, db = _lin_bwd(da, ctx, s[p + "self_attn.out_proj.weight"])
             acc(p + "self_attn.out_proj.weight", dw); acc(p + "self_attn.out_proj.bias", db)
             dctx = dctx.reshape(B, S, H, hd).transpose(0, 2, 1, 3)
             dpr = dctx @ v.transpose(0, 1, 3, 2)
-            dv = pr.transpose(0, 1, 3, 2) @ dctx
+            if dm:
+                dpr = dpr * dm[0]
+            dv = prd.transpose(0, 1, 3, 2) @ dctx
             dsc = pr * (dpr - (dpr * pr).sum(axis=-1, keepdims=True))          # masked entries have pr = 0
             dq = (dsc @ k) * dt.type(hd ** -0.5)
             dk = dsc.transpose(0, 1, 3, 2) @ q
@@ -191,6 +284,8 @@ class TIMOracleGrad(TIMOracle):
             dx = dz1 + dxa
 
         # ------------------------------------------------------------------ token assembly (encodings.py) backward
+        if seq_m is not None:
+            dx = dx * seq_m
         dte = np.zeros_like(te)
         if cot.get("time_encodings") is not None:
             dte += np.asarray(cot["time_encodings"], dt)
@@ -244,6 +339,8 @@ class TIMOracleGrad(TIMOracle):
             dact, dw, db = _ln_bwd(de, ln, s[p + "3.weight"]); acc(p + "3.weight", dw); acc(p + "3.bias", db)
             dpre = _gelu_bwd(dact, pre)
             dxin, dw, db = _lin_bwd(dpre, xin, s[p + "1.weight"]); acc(p + "1.weight", dw); acc(p + "1.bias", db)
+            if which in feat_mask:
+                dxin = dxin * feat_mask[which]
             g["input.vis" if which == "visual" else "input.aud"] = dxin
 
         # ------------------------------------------------------------------ time MLP backward (tim.py:66-74)

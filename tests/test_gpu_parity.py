@@ -339,14 +339,19 @@ def test_patch_model_dropin(lib, name, dt):
     assert set(model.state_dict().keys()) >= set(sd.keys())                  # the module tree / checkpoint layout is untouched
     with pytest.raises(ValueError):
         model.eval()(times, "no_such_forward_type")
-    # train() mode: a module that would apply dropout is refused (the training leg has no dropout kernels) instead of being run
-    # without it - also under no_grad, where the reference still applies dropout (helpers/transformers.py:73-82)
+    # train() mode under no_grad: the reference still applies dropout (helpers/transformers.py:73-82), so does the drop-in - the
+    # encoder output of a train()-mode module with non-zero probabilities differs from the eval() output, and with all
+    # probabilities zero it does not
     if cfg.variant == "recognition":
-        m2 = FakeTIM(cfg, sd).to(dev)
-        m2.add_module("extra_dropout", torch.nn.Dropout(0.5))
-        m2 = patch_model(m2.train(), compute_dtype=dt)
-        with pytest.raises(NotImplementedError), torch.no_grad():
-            m2(times, "time_mlp")
+        outs = {}
+        for tag, pr in (("p0", 0.0), ("p", 0.3)):
+            m2 = patch_model(FakeTIM(cfg, sd, feat_drop=pr, seq_drop=pr, enc_dropout=pr if dt == "fp32" else 0.0).to(dev).train(), compute_dtype=dt)
+            with torch.no_grad():
+                te = m2(times, "time_mlp")
+                outs[tag] = m2([vis, aud], "encoder", te, Qv, Qa)[0][2].float().cpu().numpy()
+        ev = run()["action"].float().cpu().numpy()
+        assert rel_l2(outs["p0"], ev) <= 5 * tol
+        assert rel_l2(outs["p"], ev) > 0.05
 
 
 @pytest.mark.parametrize("name", ["vn", "act", "aud"])

@@ -146,8 +146,9 @@ def cotangents(name, shapes):
     return {k: np.random.default_rng(zlib.crc32(f"{name}/{k}".encode())).standard_normal(tuple(shp)) for k, shp in shapes.items()}
 
 
-def engine_grads(cfg, sd, inp, Qv, Qa, dt, cot_fn, repeat=1):
-    """time_mlp + encoder forward in training mode, backward with the given cotangents -> (outputs, {key: gradient})."""
+def engine_grads(cfg, sd, inp, Qv, Qa, dt, cot_fn, repeat=1, dropout=None):
+    """time_mlp + encoder forward in training mode, backward with the given cotangents -> (outputs, {key: gradient}).
+    dropout: kwargs of TIMEngine.set_dropout."""
     from tim_b200.plugin import TIMEngine
     dev = torch.device("cuda", 0)
     eng = TIMEngine(cfg, 0, dt)
@@ -159,6 +160,8 @@ def engine_grads(cfg, sd, inp, Qv, Qa, dt, cot_fn, repeat=1):
     vis = torch.from_numpy(inp["vis"]).to(dev) if "vis" in inp else None
     aud = torch.from_numpy(inp["aud"]).to(dev) if "aud" in inp else None
     times = torch.from_numpy(inp["times"]).to(dev)
+    if dropout:
+        eng.set_dropout(**dropout)
     for _ in range(repeat):
         te = eng.time_mlp_train(times)
         out = eng.encoder_train(vis, aud, te, Qv, Qa)
@@ -279,7 +282,7 @@ def test_gradients_named_configs_fp16_vs_fp32_path(lib, name, B):
 def test_patch_model_training_dropin(lib):
     """The autograd drop-in: a module with the reference's parameter tree in train() mode -> loss.backward() fills param.grad (views
     of one flat buffer), optimizer.zero_grad() (set_to_none) between steps is survived, an optimizer step is picked up by the next
-    forward, non-zero dropout is refused."""
+    forward (dropout through the drop-in: test_dropout_dropin below)."""
     from oracle.tim_oracle_bwd import TIMOracleGrad
     from tests._fake_tim import FakeTIM
     from tim_b200.plugin import patch_model
@@ -323,12 +326,152 @@ def test_patch_model_training_dropin(lib):
     from oracle.tim_oracle import TIMOracle
     ref = TIMOracle(cfg, sd_now, np.float32).forward(inp["vis"], inp["aud"], inp["times"], Qv, Qa)
     assert rel_l2(action.cpu().numpy(), ref["action"]) <= 1e-5
-    # dropout is not implemented: a module that would apply it is refused, not silently run without it
-    m2 = FakeTIM(cfg, sd).to(dev)
-    m2.add_module("some_dropout", torch.nn.Dropout(0.1))
-    m2 = patch_model(m2.train(), compute_dtype="fp32")
-    with pytest.raises(NotImplementedError):
-        m2(times, "time_mlp")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# dropout (tim_set_dropout): the library's counter-based masks, restated in numpy by the oracle, which tests/test_dropout_oracle.py
+# pins to torch.autograd over the unmodified reference with the same masks at its own nn.Dropout sites
+# ---------------------------------------------------------------------------------------------------------------------
+def _dropout_cases(dt):
+    from tests.test_dropout_oracle import DROP_CASES
+    # 16-bit modes carry the attention-probability dropout in the tcgen05 kernels (head_dim 64 / 128)
+    return DROP_CASES if dt == "fp32" else [n for n in DROP_CASES if "hd64" in n or "hd128" in n]
+
+
+@pytest.mark.parametrize("dt,name", [(dt, n) for dt in ("fp32", "fp16", "bf16") for n in _dropout_cases(dt)])
+def test_gradients_with_dropout_vs_reference_autograd_golden(lib, name, dt):
+    """All six dropout sites active at the reference's default probabilities (feat 0.5, seq 0.5, encoder 0.1): outputs and every
+    parameter gradient of the CUDA training leg against torch.autograd over the unmodified reference run with the same masks
+    (tests/golden/grads_dropout.npz). A single mask bit that disagreed would show as an O(1/sqrt(n)) error: the fp32 mode's 2e-5
+    proves the masks agree element for element, in the forward and in the backward."""
+    from tests.test_dropout_oracle import _G as g, drop_case
+    cfg, sd, inp, Qv, Qa, cot, drop = drop_case(name)
+    res, grads = engine_grads(cfg, sd, inp, Qv, Qa, dt, lambda shapes: cot, dropout=drop)
+    ftol = {"fp32": 1e-5, "fp16": 3e-3, "bf16": 3e-2}[dt]
+    for k in cot:
+        e = rel_l2(res[k], g[f"{name}/out/{k}"])
+        assert e <= ftol, f"{name}/out/{k} [{dt}]: {e:.3e}"
+    report = {}
+    for k in [str(x) for x in g[f"{name}/keys"] if not str(x).startswith("input.")]:
+        tol = grad_tol(k, dt, False, cfg.variant == "detection")
+        flat = grads[k].astype(np.float64).reshape(-1)
+        idx = np.sort(np.random.default_rng(zlib.crc32(f"idx/{name}/{k}".encode())).choice(flat.size, size=min(512, flat.size), replace=False))
+        vals = g[f"{name}/vals/{k}"]
+        norm = float(g[f"{name}/stat/{k}"][0])
+        rms = norm / np.sqrt(flat.size)
+        e = float(np.sqrt(np.mean((flat[idx] - vals) ** 2))) / max(rms, 1e-30)
+        en = abs(float(np.linalg.norm(flat)) - norm) / max(norm, 1e-30)
+        report[k] = e
+        assert e <= tol and en <= tol, f"{name}/{k} [{dt}] with dropout: sampled rel error {e:.3e}, norm error {en:.3e} > {tol:.0e}"
+    _record(f"dropout/{name}/{dt}", report)
+
+
+@pytest.mark.parametrize("dt", ["fp32", "fp16"])
+def test_dropout_sites_one_at_a_time_vs_oracle(lib, dt):
+    """Each probability on its own (feat only, seq only, encoder only) against the numpy oracle on full tensors, a different seed
+    gives a different result, the same seed the same bits, and p = 0 is the un-dropped forward."""
+    from oracle.tim_oracle_bwd import TIMOracleGrad
+    from tests.test_dropout_oracle import drop_case
+    cfg, sd, inp, Qv, Qa, cot, _ = drop_case("recog_hd64")
+    oracle = TIMOracleGrad(cfg, sd, np.float64)
+    seen = {}
+    for tag, drop in (("feat", dict(p_feat=0.4, seed=11)), ("seq", dict(p_seq=0.25, seed=12)), ("enc", dict(p_enc=0.2, seed=13)),
+                      ("enc2", dict(p_enc=0.2, seed=14)), ("none", dict(seed=15))):
+        res, g1 = engine_grads(cfg, sd, inp, Qv, Qa, dt, lambda shapes: cot, dropout=drop)
+        out_ref, gref = oracle.forward_backward(inp.get("vis"), inp.get("aud"), inp["times"], Qv, Qa, cot, dropout=drop)
+        for k in cot:
+            assert rel_l2(res[k], out_ref[k]) <= {"fp32": 1e-5, "fp16": 3e-3}[dt], (tag, k)
+        for k, ref in gref.items():
+            if not k.startswith("input."):
+                tol = grad_tol(k, dt, False)
+                assert rel_l2(g1[k].reshape(-1), np.asarray(ref).reshape(-1)) <= tol, (tag, k)
+        seen[tag] = res["action"]
+    assert rel_l2(seen["enc"], seen["enc2"]) > 0.02          # another seed, other masks
+    res2, _ = engine_grads(cfg, sd, inp, Qv, Qa, dt, lambda shapes: cot, dropout=dict(p_enc=0.2, seed=13))
+    assert np.array_equal(res2["action"], seen["enc"])       # same seed, same bits
+    res0, _ = engine_grads(cfg, sd, inp, Qv, Qa, dt, lambda shapes: cot)
+    assert np.array_equal(res0["action"], seen["none"])
+
+
+def test_dropout_real_width_averages_out(lib):
+    """cfg2 at its real widths, fp16 (head_dim 128: the tcgen05 attention kernels carry the probability dropout): every dropped
+    forward differs from the p = 0 forward, and the mean over 16 seeds is much closer to it than any single one (kept values are
+    scaled by 1 / (1 - p), so the masks have mean 1)."""
+    cfg, Qv, Qa = named_config("cfg2")
+    sd = synth_state_dict(cfg, 0, "trained")
+    inp = synth_inputs(cfg, 2, Qv, Qa, 7)
+    from tim_b200.plugin import TIMEngine
+    dev = torch.device("cuda", 0)
+    eng = TIMEngine(cfg, 0, "fp16")
+    eng.enable_training()
+    eng.load_state_dict(sd)
+    vis, aud, times = (torch.from_numpy(inp[k]).to(dev) for k in ("vis", "aud", "times"))
+    te = eng.time_mlp_train(times)
+    base = eng.encoder_train(vis, aud, te, Qv, Qa)["feats"].float().clone()
+    acc = torch.zeros_like(base)
+    single = []
+    n = 16
+    for sdd in range(n):
+        eng.set_dropout(0.0, 0.0, 0.1, 1000 + sdd)
+        o = eng.encoder_train(vis, aud, te, Qv, Qa)["feats"].float()
+        single.append(float((o - base).norm() / base.norm()))
+        acc += o
+    mean_err = float((acc / n - base).norm() / base.norm())
+    assert min(single) > 0.01 and mean_err < 0.6 * float(np.mean(single)), (single, mean_err)
+    eng.close()
+
+
+def test_dropout_dropin(lib):
+    """patch_model() in train() mode on a module whose dropout modules hold non-zero probabilities: the probabilities are read
+    from the module, the seed follows torch.manual_seed (same seed -> same loss and gradients, next step -> other masks), and the
+    gradients equal the oracle's for the masks of that seed."""
+    from oracle.tim_oracle_bwd import TIMOracleGrad
+    from tests._fake_tim import FakeTIM
+    from tests.test_dropout_oracle import drop_case
+    from tim_b200.plugin import patch_model
+    cfg, sd, inp, Qv, Qa, cot, _ = drop_case("recog_av_small")
+    dev = torch.device("cuda", 0)
+    vis, aud, times = (torch.from_numpy(inp[k]).to(dev) for k in ("vis", "aud", "times"))
+
+    def step(model):
+        model.zero_grad()
+        te = model(times, "time_mlp")
+        (verb, noun, action, audio), feats = model([vis, aud], "encoder", te, Qv, Qa)
+        outs = dict(verb=verb, noun=noun, action=action, audio=audio, feats=feats)
+        loss = sum((v * torch.from_numpy(cot[k].astype(np.float32)).to(dev)).sum() for k, v in outs.items() if v is not None)
+        loss.backward()
+        return float(loss), {k: p.grad.detach().cpu().numpy().copy() for k, p in model.named_parameters() if p.grad is not None}
+
+    seeds = []
+    runs = []
+    for _ in range(2):
+        torch.manual_seed(4321)
+        model = patch_model(FakeTIM(cfg, sd, feat_drop=0.5, seq_drop=0.5, enc_dropout=0.1).to(dev).train(), compute_dtype="fp32")
+        b = model._tim_b200
+        real = b.engine.set_dropout
+        b.engine.set_dropout = lambda pf, ps, pe, seed, real=real: (seeds.append((pf, ps, pe, seed)), real(pf, ps, pe, seed))[1]
+        runs.append((step(model), step(model)))
+    (l0, g0), (l1, g1) = runs[0]
+    assert runs[1][0][0] == l0 and runs[1][1][0] == l1 and l0 != l1             # reproducible; a new step draws new masks
+    assert seeds[0][:3] == (0.5, 0.5, 0.1) and seeds[0][3] != seeds[1][3] and seeds[0] == seeds[2]
+    _, gref = TIMOracleGrad(cfg, sd, np.float64).forward_backward(inp["vis"], inp["aud"], inp["times"], Qv, Qa, cot,
+                                                                 dropout=dict(p_feat=0.5, p_seq=0.5, p_enc=0.1, seed=seeds[0][3]))
+    for k, ref in gref.items():
+        if not k.startswith("input."):
+            assert rel_l2(g0[k].reshape(-1), np.asarray(ref).reshape(-1)) <= 2e-5, k
+    # eval() mode: no dropout
+    model.eval()
+    with torch.no_grad():
+        te = model(times, "time_mlp")
+        a1 = model([vis, aud], "encoder", te, Qv, Qa)[0][2]
+        a2 = model([vis, aud], "encoder", te, Qv, Qa)[0][2]
+    assert torch.equal(a1, a2)
+    # 16-bit modes: the probability dropout lives in the tcgen05 attention kernels (head_dim 64 / 128); other widths are refused loudly
+    from tim_b200 import _lib
+    m16 = patch_model(FakeTIM(cfg, sd, enc_dropout=0.1).to(dev).train(), compute_dtype="fp16")       # head_dim 32
+    with pytest.raises(_lib.TimError, match="head_dim"):
+        te = m16(times, "time_mlp")
+        m16([vis, aud], "encoder", te, Qv, Qa)
 
 
 def test_training_errors_are_loud(lib):

@@ -80,6 +80,7 @@ SYMBOLS = {
     "tim_fold_check": (C.c_int, [C.c_void_p]),
     "tim_train_enable": (C.c_int, [C.c_void_p]),
     "tim_bind_grad": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p]),
+    "tim_set_dropout": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_uint64]),
     "tim_time_mlp_fwd_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "tim_time_mlp_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tim_encoder_fwd_train": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,

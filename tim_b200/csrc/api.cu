@@ -1384,6 +1384,16 @@ int tim_bind_grad(tim_ctx* c, const char* key, float* dst) {
     return TIM_OK;
 }
 
+int tim_set_dropout(tim_ctx* c, float p_feat, float p_seq, float p_enc, uint64_t seed) {
+    if (!c) return TIM_ERR_INVALID;
+    if (!c->train || !c->train->enabled) return c->fail(TIM_ERR_INVALID, "tim_set_dropout: call tim_train_enable first");
+    if (!(p_feat >= 0.0f && p_feat < 1.0f && p_seq >= 0.0f && p_seq < 1.0f && p_enc >= 0.0f && p_enc < 1.0f))
+        return c->fail(TIM_ERR_INVALID, "tim_set_dropout: probabilities must lie in [0, 1)");
+    c->train->p_feat = p_feat; c->train->p_seq = p_seq; c->train->p_enc = p_enc;
+    c->train->drop_seed = static_cast<uint32_t>(seed ^ (seed >> 32));
+    return TIM_OK;
+}
+
 int tim_time_mlp_fwd_train(tim_ctx* c, const float* times, float* out, int B, int T_, void* stream) {
     if (!c) return TIM_ERR_INVALID;
     if (!times || !out || B <= 0 || T_ <= 0) return c->fail(TIM_ERR_INVALID, "tim_time_mlp_fwd_train: bad arguments");

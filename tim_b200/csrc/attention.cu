@@ -253,7 +253,7 @@ constexpr int AS_WARPS = 4;
 constexpr int AS_ROWS = 16;          // rows per CTA
 
 __global__ void __launch_bounds__(AS_WARPS * 32) attention_simt_kernel(const float* __restrict__ qkv, float* __restrict__ out,
-                                                                       int B, int Ft, int Qt, int H, int hd, int tiles_f) {
+                                                                       int B, int Ft, int Qt, int H, int hd, int tiles_f, DropSite drop) {
     extern __shared__ float smf[];
     float* sK = smf;                               // [Ft][hd + 1]
     float* sV = sK + static_cast<size_t>(Ft) * (hd + 1);   // [Ft][hd]
@@ -305,8 +305,16 @@ __global__ void __launch_bounds__(AS_WARPS * 32) attention_simt_kernel(const flo
             sum += p;
         }
         sum = warp_sum(sum);
-        const float p_self = qtile ? exp2f(s_self - mx) : 0.0f;
+        float p_self = qtile ? exp2f(s_self - mx) : 0.0f;
         const float inv = 1.0f / (sum + p_self);
+        if (drop.thr) {
+            // attention-probability dropout (training forward, nn.MultiheadAttention(dropout=p)): the normalised probabilities
+            // are dropped, the normaliser is not. Element index: ((b H + h) S + row in clip) * DROP_ATTN_KW + key (own key: Ft)
+            const uint32_t rbase = ((static_cast<uint32_t>(b) * H + h) * static_cast<uint32_t>(Ft + Qt) + static_cast<uint32_t>((qtile ? Ft : 0) + row0 + r)) *
+                                   static_cast<uint32_t>(DROP_ATTN_KW);
+            for (int j = lane; j < Ft; j += 32) myp[j] *= drop_one(rbase + j, drop.key, drop.thr, drop.scale);
+            p_self *= drop_one(rbase + Ft, drop.key, drop.thr, drop.scale);
+        }
         __syncwarp();
         for (int c = lane; c < hd; c += 32) {
             float acc = qtile ? p_self * qrow[2 * E + c] : 0.0f;
@@ -338,14 +346,15 @@ size_t attention_simt_smem(int Ft, int hd) {
     return (static_cast<size_t>(Ft) * (hd + 1) + static_cast<size_t>(Ft) * hd + AS_WARPS * hd + AS_WARPS * Ft) * sizeof(float);
 }
 
-cudaError_t launch_attention_simt(const float* qkv, float* out, int B, int Ft, int Qt, int H, int hd, cudaStream_t s) {
+cudaError_t launch_attention_simt(const float* qkv, float* out, int B, int Ft, int Qt, int H, int hd, cudaStream_t s, DropSite drop) {
+    if (drop.thr && (Ft + 1 > DROP_ATTN_KW || 1ull * B * H * (Ft + Qt) * DROP_ATTN_KW > 0xffffffffull)) return cudaErrorInvalidValue;
     const size_t smem = attention_simt_smem(Ft, hd);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     static SmemAttrCache cache;
     if (cudaError_t e = ensure_dynamic_smem(attention_simt_kernel, smem, cache); e != cudaSuccess) return e;
     const int tiles_f = (Ft + AS_ROWS - 1) / AS_ROWS, tiles_q = (Qt + AS_ROWS - 1) / AS_ROWS;
     dim3 grid(tiles_f + tiles_q, H, B);
-    attention_simt_kernel<<<grid, AS_WARPS * 32, smem, s>>>(qkv, out, B, Ft, Qt, H, hd, tiles_f);
+    attention_simt_kernel<<<grid, AS_WARPS * 32, smem, s>>>(qkv, out, B, Ft, Qt, H, hd, tiles_f, drop);
     return cudaGetLastError();
 }
 

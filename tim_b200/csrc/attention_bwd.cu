@@ -487,7 +487,8 @@ cudaError_t launch_bwd_hd(const T* qkv, const T* dO, T* dqkv, float4* stats, int
 constexpr int SB_WARPS = 4;
 
 __global__ void __launch_bounds__(SB_WARPS * 32) attn_bwd_simt_kernel(const float* __restrict__ qkv, const float* __restrict__ dO,
-                                                                      float* __restrict__ dqkv, int B, int Ft, int Qt, int H, int hd, float qscale) {
+                                                                      float* __restrict__ dqkv, int B, int Ft, int Qt, int H, int hd, float qscale,
+                                                                      DropSite drop) {
     extern __shared__ float smf[];
     float* sK = smf;                                         // [Ft][hd + 1]
     float* sV = sK + static_cast<size_t>(Ft) * (hd + 1);     // [Ft][hd + 1]
@@ -538,11 +539,23 @@ __global__ void __launch_bounds__(SB_WARPS * 32) attn_bwd_simt_kernel(const floa
         float p_self = qrow ? exp2f(s_self - mx) : 0.0f;
         const float inv = 1.0f / (sum + p_self);
         p_self *= inv;
+        // dropout of the probabilities in the forward: the gradient w.r.t. P is dP o mask, and dV sees the dropped P
+        const uint32_t rbase = ((static_cast<uint32_t>(b) * H + h) * static_cast<uint32_t>(Ft + Qt) + static_cast<uint32_t>(r)) * static_cast<uint32_t>(DROP_ATTN_KW);
+        float m_self = 1.0f;
+        if (drop.thr) {
+            for (int j = lane; j < Ft; j += 32) mys[j] *= drop_one(rbase + j, drop.key, drop.thr, drop.scale);
+            m_self = drop_one(rbase + Ft, drop.key, drop.thr, drop.scale);
+            dps *= m_self;
+        }
         float D = 0.0f;
         for (int j = lane; j < Ft; j += 32) { const float p = myp[j] * inv; myp[j] = p; D = fmaf(p, mys[j], D); }
         D = warp_sum(D) + p_self * dps;
         for (int j = lane; j < Ft; j += 32) mys[j] = myp[j] * (mys[j] - D);
         const float dss = p_self * (dps - D);
+        if (drop.thr) {                                  // from here on myp is the DROPPED probability (what multiplied V in the forward)
+            for (int j = lane; j < Ft; j += 32) myp[j] *= drop_one(rbase + j, drop.key, drop.thr, drop.scale);
+        }
+        const float p_self_d = p_self * m_self;
         __syncwarp();
         for (int c = lane; c < hd; c += 32) {
             float acc = qrow ? dss * qp[E + c] : 0.0f;
@@ -550,7 +563,7 @@ __global__ void __launch_bounds__(SB_WARPS * 32) attn_bwd_simt_kernel(const floa
             dqkv[row * ld + h * hd + c] = acc * qscale;
             if (qrow) {
                 dqkv[row * ld + E + h * hd + c] = kLn2 * dss * myq[c];
-                dqkv[row * ld + 2 * E + h * hd + c] = p_self * myd[c];
+                dqkv[row * ld + 2 * E + h * hd + c] = p_self_d * myd[c];
             }
             const float qv = myq[c] * kLn2, dv = myd[c];
             for (int j = 0; j < Ft; ++j) {
@@ -591,14 +604,15 @@ size_t attention_bwd_simt_smem(int Ft, int hd) {
 
 // dqkv must be zero on entry for the feature rows' k / v columns (the caller memsets the whole buffer)
 cudaError_t launch_attention_bwd_simt(const float* qkv, const float* dO, float* dqkv, int B, int Ft, int Qt, int H, int hd, float qscale,
-                                      cudaStream_t s) {
+                                      cudaStream_t s, DropSite drop) {
+    if (drop.thr && (Ft + 1 > DROP_ATTN_KW || 1ull * B * H * (Ft + Qt) * DROP_ATTN_KW > 0xffffffffull)) return cudaErrorInvalidValue;
     const size_t smem = attention_bwd_simt_smem(Ft, hd);
     if (smem > 227 * 1024) return cudaErrorInvalidValue;
     static SmemAttrCache cache;
     if (cudaError_t e = ensure_dynamic_smem(attn_bwd_simt_kernel, smem, cache); e != cudaSuccess) return e;
     const long long items = 1LL * B * H;
     if (items <= 0) return cudaSuccess;
-    attn_bwd_simt_kernel<<<static_cast<unsigned>(items), SB_WARPS * 32, smem, s>>>(qkv, dO, dqkv, B, Ft, Qt, H, hd, qscale);
+    attn_bwd_simt_kernel<<<static_cast<unsigned>(items), SB_WARPS * 32, smem, s>>>(qkv, dO, dqkv, B, Ft, Qt, H, hd, qscale, drop);
     return cudaGetLastError();
 }
 

@@ -261,6 +261,12 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                 float ps = qt ? ex2_approx(sself - m) : 0.0f;
                 const float inv = valid ? 1.0f / ((ls[0] + ls[1]) + (ls[2] + ls[3]) + ps) : 0.0f;      // padded rows: P = dS = 0
                 ps *= inv;
+                // dropout of the probabilities in the forward (kernels.h: DropSite): the gradient w.r.t. P is dP o mask, dV_f sees the
+                // dropped P, D and dS use the un-dropped P
+                const uint32_t drop_pair0 = ((((static_cast<uint32_t>(b) * p.H + h) * static_cast<uint32_t>(Ft + Qt) +
+                                              static_cast<uint32_t>((qt ? Ft + row0 : 0) + row)) * static_cast<uint32_t>(DROP_ATTN_KW)) >> 1);
+                const float m_self = p.drop.thr ? drop_one(2u * drop_pair0 + static_cast<uint32_t>(Ft), p.drop.key, p.drop.thr, p.drop.scale) : 1.0f;
+                dps *= m_self;
                 // ---- D = sum_j P_j dP_j (+ own key): first pass over dP ----
                 float dacc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
@@ -269,6 +275,14 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                         uint32_t v[16];
                         tmem_ld_32x16(taddr + 128 + c * 16, v);
                         tmem_ld_wait();
+                        if (p.drop.thr) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float m0, m1;
+                                drop_pair(drop_pair0 + c * 8 + j, p.drop.key, p.drop.thr, p.drop.scale, m0, m1);
+                                v[2 * j] = __float_as_uint(__uint_as_float(v[2 * j]) * m0); v[2 * j + 1] = __float_as_uint(__uint_as_float(v[2 * j + 1]) * m1);
+                            }
+                        }
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
                             s[c * 16 + j] *= inv;
@@ -294,8 +308,10 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 const float p0 = s[c8 * 8 + 2 * j], p1 = s[c8 * 8 + 2 * j + 1];
-                                wp[j] = pack2<T>(p0, p1);
-                                wd[j] = pack2<T>(p0 * (__uint_as_float(v[h8 * 8 + 2 * j]) - D), p1 * (__uint_as_float(v[h8 * 8 + 2 * j + 1]) - D));
+                                float m0 = 1.0f, m1 = 1.0f;
+                                if (p.drop.thr) drop_pair(drop_pair0 + c8 * 4 + j, p.drop.key, p.drop.thr, p.drop.scale, m0, m1);
+                                wp[j] = pack2<T>(p0 * m0, p1 * m1);
+                                wd[j] = pack2<T>(p0 * (__uint_as_float(v[h8 * 8 + 2 * j]) * m0 - D), p1 * (__uint_as_float(v[h8 * 8 + 2 * j + 1]) * m1 - D));
                             }
                             const uint32_t off = static_cast<uint32_t>(c8 >> 3) * 16384 + row * 128 + ((static_cast<uint32_t>(c8 & 7) ^ swz) << 4);
                             sts_u128(sP + off, qp);
@@ -327,7 +343,7 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                         for (int j = 0; j < 4; ++j) {
                             const float2 qf = unpack2<T>(qw[j]), df = unpack2<T>(dw[j]);
                             wk[j] = pack2<T>(kk * qf.x, kk * qf.y);
-                            wv[j] = pack2<T>(ps * df.x, ps * df.y);
+                            wv[j] = pack2<T>(ps * m_self * df.x, ps * m_self * df.y);
                         }
                         *reinterpret_cast<uint4*>(o + E + 8 * c) = ok;
                         *reinterpret_cast<uint4*>(o + 2 * E + 8 * c) = ov;

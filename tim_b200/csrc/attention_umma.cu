@@ -317,6 +317,10 @@ __global__ void __launch_bounds__(AU_THREADS, 1) attention_umma_kernel(const __g
                 }
                 const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
                 float ls[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                // attention-probability dropout (training forward only): the probabilities that meet V are dropped, the normaliser is
+                // not. Element index ((b H + h) S + row in clip) * DROP_ATTN_KW + key, own key at Ft (kernels.h: DropSite)
+                const uint32_t drop_pair0 = ((((static_cast<uint32_t>(ui.b) * p.H + ui.h) * static_cast<uint32_t>(Ft + Qt) +
+                                              static_cast<uint32_t>((qt ? Ft + (t - 1) * AU_BM : 0) + row)) * static_cast<uint32_t>(DROP_ATTN_KW)) >> 1);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     if (c * 16 < Fp) {
@@ -325,6 +329,14 @@ __global__ void __launch_bounds__(AU_THREADS, 1) attention_umma_kernel(const __g
                             const float e = ex2_approx(s[c * 16 + j] - m);
                             s[c * 16 + j] = e;
                             ls[j & 3] += e;
+                        }
+                        if (p.drop.thr) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float m0, m1;
+                                drop_pair(drop_pair0 + c * 8 + j, p.drop.key, p.drop.thr, p.drop.scale, m0, m1);
+                                s[c * 16 + 2 * j] *= m0; s[c * 16 + 2 * j + 1] *= m1;
+                            }
                         }
 #pragma unroll
                         for (int h8 = 0; h8 < 2; ++h8) {
@@ -339,8 +351,9 @@ __global__ void __launch_bounds__(AU_THREADS, 1) attention_umma_kernel(const __g
                 const float l = (ls[0] + ls[1]) + (ls[2] + ls[3]);
                 const float ps = qt ? ex2_approx(sself - m) : 0.0f;
                 const float inv = 1.0f / (l + ps);
+                const float m_self = p.drop.thr ? drop_one(2u * drop_pair0 + static_cast<uint32_t>(Ft), p.drop.key, p.drop.thr, p.drop.scale) : 1.0f;
                 sts_f32(stat(st, 0, row), inv);
-                sts_f32(stat(st, 1, row), ps * inv);
+                sts_f32(stat(st, 1, row), ps * inv * m_self);
                 tc_fence_before();
                 fence_proxy_async_smem();          // P (generic-proxy writes) -> visible to the tensor core's operand reads
                 __syncwarp();

@@ -14,6 +14,30 @@ void set_global_error(const char* msg);
 
 enum Act { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 
+// Dropout of the training leg (the reference's nn.Dropout sites: helpers/encodings.py:141,149,177, helpers/transformers.py:73-82,
+// 102-108). No mask tensor exists: the keep decision of element e of a site is a pure function of (seed, site, layer, e), evaluated
+// wherever the forward or the backward needs it - one 32-bit integer hash (lowbias32) per PAIR of adjacent elements, 16 bits each:
+//     h = lowbias32((e >> 1) ^ key);  keep(e) = ((e & 1) ? h >> 16 : h & 0xffff) >= thr;  kept values are scaled by 65536 / (65536 - thr)
+// with thr = round(p * 65536). tests/ and oracle/tim_oracle_bwd.py restate the same function in numpy, so gradient parity is
+// checked WITH dropout, mask for mask. e is the element's flat index in the library's own layout (two-stream token rows).
+struct DropSite {
+    uint32_t key = 0;
+    uint32_t thr = 0;       // 0: no dropout at this site
+    float scale = 1.0f;
+};
+enum DropSiteId { DROP_FEAT_VIS = 1, DROP_FEAT_AUD = 2, DROP_SEQ = 3, DROP_ATTN = 4, DROP_SUB1 = 5, DROP_FFN = 6, DROP_SUB2 = 7 };
+inline DropSite make_drop_site(float p, uint32_t seed, uint32_t site, uint32_t layer) {
+    DropSite d;
+    if (p <= 0.0f) return d;
+    uint32_t thr = static_cast<uint32_t>(p * 65536.0f + 0.5f);
+    if (thr > 65535u) thr = 65535u;
+    d.thr = thr;
+    d.scale = 65536.0f / static_cast<float>(65536u - thr);
+    d.key = seed ^ (site * 0x9E3779B9u) ^ (layer * 0x85EBCA6Bu);
+    return d;
+}
+constexpr int DROP_ATTN_KW = 130;    // keys per row in the attention-probability index: feature keys 0 .. Ft - 1, own key at Ft (Ft <= 128)
+
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: remember the largest size requested per device, so a
 // process that drives several GPUs (several contexts) sets it on each of them.
 struct SmemAttrCache { size_t set[64] = {}; };
@@ -127,6 +151,7 @@ struct AttnUmmaParams {
     int tpu, chunks;      // row tiles per work unit, work units per (clip, head)
     int num_units;
     int pf_mode, pf_tiles; // L2 prefetch policy of the TMA producer (see launch_attention_umma)
+    DropSite drop;         // attention-probability dropout (training forward; attention_umma.cu only)
 };
 bool attention_umma_supported(int Ft, int hd);
 size_t attention_umma_smem(int Ft, int hd);
@@ -139,7 +164,7 @@ cudaError_t launch_attention_umma(AttnUmmaParams p, int hd, int num_sms, cudaStr
 template <typename T>
 cudaError_t launch_attention_umma3(AttnUmmaParams p, int hd, int num_sms, cudaStream_t s);
 
-cudaError_t launch_attention_simt(const float* qkv, float* out, int B, int Ft, int Qt, int H, int hd, cudaStream_t s);
+cudaError_t launch_attention_simt(const float* qkv, float* out, int B, int Ft, int Qt, int H, int hd, cudaStream_t s, DropSite drop = DropSite());
 size_t attention_simt_smem(int Ft, int hd);
 
 // ---- elementwise / row kernels ----
@@ -245,6 +270,7 @@ struct AttnBwdUmmaParams {
     int B, Ft, Qt, H;
     int Fp, tiles_q, num_units;       // filled by the launcher
     float qscale;
+    DropSite drop;                    // attention-probability dropout of the forward this is the backward of
 };
 bool attention_bwd_umma_supported(int Ft, int hd);
 template <typename T>
@@ -252,18 +278,30 @@ cudaError_t launch_attention_bwd_umma(AttnBwdUmmaParams p, int hd, int num_sms, 
 
 size_t attention_bwd_simt_smem(int Ft, int hd);
 cudaError_t launch_attention_bwd_simt(const float* qkv, const float* dO, float* dqkv, int B, int Ft, int Qt, int H, int hd, float qscale,
-                                      cudaStream_t s);
+                                      cudaStream_t s, DropSite drop = DropSite());
 
 // ---- row / elementwise kernels (train_rows.cu) ----
 // LayerNorm backward; dy is overwritten by dz, dz16 (optional) receives its operand copy; dgamma / dbeta / dbias accumulate (+=)
+// drop: dropout of the sub-layer output that was added into z (dropout1 / dropout2): dz16 and dbias then carry dz o mask (the
+// gradient w.r.t. the sub-layer's output), dy keeps the un-masked dz (the residual branch)
 template <typename T>
 cudaError_t launch_ln_bwd(float* dy, int ldd, const float* z, int ldz, const float* gamma, T* dz16, int ld16, float* dgamma, float* dbeta,
-                          float* dbias, int M, int n, cudaStream_t s);
+                          float* dbias, int M, int n, cudaStream_t s, DropSite drop = DropSite());
 // out = d * f'(a); mode 0: erf-GELU, a = pre-activation; mode 1: ReLU, a = post-activation. dbias (optional) += column sums of out
 template <typename TD, typename TA, typename TO>
-cudaError_t launch_act_bwd(int mode, const TD* d, const TA* a, TO* out, int rows, int cols, float* dbias, cudaStream_t s);
+cudaError_t launch_act_bwd(int mode, const TD* d, const TA* a, TO* out, int rows, int cols, float* dbias, cudaStream_t s, DropSite drop = DropSite());
 template <typename T>
-cudaError_t launch_gelu_fwd(const T* u, T* h, size_t n, cudaStream_t s);
+cudaError_t launch_gelu_fwd(const T* u, T* h, size_t n, cudaStream_t s, DropSite drop = DropSite());
+// out = T(in o mask) over a flat fp32 array (input-feature dropout fused into the operand cast); n even
+template <typename T>
+cudaError_t launch_drop_cast(const float* in, T* out, size_t n, DropSite drop, cudaStream_t s);
+// x32 (and its 16-bit copy x16, optional) *= mask, in place, flat index = element index (token dropout; gradient masking)
+template <typename T>
+cudaError_t launch_drop_apply(float* x32, T* x16, size_t n, DropSite drop, cudaStream_t s);
+// z = R(resid) + a o mask, fp32 [M, n]: the sub-layer output a (fp32, no residual yet) is dropped and added to the residual;
+// R = LayerNorm-on-read with (rstats, rgamma, rbeta) or the identity when rstats == nullptr. z may alias a.
+cudaError_t launch_residual_drop(const float* a, const float* resid, const float2* rstats, const float* rgamma, const float* rbeta, float* z,
+                                 int M, int n, DropSite drop, cudaStream_t s);
 // out[c] += sum_{g < G, r < R} x[(g * group_rows + row_off + r) * ld + col_off + c],  c < ncols
 template <typename T>
 cudaError_t launch_colsum(const T* x, int ld, int G, int group_rows, int row_off, int R, int col_off, int ncols, float* out, cudaStream_t s);

@@ -331,6 +331,22 @@ __device__ __forceinline__ float ex2_approx(float x) {      // 2^x, one MUFU.EX2
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// dropout keep decisions of the element pair (2 * pair, 2 * pair + 1): see DropSite in kernels.h
+__device__ __forceinline__ uint32_t drop_hash(uint32_t pair, uint32_t key) {
+    uint32_t x = pair ^ key;
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+__device__ __forceinline__ void drop_pair(uint32_t pair, uint32_t key, uint32_t thr, float scale, float& m0, float& m1) {
+    const uint32_t h = drop_hash(pair, key);
+    m0 = (h & 0xffffu) >= thr ? scale : 0.0f;
+    m1 = (h >> 16) >= thr ? scale : 0.0f;
+}
+__device__ __forceinline__ float drop_one(uint32_t e, uint32_t key, uint32_t thr, float scale) {
+    const uint32_t h = drop_hash(e >> 1, key);
+    return ((e & 1u) ? (h >> 16) : (h & 0xffffu)) >= thr ? scale : 0.0f;
+}
+
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 // erf-GELU for the 16-bit epilogues: gelu(x) = relu(x) - 0.5 |x| erfc(|x| / sqrt2), with erfc(a / sqrt2) = 2^q(a) on [0, 4 sqrt2]

@@ -42,6 +42,11 @@ struct tim_train_state {
     uint8_t* tmem = nullptr; size_t tmem_bytes = 0;
     float *times = nullptr, *t3 = nullptr;
     void *t1 = nullptr, *t2 = nullptr;
+    // dropout of the NEXT training forward (tim_set_dropout); the encoder tape remembers what its forward used
+    float p_feat = 0.0f, p_seq = 0.0f, p_enc = 0.0f;
+    uint32_t drop_seed = 0;
+    float tape_p_seq = 0.0f, tape_p_enc = 0.0f;
+    uint32_t tape_seed = 0;
     // NCCL (dlopen'ed, see tim_comm_init)
     void* nccl_comm = nullptr;
     int world = 1;
@@ -121,7 +126,10 @@ int run_wgrad(tim_ctx* c, const void* dY, int ldy, const void* X, int ldx, float
 
 // attention backward: tcgen05 kernel where it applies (head_dim 64 / 128, Ft <= 128), else the two warp-MMA kernels
 template <typename T>
-int run_attention_bwd(tim_ctx* c, const T* qkv, const T* dO, T* dqkv, void* stats, int B, int Ft, int Qt, float qscale, double flops, cudaStream_t s) {
+int run_attention_bwd(tim_ctx* c, const T* qkv, const T* dO, T* dqkv, void* stats, int B, int Ft, int Qt, float qscale, double flops, cudaStream_t s,
+                      DropSite drop = DropSite()) {
+    if (drop.thr && !attention_bwd_umma_supported(Ft, c->hd))
+        return c->fail(TIM_ERR_INVALID, "attention dropout in the 16-bit modes needs head_dim 64 or 128 (tcgen05 attention kernels), got %d", c->hd);
     if (attention_bwd_umma_supported(Ft, c->hd)) {
         AttnBwdUmmaParams ap;
         std::memset(&ap, 0, sizeof(ap));
@@ -136,7 +144,8 @@ int run_attention_bwd(tim_ctx* c, const T* qkv, const T* dO, T* dqkv, void* stat
         } else {
             ap.tmQq = ap.tmQf; ap.tmDq = ap.tmDf;
         }
-        ap.qkv = qkv; ap.dO = dO; ap.dqkv = dqkv; ap.B = B; ap.Ft = Ft; ap.Qt = Qt; ap.H = c->H; ap.qscale = qscale;
+        ap.qkv = qkv; ap.dO = dO; ap.dqkv = dqkv; ap.B = B; ap.Ft = Ft; ap.Qt = Qt; ap.H = c->H; ap.qscale = qscale; ap.drop = drop;
+        if (drop.thr && 1ull * B * c->H * (Ft + Qt) * DROP_ATTN_KW > 0xffffffffull) return c->fail(TIM_ERR_INVALID, "attention dropout: batch too large for the 32-bit element index");
         LAUNCH_C(c, 9, flops, s, launch_attention_bwd_umma<T>(ap, c->hd, c->num_sms, s));
     } else {
         LAUNCH_C(c, 9, flops, s, launch_attention_bwd<T>(qkv, dO, dqkv, stats, B, Ft, Qt, c->H, c->hd, qscale, s));
@@ -304,16 +313,25 @@ int encoder_train_fwd(tim_ctx* c, const float* vis, const float* aud, const floa
 
     // ---- embedders: Linear (pre-activation kept) -> GELU -> (LayerNorm inside the assembly) ----
     const int Mv = B * c->Fv, Ma = B * c->Fa;
-    auto embed = [&](const float* x, void* xT, const LinearW& w, int rows, int dim, float* pre, float* act) -> int {
+    // dropout configuration of this forward (all zero unless tim_set_dropout was called)
+    const float p_feat = tr.p_feat, p_seq = tr.p_seq, p_enc = tr.p_enc;
+    const uint32_t seed = tr.drop_seed;
+    tr.tape_p_seq = p_seq; tr.tape_p_enc = p_enc; tr.tape_seed = seed;
+    if (p_enc > 0.0f && !f32 && !(c->attn_version == 2 && attention_umma_supported(c->Ft, c->hd) && attention_bwd_umma_supported(c->Ft, c->hd)))
+        return c->fail(TIM_ERR_INVALID, "attention dropout in the 16-bit modes needs head_dim 64 or 128 and the tcgen05 attention kernels (head_dim %d)", c->hd);
+    auto embed = [&](const float* x, void* xT, const LinearW& w, int rows, int dim, float* pre, float* act, uint32_t site) -> int {
         if (!x) return c->fail(TIM_ERR_INVALID, "input features are NULL");
-        if constexpr (f32) CU_OK(c, cudaMemcpyAsync(xT, x, static_cast<size_t>(rows) * dim * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        if (p_feat > 0.0f) {       // feat_drop (encodings.py:141,149): fused into the operand cast
+            if (dim & 1) return c->fail(TIM_ERR_INVALID, "feature dropout needs an even feature width");
+            LAUNCH(c, launch_drop_cast<T>(x, static_cast<T*>(xT), static_cast<size_t>(rows) * dim, make_drop_site(p_feat, seed, site, 0), s));
+        } else if constexpr (f32) CU_OK(c, cudaMemcpyAsync(xT, x, static_cast<size_t>(rows) * dim * sizeof(float), cudaMemcpyDeviceToDevice, s));
         else LAUNCH(c, launch_cast<T>(x, static_cast<T*>(xT), rows, dim, 0, 1.0f, s));
         TIM_TRY(run_linear<T>(c, xT, dim, w, plain_rows(rows), epi(pre, d, true, ACT_NONE), s));
         LAUNCH(c, launch_gelu_fwd<float>(pre, act, static_cast<size_t>(rows) * d, s));
         return TIM_OK;
     };
-    if (c->Fv) TIM_TRY(embed(vis, tr.visT, c->emb_v, Mv, g.vis_dim, tr.embv_pre, tr.embv_act));
-    if (c->Fa) TIM_TRY(embed(aud, tr.audT, c->emb_a, Ma, g.aud_dim, tr.emba_pre, tr.emba_act));
+    if (c->Fv) TIM_TRY(embed(vis, tr.visT, c->emb_v, Mv, g.vis_dim, tr.embv_pre, tr.embv_act, DROP_FEAT_VIS));
+    if (c->Fa) TIM_TRY(embed(aud, tr.audT, c->emb_a, Ma, g.aud_dim, tr.emba_pre, tr.emba_act, DROP_FEAT_AUD));
     AssembleParams ap;
     std::memset(&ap, 0, sizeof(ap));
     ap.B = B; ap.d = d; ap.T = T_; ap.Fv = c->Fv; ap.Fa = c->Fa;
@@ -325,12 +343,23 @@ int encoder_train_fwd(tim_ctx* c, const float* vis, const float* aud, const floa
     for (int i = 0; i < qp.n_groups; ++i) ap.groups[i] = qp.groups[i];
     ap.Qt = Qt; ap.x32 = tr.tok32; ap.x16 = f32 ? nullptr : tr.layers[0].xin;
     LAUNCH_C(c, 3, 0.0, s, launch_assemble<T>(ap, s));
+    if (p_seq > 0.0f)          // seq_drop on the assembled tokens (encodings.py:177, 250), flat index over the two-stream rows
+        LAUNCH(c, launch_drop_apply<T>(tr.tok32, f32 ? static_cast<T*>(nullptr) : static_cast<T*>(tr.layers[0].xin), M * E, make_drop_site(p_seq, seed, DROP_SEQ, 0), s));
 
     const int Mi = static_cast<int>(M);
     const double attn_flops = 4.0 * E * (static_cast<double>(Ft) * Ft + static_cast<double>(Qt) * (Ft + 1)) * B;
+    // with dropout1 / dropout2 the sub-layer output is written WITHOUT its residual into a scratch buffer and a row kernel forms
+    // z = R(residual) + output o mask (the GEMM epilogues stay the ones the inference forward validated)
+    float* sub32 = nullptr;
+    if (p_enc > 0.0f) {
+        TIM_TRY(ensure_ws(c, M * E * sizeof(float) + 256));
+        sub32 = reinterpret_cast<float*>(c->ws);
+    }
     for (int l = 0; l < c->L; ++l) {
         Layer& ly = c->layers[l];
         LayerTape& t = tr.layers[l];
+        const DropSite d_attn = make_drop_site(p_enc, seed, DROP_ATTN, l), d_sub1 = make_drop_site(p_enc, seed, DROP_SUB1, l);
+        const DropSite d_ffn = make_drop_site(p_enc, seed, DROP_FFN, l), d_sub2 = make_drop_site(p_enc, seed, DROP_SUB2, l);
         const Layer* lp = l > 0 ? &c->layers[l - 1] : nullptr;
         const LayerTape* tp = l > 0 ? &tr.layers[l - 1] : nullptr;
         if constexpr (!f32) {
@@ -338,32 +367,55 @@ int encoder_train_fwd(tim_ctx* c, const float* vis, const float* aud, const floa
         }
         TIM_TRY(run_linear<T>(c, t.xin, E, ly.in_proj, plain_rows(Mi), epi(t.qkv, 3 * E, f32), s));
         if constexpr (f32) {
-            LAUNCH_C(c, 1, attn_flops, s, launch_attention_simt(static_cast<const float*>(t.qkv), static_cast<float*>(t.att), B, Ft, Qt, c->H, c->hd, s));
+            LAUNCH_C(c, 1, attn_flops, s, launch_attention_simt(static_cast<const float*>(t.qkv), static_cast<float*>(t.att), B, Ft, Qt, c->H, c->hd, s, d_attn));
         } else {
             AttnUmmaParams attn_p;
             bool attn_umma = false;
             TIM_TRY(prepare_attention<T>(c, &attn_p, &attn_umma, static_cast<const T*>(t.qkv), static_cast<T*>(t.att), B, Ft, Qt));
+            attn_p.drop = d_attn;
+            if (d_attn.thr && 1ull * B * c->H * (Ft + Qt) * DROP_ATTN_KW > 0xffffffffull) return c->fail(TIM_ERR_INVALID, "attention dropout: batch too large for the 32-bit element index");
             if (attn_umma) LAUNCH_C(c, 1, attn_flops, s, launch_attention_tc<T>(c, attn_p, s));
             else LAUNCH_C(c, 1, attn_flops, s, launch_attention_mma<T>(static_cast<const T*>(t.qkv), static_cast<T*>(t.att), B, Ft, Qt, c->H, c->hd, s));
         }
         if constexpr (f32) {
-            TIM_TRY(run_linear<T>(c, t.att, E, ly.out_proj, plain_rows(Mi), epi(t.z1, E, true, ACT_NONE, static_cast<const float*>(t.xin), E), s));
+            if (d_sub1.thr) {
+                TIM_TRY(run_linear<T>(c, t.att, E, ly.out_proj, plain_rows(Mi), epi(sub32, E, true), s));
+                LAUNCH(c, launch_residual_drop(sub32, static_cast<const float*>(t.xin), nullptr, nullptr, nullptr, t.z1, Mi, E, d_sub1, s));
+            } else {
+                TIM_TRY(run_linear<T>(c, t.att, E, ly.out_proj, plain_rows(Mi), epi(t.z1, E, true, ACT_NONE, static_cast<const float*>(t.xin), E), s));
+            }
             LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(t.z1, E, ly.n1g, ly.n1b, static_cast<float*>(t.x1), E, static_cast<T*>(nullptr), 0, Mi, E, s));
             TIM_TRY(run_linear<T>(c, t.x1, E, ly.lin1, plain_rows(Mi), epi(t.u, FF, true, ACT_NONE), s));
-            LAUNCH(c, launch_gelu_fwd<T>(static_cast<const T*>(t.u), static_cast<T*>(t.hid), M * FF, s));
-            TIM_TRY(run_linear<T>(c, t.hid, FF, ly.lin2, plain_rows(Mi), epi(t.z2, E, true, ACT_NONE, static_cast<const float*>(t.x1), E), s));
+            LAUNCH(c, launch_gelu_fwd<T>(static_cast<const T*>(t.u), static_cast<T*>(t.hid), M * FF, s, d_ffn));
+            if (d_sub2.thr) {
+                TIM_TRY(run_linear<T>(c, t.hid, FF, ly.lin2, plain_rows(Mi), epi(sub32, E, true), s));
+                LAUNCH(c, launch_residual_drop(sub32, static_cast<const float*>(t.x1), nullptr, nullptr, nullptr, t.z2, Mi, E, d_sub2, s));
+            } else {
+                TIM_TRY(run_linear<T>(c, t.hid, FF, ly.lin2, plain_rows(Mi), epi(t.z2, E, true, ACT_NONE, static_cast<const float*>(t.x1), E), s));
+            }
             float* nxt = l < c->L - 1 ? static_cast<float*>(tr.layers[l + 1].xin) : static_cast<float*>(tr.xh);
             LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(t.z2, E, ly.n2g, ly.n2b, nxt, E, static_cast<T*>(nullptr), 0, Mi, E, s));
         } else {
-            Epilogue e1 = epi(t.z1, E, true, ACT_NONE, l > 0 ? tp->z2 : tr.tok32, E);
-            if (l > 0) { e1.rstats = tp->st2; e1.rgamma = lp->n2g; e1.rbeta = lp->n2b; }
-            TIM_TRY(run_linear<T>(c, t.att, E, ly.out_proj, plain_rows(Mi), e1, s));
+            if (d_sub1.thr) {
+                TIM_TRY(run_linear<T>(c, t.att, E, ly.out_proj, plain_rows(Mi), epi(sub32, E, true), s));
+                LAUNCH(c, launch_residual_drop(sub32, l > 0 ? tp->z2 : tr.tok32, l > 0 ? tp->st2 : nullptr, l > 0 ? lp->n2g : nullptr,
+                                               l > 0 ? lp->n2b : nullptr, t.z1, Mi, E, d_sub1, s));
+            } else {
+                Epilogue e1 = epi(t.z1, E, true, ACT_NONE, l > 0 ? tp->z2 : tr.tok32, E);
+                if (l > 0) { e1.rstats = tp->st2; e1.rgamma = lp->n2g; e1.rbeta = lp->n2b; }
+                TIM_TRY(run_linear<T>(c, t.att, E, ly.out_proj, plain_rows(Mi), e1, s));
+            }
             LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(t.z1, E, ly.n1g, ly.n1b, nullptr, 0, static_cast<T*>(t.x1), E, Mi, E, s, t.st1));
             TIM_TRY(run_linear<T>(c, t.x1, E, ly.lin1, plain_rows(Mi), epi(t.u, FF, false, ACT_NONE), s));
-            LAUNCH(c, launch_gelu_fwd<T>(static_cast<const T*>(t.u), static_cast<T*>(t.hid), M * FF, s));
-            Epilogue e2 = epi(t.z2, E, true, ACT_NONE, t.z1, E);
-            e2.rstats = t.st1; e2.rgamma = ly.n1g; e2.rbeta = ly.n1b;
-            TIM_TRY(run_linear<T>(c, t.hid, FF, ly.lin2, plain_rows(Mi), e2, s));
+            LAUNCH(c, launch_gelu_fwd<T>(static_cast<const T*>(t.u), static_cast<T*>(t.hid), M * FF, s, d_ffn));
+            if (d_sub2.thr) {
+                TIM_TRY(run_linear<T>(c, t.hid, FF, ly.lin2, plain_rows(Mi), epi(sub32, E, true), s));
+                LAUNCH(c, launch_residual_drop(sub32, t.z1, t.st1, ly.n1g, ly.n1b, t.z2, Mi, E, d_sub2, s));
+            } else {
+                Epilogue e2 = epi(t.z2, E, true, ACT_NONE, t.z1, E);
+                e2.rstats = t.st1; e2.rgamma = ly.n1g; e2.rbeta = ly.n1b;
+                TIM_TRY(run_linear<T>(c, t.hid, FF, ly.lin2, plain_rows(Mi), e2, s));
+            }
             if (l == c->L - 1 && Mq)
                 LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(t.z2 + Mf * E, E, ly.n2g, ly.n2b, nullptr, 0, static_cast<T*>(tr.xh), E, static_cast<int>(Mq), E, s));
         }
@@ -439,11 +491,14 @@ int encoder_train_bwd(tim_ctx* c, const tim_outputs* go, float* d_te, cudaStream
     int cmax = 8;
     for (int n : {g.n_verb, g.n_noun, g.n_action, g.n_audio}) if (n > cmax) cmax = n;
     const int cpmax = (cmax + 7) & ~7;
+    const float p_seq = tr.tape_p_seq, p_enc = tr.tape_p_enc;
+    const uint32_t seed = tr.tape_seed;
     float *g32, *dxq, *demb_v, *demb_a; T *g16, *dh, *da, *dqkv, *dY16, *xg, *dr1, *dr2, *dpre; void* astats;
     for (int pass = 0; pass < 2; ++pass) {
         Arena a{pass ? c->ws : nullptr};
         a.take(&g32, M * E * sizeof(float));
-        a.take(&g16, f32 ? 0 : M * E * sizeof(T));
+        // operand copy of dz: the 16-bit copy, or - fp32 mode with dropout1 / dropout2 - the masked fp32 copy (dz o mask differs from dz)
+        a.take(&g16, (f32 && p_enc <= 0.0f) ? 0 : M * E * sizeof(T));
         a.take(&dh, M * FF * sizeof(T));
         a.take(&da, M * E * sizeof(T));
         a.take(&dqkv, M * 3 * E * sizeof(T));
@@ -459,8 +514,9 @@ int encoder_train_bwd(tim_ctx* c, const tim_outputs* go, float* d_te, cudaStream
         a.take(&dpre, f32 ? 0 : static_cast<size_t>(Mv > Ma ? Mv : Ma) * d * sizeof(T));
         if (!pass) TIM_TRY(ensure_ws(c, a.off));
     }
-    const T* gop = f32 ? reinterpret_cast<const T*>(g32) : g16;       // dz as the GEMM operand
-    T* g16w = f32 ? nullptr : g16;
+    const bool own_copy = !f32 || p_enc > 0.0f;
+    const T* gop = own_copy ? g16 : reinterpret_cast<const T*>(g32);   // dz (o dropout mask) as the GEMM operand
+    T* g16w = own_copy ? g16 : nullptr;
 
     // ---- seed: d L / d LN2(z2_last): feature rows from `feats`, query rows from the heads ----
     CU_OK(c, cudaMemsetAsync(g32, 0, M * E * sizeof(float), s));
@@ -533,22 +589,24 @@ int encoder_train_bwd(tim_ctx* c, const tim_outputs* go, float* d_te, cudaStream
         TIM_TRY(grad_dst(c, ly.n1g, &g_n1g)); TIM_TRY(grad_dst(c, ly.n1b, &g_n1b));
         TIM_TRY(grad_dst(c, ly.out_proj.w, &g_wo)); TIM_TRY(grad_dst(c, ly.out_proj.bias, &g_bo));
         TIM_TRY(grad_dst(c, ly.in_proj.w, &g_wi)); TIM_TRY(grad_dst(c, ly.in_proj.bias, &g_bi));
-        // norm2 backward: g32 = d / d LN2(z2) -> dz2 (in place, + operand copy); dz2 is also the gradient of linear2's output
-        LAUNCH_C(c, 2, 0.0, s, launch_ln_bwd<T>(g32, E, t.z2, E, ly.n2g, g16w, E, g_n2g, g_n2b, g_b2, Mi, E, s));
+        const DropSite d_attn = make_drop_site(p_enc, seed, DROP_ATTN, l), d_sub1 = make_drop_site(p_enc, seed, DROP_SUB1, l);
+        const DropSite d_ffn = make_drop_site(p_enc, seed, DROP_FFN, l), d_sub2 = make_drop_site(p_enc, seed, DROP_SUB2, l);
+        // norm2 backward: g32 = d / d LN2(z2) -> dz2 (in place, + operand copy); dz2 (o dropout2's mask) is the gradient of linear2's output
+        LAUNCH_C(c, 2, 0.0, s, launch_ln_bwd<T>(g32, E, t.z2, E, ly.n2g, g16w, E, g_n2g, g_n2b, g_b2, Mi, E, s, d_sub2));
         TIM_TRY(run_wgrad<T>(c, gop, E, t.hid, FF, g_w2, FF, Mi, E, FF, s));
         TIM_TRY(run_dgrad<T>(c, gop, ly.lin2, Mi, epi(dh, FF, f32), s));
-        LAUNCH(c, (launch_act_bwd<T, T, T>(0, dh, static_cast<const T*>(t.u), dh, Mi, FF, g_b1, s)));
+        LAUNCH(c, (launch_act_bwd<T, T, T>(0, dh, static_cast<const T*>(t.u), dh, Mi, FF, g_b1, s, d_ffn)));
         TIM_TRY(run_wgrad<T>(c, dh, FF, t.x1, E, g_w1, E, Mi, FF, E, s));
         // d / d x1 = du W1 + dz2 (the residual branch), in place in g32
         TIM_TRY(run_dgrad<T>(c, dh, ly.lin1, Mi, epi(g32, E, true, ACT_NONE, g32, E), s));
-        LAUNCH_C(c, 2, 0.0, s, launch_ln_bwd<T>(g32, E, t.z1, E, ly.n1g, g16w, E, g_n1g, g_n1b, g_bo, Mi, E, s));
+        LAUNCH_C(c, 2, 0.0, s, launch_ln_bwd<T>(g32, E, t.z1, E, ly.n1g, g16w, E, g_n1g, g_n1b, g_bo, Mi, E, s, d_sub1));
         TIM_TRY(run_wgrad<T>(c, gop, E, t.att, E, g_wo, E, Mi, E, E, s));
         TIM_TRY(run_dgrad<T>(c, gop, ly.out_proj, Mi, epi(da, E, f32), s));
         if constexpr (f32) {
             CU_OK(c, cudaMemsetAsync(dqkv, 0, M * 3 * E * sizeof(float), s));
-            LAUNCH_C(c, 9, attn_bwd_flops, s, launch_attention_bwd_simt(static_cast<const float*>(t.qkv), da, dqkv, B, Ft, Qt, c->H, c->hd, qscale, s));
+            LAUNCH_C(c, 9, attn_bwd_flops, s, launch_attention_bwd_simt(static_cast<const float*>(t.qkv), da, dqkv, B, Ft, Qt, c->H, c->hd, qscale, s, d_attn));
         } else {
-            TIM_TRY(run_attention_bwd<T>(c, static_cast<const T*>(t.qkv), da, dqkv, astats, B, Ft, Qt, qscale, attn_bwd_flops, s));
+            TIM_TRY(run_attention_bwd<T>(c, static_cast<const T*>(t.qkv), da, dqkv, astats, B, Ft, Qt, qscale, attn_bwd_flops, s, d_attn));
         }
         LAUNCH(c, launch_colsum<T>(dqkv, 3 * E, 1, 0, 0, Mi, 0, 3 * E, g_bi, s));
         TIM_TRY(run_wgrad<T>(c, dqkv, 3 * E, t.xin, E, g_wi, E, Mi, 3 * E, E, s));
@@ -564,6 +622,8 @@ int encoder_train_bwd(tim_ctx* c, const tim_outputs* go, float* d_te, cudaStream
     bp.n_groups = qp.n_groups;
     for (int i = 0; i < qp.n_groups; ++i) bp.groups[i] = qp.groups[i];
     if (!d_te) return c->fail(TIM_ERR_INVALID, "tim_encoder_bwd: d_time_enc is NULL");
+    if (p_seq > 0.0f)          // seq_drop: the gradient w.r.t. the assembled tokens is the gradient w.r.t. the dropped tokens o mask
+        LAUNCH(c, launch_drop_apply<T>(g32, static_cast<T*>(nullptr), M * E, make_drop_site(p_seq, seed, DROP_SEQ, 0), s));
     LAUNCH_C(c, 3, 0.0, s, launch_assemble_bwd(bp, s));
     {
         int start = 0;

@@ -79,7 +79,7 @@ template <typename T, int V>
 __global__ void __launch_bounds__(RW * 32) ln_bwd_kernel(float* __restrict__ dy, int ldd, const float* __restrict__ z, int ldz,
                                                          const float* __restrict__ gamma, T* __restrict__ dz16, int ld16,
                                                          float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                         float* __restrict__ dbias, int M, int n) {
+                                                         float* __restrict__ dbias, int M, int n, DropSite drop) {
     extern __shared__ float sred[];                      // [RW][n]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float inv_n = 1.0f / static_cast<float>(n);
@@ -134,8 +134,15 @@ __global__ void __launch_bounds__(RW * 32) ln_bwd_kernel(float* __restrict__ dy,
                 float o[4];
                 o[0] = rstd * (dd[i].x - mg - zz[i].x * mgx); o[1] = rstd * (dd[i].y - mg - zz[i].y * mgx);
                 o[2] = rstd * (dd[i].z - mg - zz[i].z * mgx); o[3] = rstd * (dd[i].w - mg - zz[i].w * mgx);
+                store4t<float>(dr + c, o);               // the residual branch keeps the un-masked gradient
+                if (drop.thr) {                          // gradient w.r.t. the dropped sub-layer output: dz o mask
+                    const uint32_t e = static_cast<uint32_t>(row) * static_cast<uint32_t>(n) + static_cast<uint32_t>(c);
+                    float m0, m1, m2, m3;
+                    drop_pair(e >> 1, drop.key, drop.thr, drop.scale, m0, m1);
+                    drop_pair((e >> 1) + 1, drop.key, drop.thr, drop.scale, m2, m3);
+                    o[0] *= m0; o[1] *= m1; o[2] *= m2; o[3] *= m3;
+                }
                 az[i].x += o[0]; az[i].y += o[1]; az[i].z += o[2]; az[i].w += o[3];
-                store4t<float>(dr + c, o);
                 if (dz16) store4t<T>(dz16 + static_cast<size_t>(row) * ld16 + c, o);
             }
         }
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(RW * 32) ln_bwd_kernel(float* __restrict__ dy,
 // ---------------------------------------------------------------------------------------------------------------------
 template <typename TD, typename TA, typename TO, int MODE>
 __global__ void __launch_bounds__(256) act_bwd_kernel(const TD* __restrict__ d, const TA* __restrict__ a, TO* __restrict__ out,
-                                                      int rows, int cols, float* __restrict__ dbias) {
+                                                      int rows, int cols, float* __restrict__ dbias, DropSite drop) {
     const int c = (blockIdx.x * 256 + threadIdx.x) * 4;
     if (c >= cols) return;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -177,6 +184,12 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const TD* __restrict__ d, 
         const size_t off = static_cast<size_t>(r) * cols + c;
         float dv[4], av[4], o[4];
         load4<TD>(d + off, dv); load4<TA>(a + off, av);
+        if (drop.thr) {                                  // the activation's output was dropped in the forward: d <- d o mask
+            float m0, m1, m2, m3;
+            drop_pair(static_cast<uint32_t>(off >> 1), drop.key, drop.thr, drop.scale, m0, m1);
+            drop_pair(static_cast<uint32_t>(off >> 1) + 1, drop.key, drop.thr, drop.scale, m2, m3);
+            dv[0] *= m0; dv[1] *= m1; dv[2] *= m2; dv[3] *= m3;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             o[j] = MODE == 0 ? dv[j] * (sizeof(TA) == 2 ? gelu_grad_fast(av[j]) : gelu_grad(av[j])) : (av[j] > 0.0f ? dv[j] : 0.0f);
@@ -194,7 +207,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const TD* __restrict__ d, 
 // all-16-bit version (the FFN's GELU backward, [M, FF]): 8 columns = 16 bytes per thread and row, two rows in flight
 template <typename T, int MODE>
 __global__ void __launch_bounds__(256) act_bwd16_kernel(const T* __restrict__ d, const T* __restrict__ a, T* __restrict__ out, int rows, int cols,
-                                                        float* __restrict__ dbias) {
+                                                        float* __restrict__ dbias, DropSite drop) {
     const int c = (blockIdx.x * 256 + threadIdx.x) * 8;
     if (c >= cols) return;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -206,7 +219,13 @@ __global__ void __launch_bounds__(256) act_bwd16_kernel(const T* __restrict__ d,
         uint32_t ow[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float2 dv = unpack2<T>(dw[j]), av = unpack2<T>(aw[j]);
+            float2 dv = unpack2<T>(dw[j]);
+            const float2 av = unpack2<T>(aw[j]);
+            if (drop.thr) {
+                float m0, m1;
+                drop_pair(static_cast<uint32_t>(off >> 1) + j, drop.key, drop.thr, drop.scale, m0, m1);
+                dv.x *= m0; dv.y *= m1;
+            }
             const float o0 = MODE == 0 ? dv.x * gelu_grad_fast(av.x) : (av.x > 0.0f ? dv.x : 0.0f);
             const float o1 = MODE == 0 ? dv.y * gelu_grad_fast(av.y) : (av.y > 0.0f ? dv.y : 0.0f);
             ow[j] = pack2<T>(o0, o1);
@@ -222,13 +241,70 @@ __global__ void __launch_bounds__(256) act_bwd16_kernel(const T* __restrict__ d,
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) gelu_fwd_kernel(const T* __restrict__ u, T* __restrict__ h, size_t n4) {
+__global__ void __launch_bounds__(256) gelu_fwd_kernel(const T* __restrict__ u, T* __restrict__ h, size_t n4, DropSite drop) {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
         float v[4], o[4];
         load4<T>(u + 4 * i, v);
 #pragma unroll
         for (int j = 0; j < 4; ++j) o[j] = sizeof(T) == 4 ? gelu_erf(v[j]) : gelu_erf_fast(v[j]);
+        if (drop.thr) {                                  // the FFN's inner dropout (transformers.py:107)
+            float m0, m1, m2, m3;
+            drop_pair(static_cast<uint32_t>(2 * i), drop.key, drop.thr, drop.scale, m0, m1);
+            drop_pair(static_cast<uint32_t>(2 * i) + 1, drop.key, drop.thr, drop.scale, m2, m3);
+            o[0] *= m0; o[1] *= m1; o[2] *= m2; o[3] *= m3;
+        }
         store4t<T>(h + 4 * i, o);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) drop_cast_kernel(const float* __restrict__ in, T* __restrict__ out, size_t n2, DropSite drop) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n2; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float2 v = *reinterpret_cast<const float2*>(in + 2 * i);
+        float m0, m1;
+        drop_pair(static_cast<uint32_t>(i), drop.key, drop.thr, drop.scale, m0, m1);
+        out[2 * i] = from_float<T>(v.x * m0);
+        out[2 * i + 1] = from_float<T>(v.y * m1);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) drop_apply_kernel(float* __restrict__ x32, T* __restrict__ x16, size_t n2, DropSite drop) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n2; i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        float2 v = *reinterpret_cast<float2*>(x32 + 2 * i);
+        float m0, m1;
+        drop_pair(static_cast<uint32_t>(i), drop.key, drop.thr, drop.scale, m0, m1);
+        v.x *= m0; v.y *= m1;
+        *reinterpret_cast<float2*>(x32 + 2 * i) = v;
+        if (x16) { x16[2 * i] = from_float<T>(v.x); x16[2 * i + 1] = from_float<T>(v.y); }
+    }
+}
+
+// z = R(resid) + a o mask (one warp per row, 16-byte accesses)
+__global__ void __launch_bounds__(RW * 32) residual_drop_kernel(const float* a, const float* __restrict__ resid, const float2* __restrict__ rstats,
+                                                                const float* __restrict__ rgamma, const float* __restrict__ rbeta, float* z, int M,
+                                                                int n, DropSite drop) {
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * RW + (threadIdx.x >> 5);
+    if (row >= M) return;
+    float rs = 1.0f, nm = 0.0f;
+    if (rstats) { const float2 st = rstats[row]; rs = st.y; nm = -st.x * st.y; }
+    const size_t base = static_cast<size_t>(row) * n;
+    for (int c = lane * 4; c < n; c += 128) {
+        float av[4], rv[4], o[4];
+        load4<float>(a + base + c, av); load4<float>(resid + base + c, rv);
+        if (rstats) {
+            float g[4], b[4];
+            load4<float>(rgamma + c, g); load4<float>(rbeta + c, b);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rv[j] = fmaf(fmaf(rv[j], rs, nm), g[j], b[j]);
+        }
+        float m0, m1, m2, m3;
+        const uint32_t e = static_cast<uint32_t>(base + c);
+        drop_pair(e >> 1, drop.key, drop.thr, drop.scale, m0, m1);
+        drop_pair((e >> 1) + 1, drop.key, drop.thr, drop.scale, m2, m3);
+        o[0] = fmaf(av[0], m0, rv[0]); o[1] = fmaf(av[1], m1, rv[1]); o[2] = fmaf(av[2], m2, rv[2]); o[3] = fmaf(av[3], m3, rv[3]);
+        store4t<float>(z + base + c, o);
     }
 }
 
@@ -466,8 +542,9 @@ inline dim3 col_grid(int cols, long long rows) {
 
 template <typename T>
 cudaError_t launch_ln_bwd(float* dy, int ldd, const float* z, int ldz, const float* gamma, T* dz16, int ld16, float* dgamma, float* dbeta,
-                          float* dbias, int M, int n, cudaStream_t s) {
+                          float* dbias, int M, int n, cudaStream_t s, DropSite drop) {
     if (M <= 0) return cudaSuccess;
+    if (drop.thr && (static_cast<unsigned long long>(M) * n > 0xffffffffull || ld16 != n)) return cudaErrorInvalidValue;
     if ((n & 3) || (ldd & 3) || (ldz & 3) || (dz16 && (ld16 & 3)) || n > 2048) return cudaErrorInvalidValue;
     const size_t smem = static_cast<size_t>(RW) * n * sizeof(float);
     const int grid = row_grid(M, 148 * 2);
@@ -476,7 +553,7 @@ cudaError_t launch_ln_bwd(float* dy, int ldd, const float* z, int ldz, const flo
         auto kern = ln_bwd_kernel<T, V_>;                                                                               \
         static SmemAttrCache cache;                                                                                     \
         if (cudaError_t e = ensure_dynamic_smem(kern, smem, cache); e != cudaSuccess) return e;                         \
-        kern<<<grid, RW * 32, smem, s>>>(dy, ldd, z, ldz, gamma, dz16, ld16, dgamma, dbeta, dbias, M, n);               \
+        kern<<<grid, RW * 32, smem, s>>>(dy, ldd, z, ldz, gamma, dz16, ld16, dgamma, dbeta, dbias, M, n, drop);         \
     } while (0)
     if (n <= 512) TIM_LNB(4);
     else if (n <= 1024) TIM_LNB(8);
@@ -485,31 +562,32 @@ cudaError_t launch_ln_bwd(float* dy, int ldd, const float* z, int ldz, const flo
 #undef TIM_LNB
     return cudaGetLastError();
 }
-template cudaError_t launch_ln_bwd<float>(float*, int, const float*, int, const float*, float*, int, float*, float*, float*, int, int, cudaStream_t);
-template cudaError_t launch_ln_bwd<__half>(float*, int, const float*, int, const float*, __half*, int, float*, float*, float*, int, int, cudaStream_t);
-template cudaError_t launch_ln_bwd<__nv_bfloat16>(float*, int, const float*, int, const float*, __nv_bfloat16*, int, float*, float*, float*, int, int, cudaStream_t);
+template cudaError_t launch_ln_bwd<float>(float*, int, const float*, int, const float*, float*, int, float*, float*, float*, int, int, cudaStream_t, DropSite);
+template cudaError_t launch_ln_bwd<__half>(float*, int, const float*, int, const float*, __half*, int, float*, float*, float*, int, int, cudaStream_t, DropSite);
+template cudaError_t launch_ln_bwd<__nv_bfloat16>(float*, int, const float*, int, const float*, __nv_bfloat16*, int, float*, float*, float*, int, int, cudaStream_t, DropSite);
 
 template <typename TD, typename TA, typename TO>
-cudaError_t launch_act_bwd(int mode, const TD* d, const TA* a, TO* out, int rows, int cols, float* dbias, cudaStream_t s) {
+cudaError_t launch_act_bwd(int mode, const TD* d, const TA* a, TO* out, int rows, int cols, float* dbias, cudaStream_t s, DropSite drop) {
     if (rows <= 0 || cols <= 0) return cudaSuccess;
     if (cols & 3) return cudaErrorInvalidValue;
+    if (drop.thr && static_cast<unsigned long long>(rows) * cols > 0xffffffffull) return cudaErrorInvalidValue;
     if constexpr (std::is_same<TD, TA>::value && std::is_same<TD, TO>::value && sizeof(TD) == 2) {
         if ((cols & 7) == 0 && ((reinterpret_cast<uintptr_t>(d) | reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
             const int gx = (cols + 2047) / 2048;
             long long gy = (148 * 8 + gx - 1) / gx;
             if (gy > rows) gy = rows;
             const dim3 grid(gx, static_cast<unsigned>(gy));
-            if (mode == 0) act_bwd16_kernel<TD, 0><<<grid, 256, 0, s>>>(d, a, out, rows, cols, dbias);
-            else act_bwd16_kernel<TD, 1><<<grid, 256, 0, s>>>(d, a, out, rows, cols, dbias);
+            if (mode == 0) act_bwd16_kernel<TD, 0><<<grid, 256, 0, s>>>(d, a, out, rows, cols, dbias, drop);
+            else act_bwd16_kernel<TD, 1><<<grid, 256, 0, s>>>(d, a, out, rows, cols, dbias, drop);
             return cudaGetLastError();
         }
     }
     const dim3 grid = col_grid(cols, rows);
-    if (mode == 0) act_bwd_kernel<TD, TA, TO, 0><<<grid, 256, 0, s>>>(d, a, out, rows, cols, dbias);
-    else act_bwd_kernel<TD, TA, TO, 1><<<grid, 256, 0, s>>>(d, a, out, rows, cols, dbias);
+    if (mode == 0) act_bwd_kernel<TD, TA, TO, 0><<<grid, 256, 0, s>>>(d, a, out, rows, cols, dbias, drop);
+    else act_bwd_kernel<TD, TA, TO, 1><<<grid, 256, 0, s>>>(d, a, out, rows, cols, dbias, drop);
     return cudaGetLastError();
 }
-#define TIM_ACT_BWD(TD, TA, TO) template cudaError_t launch_act_bwd<TD, TA, TO>(int, const TD*, const TA*, TO*, int, int, float*, cudaStream_t);
+#define TIM_ACT_BWD(TD, TA, TO) template cudaError_t launch_act_bwd<TD, TA, TO>(int, const TD*, const TA*, TO*, int, int, float*, cudaStream_t, DropSite);
 TIM_ACT_BWD(float, float, float)
 TIM_ACT_BWD(__half, __half, __half)
 TIM_ACT_BWD(__nv_bfloat16, __nv_bfloat16, __nv_bfloat16)
@@ -518,15 +596,45 @@ TIM_ACT_BWD(float, float, __nv_bfloat16)
 #undef TIM_ACT_BWD
 
 template <typename T>
-cudaError_t launch_gelu_fwd(const T* u, T* h, size_t n, cudaStream_t s) {
+cudaError_t launch_gelu_fwd(const T* u, T* h, size_t n, cudaStream_t s, DropSite drop) {
     if (!n) return cudaSuccess;
-    if (n & 3) return cudaErrorInvalidValue;
-    gelu_fwd_kernel<T><<<flat_grid(n / 4), 256, 0, s>>>(u, h, n / 4);
+    if ((n & 3) || (drop.thr && n > 0xffffffffull)) return cudaErrorInvalidValue;
+    gelu_fwd_kernel<T><<<flat_grid(n / 4), 256, 0, s>>>(u, h, n / 4, drop);
     return cudaGetLastError();
 }
-template cudaError_t launch_gelu_fwd<float>(const float*, float*, size_t, cudaStream_t);
-template cudaError_t launch_gelu_fwd<__half>(const __half*, __half*, size_t, cudaStream_t);
-template cudaError_t launch_gelu_fwd<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, size_t, cudaStream_t);
+template cudaError_t launch_gelu_fwd<float>(const float*, float*, size_t, cudaStream_t, DropSite);
+template cudaError_t launch_gelu_fwd<__half>(const __half*, __half*, size_t, cudaStream_t, DropSite);
+template cudaError_t launch_gelu_fwd<__nv_bfloat16>(const __nv_bfloat16*, __nv_bfloat16*, size_t, cudaStream_t, DropSite);
+
+template <typename T>
+cudaError_t launch_drop_cast(const float* in, T* out, size_t n, DropSite drop, cudaStream_t s) {
+    if (!n) return cudaSuccess;
+    if ((n & 1) || n > 0xffffffffull) return cudaErrorInvalidValue;
+    drop_cast_kernel<T><<<flat_grid(n / 2), 256, 0, s>>>(in, out, n / 2, drop);
+    return cudaGetLastError();
+}
+template cudaError_t launch_drop_cast<float>(const float*, float*, size_t, DropSite, cudaStream_t);
+template cudaError_t launch_drop_cast<__half>(const float*, __half*, size_t, DropSite, cudaStream_t);
+template cudaError_t launch_drop_cast<__nv_bfloat16>(const float*, __nv_bfloat16*, size_t, DropSite, cudaStream_t);
+
+template <typename T>
+cudaError_t launch_drop_apply(float* x32, T* x16, size_t n, DropSite drop, cudaStream_t s) {
+    if (!n || !drop.thr) return cudaSuccess;
+    if ((n & 1) || n > 0xffffffffull) return cudaErrorInvalidValue;
+    drop_apply_kernel<T><<<flat_grid(n / 2), 256, 0, s>>>(x32, x16, n / 2, drop);
+    return cudaGetLastError();
+}
+template cudaError_t launch_drop_apply<float>(float*, float*, size_t, DropSite, cudaStream_t);
+template cudaError_t launch_drop_apply<__half>(float*, __half*, size_t, DropSite, cudaStream_t);
+template cudaError_t launch_drop_apply<__nv_bfloat16>(float*, __nv_bfloat16*, size_t, DropSite, cudaStream_t);
+
+cudaError_t launch_residual_drop(const float* a, const float* resid, const float2* rstats, const float* rgamma, const float* rbeta, float* z,
+                                 int M, int n, DropSite drop, cudaStream_t s) {
+    if (M <= 0) return cudaSuccess;
+    if ((n & 3) || static_cast<unsigned long long>(M) * n > 0xffffffffull) return cudaErrorInvalidValue;
+    residual_drop_kernel<<<(M + RW - 1) / RW, RW * 32, 0, s>>>(a, resid, rstats, rgamma, rbeta, z, M, n, drop);
+    return cudaGetLastError();
+}
 
 template <typename T>
 cudaError_t launch_colsum(const T* x, int ld, int G, int group_rows, int row_off, int R, int col_off, int ncols, float* out, cudaStream_t s) {

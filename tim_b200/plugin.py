@@ -190,6 +190,11 @@ class TIMEngine:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.tim_train_enable(self._ctx), self._ctx)
 
+    def set_dropout(self, p_feat: float = 0.0, p_seq: float = 0.0, p_enc: float = 0.0, seed: int = 0) -> None:
+        """Dropout of the next encoder_train (and its backward): the reference's feat_drop / seq_drop / enc_dropout (tim.py:22-28).
+        Masks are a counter-based hash of (seed, site, layer, element) - pass a fresh seed per step; all zero = no dropout."""
+        _lib.check(self.lib.tim_set_dropout(self._ctx, float(p_feat), float(p_seq), float(p_enc), int(seed) & 0xFFFFFFFFFFFFFFFF), self._ctx)
+
     def bind_grad(self, key: str, grad: torch.Tensor) -> None:
         """The backward accumulates d loss / d <key> into `grad` (fp32, contiguous, on this device)."""
         if grad.device != self.device or grad.dtype != torch.float32 or not grad.is_contiguous():
@@ -414,11 +419,6 @@ class _Binding:
             return
         import torch.distributed as dist
         from .dist import FlatGrads
-        bad = [n for n, m in self.model.named_modules()
-               if (isinstance(m, torch.nn.Dropout) and m.p > 0) or (isinstance(m, torch.nn.MultiheadAttention) and m.dropout > 0)]
-        if bad:
-            raise NotImplementedError("tim_b200: the training leg has no dropout kernels; construct the model with all dropout "
-                                      f"probabilities 0 (non-zero in: {', '.join(bad[:4])}{' ...' if len(bad) > 4 else ''})")
         self.engine.enable_training()
         self.versions.clear()                       # every weight is packed again, now with its transposed copy
         self.flat = FlatGrads(self.model.named_parameters())
@@ -429,7 +429,41 @@ class _Binding:
         if self.distributed:
             self.engine.comm_init()
         self.callback_queued = False
+        self.drop_step = 0
         self.training_ready = True
+
+    def dropout_probs(self):
+        """(feat_drop, seq_drop, enc_dropout) as the reference's modules hold them NOW (helpers/encodings.py:141,149,177,
+        helpers/transformers.py:73-82) - read at every step, so a schedule that edits module.p keeps working. The library has one
+        probability for the transformer's four sites in all layers, which is how the reference constructs them (tim.py:119)."""
+        fe = self.model.feature_encoding
+        feat, enc = set(), set()
+        for name in ("visual_embedder", "audio_embedder"):
+            first = getattr(getattr(fe, name, None), "0", None)             # nn.Sequential(Dropout, Linear, GELU, LayerNorm)
+            if isinstance(first, torch.nn.Dropout):
+                feat.add(float(first.p))
+        for layer in getattr(self.model, self.engine.cfg.encoder_prefix).layers.children():
+            enc.add(float(getattr(layer.self_attn, "dropout", 0.0)))
+            enc.update(float(m.p) for m in (getattr(layer, n, None) for n in ("dropout1", "dropout", "dropout2")) if m is not None)
+        if len(feat) > 1 or len(enc) > 1:
+            raise NotImplementedError(f"tim_b200: the dropout probabilities differ between sites (embedders {sorted(feat)}, encoder "
+                                      f"layers {sorted(enc)}); the library takes one feat_drop and one enc_dropout")
+        seq = getattr(fe, "dropout", None)
+        return (feat.pop() if feat else 0.0), (float(seq.p) if seq is not None else 0.0), (enc.pop() if enc else 0.0)
+
+    def apply_dropout(self):
+        """Dropout of the next training forward: the module's probabilities and a fresh seed. The seed is a function of
+        torch.initial_seed() (what torch.manual_seed set), the rank and a step counter - reproducible, different on every rank and
+        step, and it consumes nothing from torch's generators (the reference's CPU randperm draws stay where they were)."""
+        p_feat, p_seq, p_enc = self.dropout_probs() if self.model.training else (0.0, 0.0, 0.0)
+        import torch.distributed as dist
+        rank = dist.get_rank() if self.distributed else 0
+        x = (torch.initial_seed() + 0x9E3779B97F4A7C15 * (self.drop_step + 1) + (rank << 40)) & 0xFFFFFFFFFFFFFFFF
+        x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF          # splitmix64 finaliser
+        x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        x ^= x >> 31
+        self.drop_step += 1
+        self.engine.set_dropout(p_feat, p_seq, p_enc, x)
 
     def attach_grads(self):
         """param.grad must be the flat buffer's views when the backward runs (optimizer.zero_grad() sets them to None by default):
@@ -494,6 +528,7 @@ def _encoder_train(b: "_Binding", vis, aud, time_enc, Qv, Qa):
     b.enable_training()
     b.sync()
     b.attach_grads()
+    b.apply_dropout()
     outs = _EncoderFn.apply(b, vis, aud, time_enc, int(Qv or 0), int(Qa or 0), b.anchor)
     return dict(zip(_EncoderFn.KEYS, outs))
 
@@ -509,13 +544,13 @@ def _forward_recognition(self, inputs, forward_type, time_encodings=None, num_v_
         raise ValueError(f"unknown forward_type {forward_type!r}")
     if self.training:
         # the reference applies dropout whenever the module is in train() mode, with or without autograd (helpers/transformers.py:
-        # 73-82, encodings.py:141,149,177): the training leg below refuses non-zero dropout probabilities instead of diverging
+        # 73-82, encodings.py:141,149,177): the encoder of a train()-mode module always runs the training forward (tim_set_dropout)
         b.enable_training()
-        if torch.is_grad_enabled():
-            if forward_type == "time_mlp":
-                b.sync()
-                b.attach_grads()
-                return _TimeMLPFn.apply(b, inputs, b.anchor)
+        if forward_type == "time_mlp" and torch.is_grad_enabled():
+            b.sync()
+            b.attach_grads()
+            return _TimeMLPFn.apply(b, inputs, b.anchor)
+        if forward_type == "encoder":
             o = _encoder_train(b, inputs[0], inputs[1], time_encodings, num_v_queries, num_a_queries)
             return (o["verb"], o["noun"], o["action"], o["audio"]), o["feats"]
     b.sync()
@@ -621,15 +656,13 @@ def _forward_detection_train(self, inputs, feature_times, target):
         a_offsets, a_labels, a_ious = _label_queries_device(self, b.engine, a_queries, target, "audio")
         all_times = torch.cat([all_times, a_queries], dim=1)
         a_queries = torch.flatten(a_queries, 0, 1)
+    b.sync()
     if torch.is_grad_enabled():
-        b.sync()
         b.attach_grads()
         te = _TimeMLPFn.apply(b, all_times, b.anchor)
-        o = _encoder_train(b, inputs[0], inputs[1], te, nv, na)
     else:
-        b.sync()
         te = b.engine.time_mlp(all_times)
-        o = b.engine.encoder(inputs[0], inputs[1], te, nv, na)
+    o = _encoder_train(b, inputs[0], inputs[1], te, nv, na)       # train() mode: dropout applies with or without autograd
     cls = (o["verb"], o["noun"], o["action"], o["audio"])
     reg = (o["reg_v"], o["reg_a"])
     return (cls, reg, o["feats"]), (v_offsets, a_offsets), (v_labels, a_labels), (v_queries, a_queries), (v_ious, a_ious)
