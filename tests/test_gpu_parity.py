@@ -349,7 +349,10 @@ def test_patch_model_dropin(lib, name, dt):
             with torch.no_grad():
                 te = m2(times, "time_mlp")
                 outs[tag] = m2([vis, aud], "encoder", te, Qv, Qa)[0][2].float().cpu().numpy()
-        ev = run()["action"].float().cpu().numpy()
+        # eval() output of the same ORIGINAL weights (`model` above carries the scaled linear1 by now)
+        m3 = patch_model(FakeTIM(cfg, sd).to(dev).eval(), compute_dtype=dt)
+        with torch.no_grad():
+            ev = m3([vis, aud], "encoder", m3(times, "time_mlp"), Qv, Qa)[0][2].float().cpu().numpy()
         assert rel_l2(outs["p0"], ev) <= 5 * tol
         assert rel_l2(outs["p"], ev) > 0.05
 
