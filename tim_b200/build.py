@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtim_b200.so")
-SOURCES = ["api.cu", "gemm_umma.cu", "gemm_umma2.cu", "gemm_simt.cu", "attention.cu", "attention_umma.cu", "attention_umma3.cu", "elementwise.cu", "labels.cu", "nms.cu", "detpost.cu",
+SOURCES = ["api.cu", "gemm_umma.cu", "gemm_umma2.cu", "gemm_simt.cu", "attention.cu", "attention_umma.cu", "attention_umma4.cu", "elementwise.cu", "labels.cu", "nms.cu", "detpost.cu",
            "gemm_wgrad.cu", "attention_bwd.cu", "attention_bwd_umma.cu", "train_rows.cu"]
 HEADERS = ["kernels.h", "ptx.cuh", "train.inl", os.path.join("..", "..", "include", "tim_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

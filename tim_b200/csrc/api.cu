@@ -97,7 +97,7 @@ struct tim_ctx {
     uint64_t launches = 0;
     EncodeTiledFn encode = nullptr;
     int gemm_version = 2;       // 2: CTA-pair kernel where the shape allows, 1: single-CTA kernel only (TIM_B200_GEMM=1)
-    int attn_version = 2;       // 2: tcgen05 attention (attention_umma.cu, default); 3: the deeper-pipeline form (attention_umma3.cu: measured slower, kept for A/B); 1: warp-MMA attention only (TIM_B200_ATTN)
+    int attn_version = 4;       // 4: tcgen05 attention, decoupled pipeline (attention_umma4.cu, default where it fits, else 2); 2: the r01 form (attention_umma.cu); 1: warp-MMA attention only (TIM_B200_ATTN)
     bool fold_ln = false;       // encoder LayerNorms folded into the GEMMs around them (16-bit path, CTA-pair kernel shapes; TIM_B200_FOLD=0 disables)
     bool fold_dirty = true;     // a weight changed since the folded copies were made
     bool planes = true;         // folded flow keeps the residual stream as two 16-bit planes (mode 7); TIM_B200_PLANES=0: fp32 + 16-bit copy (mode 5)
@@ -519,10 +519,12 @@ int prepare_attention(tim_ctx* c, AttnUmmaParams* ap, bool* use_umma, const T* q
     return TIM_OK;
 }
 
-// tcgen05 attention forward: attention_umma.cu; TIM_B200_ATTN=3 selects the deeper-pipeline form (attention_umma3.cu, measured slower)
+// tcgen05 attention forward: the decoupled-pipeline kernel (attention_umma4.cu) where it applies (head_dim 64 / 128 and the staging
+// tile fits next to two stages), else attention_umma.cu; TIM_B200_ATTN=2 forces the latter
 template <typename T>
 cudaError_t launch_attention_tc(const tim_ctx* c, const AttnUmmaParams& ap, cudaStream_t s) {
-    return c->attn_version >= 3 ? launch_attention_umma3<T>(ap, c->hd, c->num_sms, s) : launch_attention_umma<T>(ap, c->hd, c->num_sms, s);
+    return c->attn_version >= 4 && attention_umma4_supported(ap.Ft, c->hd) ? launch_attention_umma4<T>(ap, c->hd, c->num_sms, s)
+                                                                          : launch_attention_umma<T>(ap, c->hd, c->num_sms, s);
 }
 
 inline Epilogue epi(void* out, int ldo, bool out_fp32, int act = ACT_NONE, const float* resid = nullptr, int ldr = 0) {
@@ -978,7 +980,7 @@ int tim_create(tim_ctx** out, const tim_config* cfg, int device) {
     c->vn_tokens = g.variant == TIM_RECOGNITION && g.include_verb_noun && c->vis_data;
     c->esize = g.compute_dtype == TIM_FP32 ? 4 : 2;
     if (const char* gv = std::getenv("TIM_B200_GEMM")) c->gemm_version = std::atoi(gv) == 1 ? 1 : 2;
-    if (const char* av = std::getenv("TIM_B200_ATTN")) { const int v = std::atoi(av); c->attn_version = v < 1 ? 1 : (v > 3 ? 3 : v); }
+    if (const char* av = std::getenv("TIM_B200_ATTN")) { const int v = std::atoi(av); c->attn_version = v < 1 ? 1 : (v > 4 ? 4 : v); }
     if (const char* wv = std::getenv("TIM_B200_WGRAD_SPLITS")) c->wgrad_splits = std::atoi(wv);
     if (c->d % 4) return bail(c->fail(TIM_ERR_INVALID, "d_model must be a multiple of 4"));
     if (c->vis_data && !g.n_action) return bail(c->fail(TIM_ERR_INVALID, "visual data modality needs n_action > 0"));
@@ -1628,7 +1630,7 @@ int tim_bench_attention(int dtype, const void* qkv16, void* out16, int B, int Ft
     }
     if (dtype != TIM_BF16 && dtype != TIM_FP16) return fin(c->fail(TIM_ERR_INVALID, "tim_bench_attention: 16-bit dtypes only"));
     c->num_sms = prop.multiProcessorCount; c->device = dev; c->cfg.compute_dtype = dtype; c->esize = 2;
-    c->H = H; c->hd = hd; c->E = H * hd; c->attn_version = version < 1 ? 1 : (version > 3 ? 3 : version);
+    c->H = H; c->hd = hd; c->E = H * hd; c->attn_version = version < 1 ? 1 : (version > 4 ? 4 : version);
     int r = get_encode_fn(c);
     if (r) return fin(r);
     cudaStream_t s = nullptr;
@@ -1679,7 +1681,7 @@ int tim_test_attention(int dtype, const float* qkv, float* out, int B, int Ft, i
         }
         c->num_sms = prop.multiProcessorCount; c->device = dev; c->cfg.compute_dtype = dtype; c->esize = 2;
         c->H = H; c->hd = hd; c->E = static_cast<int>(E);
-        if (const char* av = std::getenv("TIM_B200_ATTN")) { const int v = std::atoi(av); c->attn_version = v < 1 ? 1 : (v > 3 ? 3 : v); }
+        if (const char* av = std::getenv("TIM_B200_ATTN")) { const int v = std::atoi(av); c->attn_version = v < 1 ? 1 : (v > 4 ? 4 : v); }
         int rc = get_encode_fn(c);
         if (rc) return fin(rc);
         // same dispatch as the forward: tcgen05 kernel where the shape allows, warp-MMA kernel otherwise

@@ -60,7 +60,8 @@ __device__ __forceinline__ UnitInfo decode_unit(const AttnUmmaParams& p, int u) 
     return ui;
 }
 
-template <typename T, int HD>
+// DROP: attention-probability dropout compiled in (training forward with p > 0 only: the inference kernel carries none of it)
+template <typename T, int HD, bool DROP>
 __global__ void __launch_bounds__(AU_THREADS, 1) attention_umma_kernel(const __grid_constant__ AttnUmmaParams p) {
     using C = AUCfg<HD>;
     constexpr int NST = C::NST, KBOX = C::KBOX;
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(AU_THREADS, 1) attention_umma_kernel(const __g
                             s[c * 16 + j] = e;
                             ls[j & 3] += e;
                         }
-                        if (p.drop.thr) {
+                        if constexpr (DROP) {
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 float m0, m1;
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(AU_THREADS, 1) attention_umma_kernel(const __g
                 const float l = (ls[0] + ls[1]) + (ls[2] + ls[3]);
                 const float ps = qt ? ex2_approx(sself - m) : 0.0f;
                 const float inv = 1.0f / (l + ps);
-                const float m_self = p.drop.thr ? drop_one(2u * drop_pair0 + static_cast<uint32_t>(Ft), p.drop.key, p.drop.thr, p.drop.scale) : 1.0f;
+                const float m_self = DROP ? drop_one(2u * drop_pair0 + static_cast<uint32_t>(Ft), p.drop.key, p.drop.thr, p.drop.scale) : 1.0f;
                 sts_f32(stat(st, 0, row), inv);
                 sts_f32(stat(st, 1, row), ps * inv * m_self);
                 tc_fence_before();
@@ -483,11 +484,18 @@ template <int HD> size_t smem_for(int Fp) {
 template <typename T, int HD>
 cudaError_t launch_hd(const AttnUmmaParams& p, int num_sms, cudaStream_t s) {
     const size_t smem = smem_for<HD>(p.Fp);
-    auto kern = attention_umma_kernel<T, HD>;
-    static SmemAttrCache cache;
-    if (cudaError_t e = ensure_dynamic_smem(kern, smem, cache); e != cudaSuccess) return e;
     const int grid = p.num_units < num_sms ? p.num_units : num_sms;
-    kern<<<grid, AU_THREADS, smem, s>>>(p);
+    if (p.drop.thr) {
+        auto kern = attention_umma_kernel<T, HD, true>;
+        static SmemAttrCache cache;
+        if (cudaError_t e = ensure_dynamic_smem(kern, smem, cache); e != cudaSuccess) return e;
+        kern<<<grid, AU_THREADS, smem, s>>>(p);
+    } else {
+        auto kern = attention_umma_kernel<T, HD, false>;
+        static SmemAttrCache cache;
+        if (cudaError_t e = ensure_dynamic_smem(kern, smem, cache); e != cudaSuccess) return e;
+        kern<<<grid, AU_THREADS, smem, s>>>(p);
+    }
     return cudaGetLastError();
 }
 

@@ -151,7 +151,7 @@ struct AttnUmmaParams {
     int tpu, chunks;      // row tiles per work unit, work units per (clip, head)
     int num_units;
     int pf_mode, pf_tiles; // L2 prefetch policy of the TMA producer (see launch_attention_umma)
-    DropSite drop;         // attention-probability dropout (training forward; attention_umma.cu only)
+    DropSite drop;         // attention-probability dropout (training forward; attention_umma.cu / attention_umma4.cu)
 };
 bool attention_umma_supported(int Ft, int hd);
 size_t attention_umma_smem(int Ft, int hd);
@@ -159,10 +159,11 @@ size_t attention_umma_smem(int Ft, int hd);
 template <typename T>
 cudaError_t launch_attention_umma(AttnUmmaParams p, int hd, int num_sms, cudaStream_t s);
 
-// deeper-pipeline form (attention_umma3.cu): one buffer and 128 TMEM columns per tile in flight, own-key / own-value terms by the
-// thread that owns the row; same parameter block and tensor maps
+// decoupled-pipeline form (attention_umma4.cu): event-driven MMA issue, own output staging tile, stages released at P.V completion;
+// same parameter block and tensor maps. head_dim 64 / 128 and K_f + V_f + two stages + staging within 227 KB
+bool attention_umma4_supported(int Ft, int hd);
 template <typename T>
-cudaError_t launch_attention_umma3(AttnUmmaParams p, int hd, int num_sms, cudaStream_t s);
+cudaError_t launch_attention_umma4(AttnUmmaParams p, int hd, int num_sms, cudaStream_t s);
 
 cudaError_t launch_attention_simt(const float* qkv, float* out, int B, int Ft, int Qt, int H, int hd, cudaStream_t s, DropSite drop = DropSite());
 size_t attention_simt_smem(int Ft, int hd);

@@ -317,7 +317,7 @@ int encoder_train_fwd(tim_ctx* c, const float* vis, const float* aud, const floa
     const float p_feat = tr.p_feat, p_seq = tr.p_seq, p_enc = tr.p_enc;
     const uint32_t seed = tr.drop_seed;
     tr.tape_p_seq = p_seq; tr.tape_p_enc = p_enc; tr.tape_seed = seed;
-    if (p_enc > 0.0f && !f32 && !(c->attn_version == 2 && attention_umma_supported(c->Ft, c->hd) && attention_bwd_umma_supported(c->Ft, c->hd)))
+    if (p_enc > 0.0f && !f32 && !(c->attn_version >= 2 && attention_umma_supported(c->Ft, c->hd) && attention_bwd_umma_supported(c->Ft, c->hd)))
         return c->fail(TIM_ERR_INVALID, "attention dropout in the 16-bit modes needs head_dim 64 or 128 and the tcgen05 attention kernels (head_dim %d)", c->hd);
     auto embed = [&](const float* x, void* xT, const LinearW& w, int rows, int dim, float* pre, float* act, uint32_t site) -> int {
         if (!x) return c->fail(TIM_ERR_INVALID, "input features are NULL");

@@ -26,7 +26,7 @@ SHAPES = {  # name: (B, Ft, Qt, H, hd)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--versions", default="1,2,3", help="1 warp-MMA, 2 tcgen05 (r01 form), 3 tcgen05 deeper pipeline")
+    ap.add_argument("--versions", default="1,2,4", help="1 warp-MMA, 2 tcgen05 (r01 form), 4 tcgen05 decoupled pipeline")
     ap.add_argument("--dtype", default="fp16")
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--shapes", default="cfg2,cfg3,cfg4")
@@ -53,7 +53,7 @@ def main():
             gbs = M * 8 * E / (ms.value * 1e-3) / 1e9
             outs[v] = out
             print(f"{name:6s} v{v} B={B} Ft={Ft} Qt={Qt} H={H} hd={hd}: {ms.value * 1e3:9.1f} us  {gbs:8.1f} GB/s algorithmic", flush=True)
-        for v in (2, 3):
+        for v in (2, 4):
             if 1 in outs and v in outs:
                 d = (outs[1].float() - outs[v].float()).norm() / outs[1].float().norm()
                 print(f"{name:6s} v{v} vs v1 rel-L2 {d.item():.2e}")
