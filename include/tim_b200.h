@@ -272,6 +272,11 @@ int tim_bench_wgrad(int compute_dtype, const void* dY16, const void* X16, float*
 int tim_test_attention_bwd(int compute_dtype, const float* qkv, const float* dO, float* dqkv, int B, int Ft, int Qt, int H, int hd,
                            float qscale, void* stream);
 
+/* debug hook (tools/attn_roles.py): a device buffer [>= 148][16] of 64-bit counters to which every launch of the decoupled attention
+ * forward kernel adds, per CTA, the cycles one warp of each role spent waiting (see attention_umma4.cu: PR_*); NULL switches it off.
+ * Process-wide, not thread-safe: a measurement aid, not part of the data path. */
+int tim_debug_role_prof(unsigned long long* dev_buf);
+
 /* timing hook (tools/attn_bench.py): `iters` back-to-back attention launches on a 16-bit two-stream qkv buffer
  * [(B*Ft + B*Qt), 3*H*hd] -> out16 [(B*Ft + B*Qt), H*hd]; version 1 = warp-MMA kernel, 2 = tcgen05 kernel (where supported). */
 int tim_bench_attention(int compute_dtype, const void* qkv16, void* out16, int B, int Ft, int Qt, int H, int hd, int version,

@@ -1617,6 +1617,11 @@ int tim_bench_linear(int dtype, const void* A16, const void* W16, const float* b
     return TIM_OK;
 }
 
+int tim_debug_role_prof(unsigned long long* dev_buf) {
+    set_attention_role_prof(dev_buf);
+    return TIM_OK;
+}
+
 int tim_bench_attention(int dtype, const void* qkv16, void* out16, int B, int Ft, int Qt, int H, int hd, int version, int iters,
                         float* ms_per_iter) {
     TmpCtx t;

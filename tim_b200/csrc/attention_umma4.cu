@@ -13,9 +13,9 @@
 //   * the output staging tile is its OWN buffer (one, shared by both stages: each epilogue warp owns a 32-row slab and waits for
 //     its previous bulk store to have read it), so a stage's shared memory is free the moment P.V completes: the producer waits on
 //     o_full itself and the load of tile g+2 runs under the epilogue of tile g;
-//   * the epilogue drains the whole O tile from TMEM into registers first and releases the TMEM stage (t_empty) before it does the
-//     arithmetic; the own-value rows are parked in the staging slab in the output layout and each thread overwrites its own row in
-//     place (no scratch in the stage buffers);
+//   * the epilogue releases the TMEM stage (t_empty) as soon as the second half of the O tile is in registers; the own-value rows
+//     (16-byte loads issued before the waits) are parked in the staging slab in the output layout and each thread overwrites its
+//     own row in place (no scratch in the stage buffers);
 //   * the number of 16-key chunks is a template parameter for Ft in (96, 112] and (112, 128] (cfg2 / cfg4: 100 keys), which removes
 //     the data-dependent branches from the softmax loops.
 // head_dim 64 / 128 and K_f + V_f + 2 stages + staging <= 227 KB; everything else stays on attention_umma.cu.
@@ -72,6 +72,24 @@ __device__ __forceinline__ bool mbar_test_all(uint32_t bar, uint32_t parity) {
         : "memory");
     return __all_sync(0xffffffffu, done != 0);
 }
+
+// 16-byte read-only global load that stays where it is written (the compiler hoists plain loads above the epilogue arithmetic,
+// where the O tile already fills the register file)
+__device__ __forceinline__ uint4 ldg_nc_u128_pinned(const void* ptr) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr) : "memory");
+    return v;
+}
+
+// role profile (debug hook, off unless tim_debug_role_prof gave a buffer): cycles one warp of each role spends in its waits
+struct ProfClock {
+    bool on;
+    long long t0;
+    __device__ __forceinline__ void begin() { if (on) t0 = clock64(); }
+    __device__ __forceinline__ void end(unsigned long long& acc) { if (on) acc += static_cast<unsigned long long>(clock64() - t0); }
+};
+enum { PR_TOTAL = 0, PR_PROD_KF, PR_PROD_STAGE, PR_PROD_VF, PR_MMA_IDLE, PR_MMA_TOTAL, PR_SM_WAIT_S, PR_SM_TOTAL, PR_EP_WAIT_READ, PR_EP_WAIT_P,
+       PR_EP_WAIT_O, PR_EP_TOTAL, PR_TILES, PR_EP_WAIT_TMEM, PR_COUNT };
 
 // the MMA warp's walk over (unit, tile): two of these run independently, one for the S products, one for the P.V products
 struct TileIt {
@@ -147,6 +165,10 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_umma4_kernel(const __
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    ProfClock pc;
+    pc.on = p.prof != nullptr;
+    unsigned long long pr[PR_COUNT] = {};
+    const long long t_start = pc.on ? clock64() : 0;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -189,7 +211,9 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_umma4_kernel(const __
         uint32_t g = 0, un = 0;
         for (int u = blockIdx.x; u < p.num_units; u += gridDim.x, ++un) {
             const Unit4 ui = decode_unit4(p, u);
+            pc.begin();
             mbar_wait(kf_empty, (un & 1u) ^ 1u);
+            pc.end(pr[PR_PROD_KF]);
             if (elect_one()) {
                 mbar_arrive_expect_tx(kf_full, kv_bytes);
 #pragma unroll
@@ -201,7 +225,9 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_umma4_kernel(const __
                 if (p.pf_mode >= 1) prefetch_next();
                 // the stage's buffers (Q -> P, K_q) are free once P.V of the tile that used them has completed (which implies its S
                 // products have): nothing else reads them
+                pc.begin();
                 mbar_wait(o_full(st), ph ^ 1u);
+                pc.end(pr[PR_PROD_STAGE]);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(q_full(st), t == 0 ? C::Q_BYTES : 2 * C::Q_BYTES);
 #pragma unroll
@@ -215,7 +241,9 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_umma4_kernel(const __
                     }
                 }
                 if (t == ui.t_lo) {
+                    pc.begin();
                     mbar_wait(vf_empty, (un & 1u) ^ 1u);
+                    pc.end(pr[PR_PROD_VF]);
                     if (elect_one()) {
                         mbar_arrive_expect_tx(vf_full, kv_bytes);
 #pragma unroll
@@ -226,6 +254,10 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_umma4_kernel(const __
             }
         }
         __syncwarp();
+        if (pc.on && lane == 0) {
+            pr[PR_TOTAL] = static_cast<unsigned long long>(clock64() - t_start);
+            for (int i = PR_TOTAL; i <= PR_PROD_VF; ++i) atomicAdd(p.prof + blockIdx.x * 16 + i, pr[i]);
+        }
     } else if (warp == 1) {
         // ===================== MMA issuer (event-driven) =====================
         const uint32_t idesc_s = umma_idesc_f16(FmtOf4<T>::v, A4_BM, static_cast<uint32_t>(Fp));
@@ -291,10 +323,14 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_umma4_kernel(const __
                     progressed = true;
                 }
             }
-            if (progressed) idle = 0;
-            else if (++idle > TIM_SPIN_LIMIT) __trap();
+            if (progressed) { if (idle) pc.end(pr[PR_MMA_IDLE]); idle = 0; }
+            else { if (idle == 0) pc.begin(); if (++idle > TIM_SPIN_LIMIT) __trap(); }
         }
         __syncwarp();
+        if (pc.on && lane == 0) {
+            atomicAdd(p.prof + blockIdx.x * 16 + PR_MMA_IDLE, pr[PR_MMA_IDLE]);
+            atomicAdd(p.prof + blockIdx.x * 16 + PR_MMA_TOTAL, static_cast<unsigned long long>(clock64() - t_start));
+        }
     } else if (warp < 6) {
         // ===================== softmax (warps 2..5) =====================
         const int quarter = warp & 3;
@@ -307,7 +343,9 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_umma4_kernel(const __
                 const int st = g % NST;
                 const uint32_t ph = (g / NST) & 1u;
                 const bool qt = t > 0;
+                pc.begin();
                 mbar_wait(s_full(st), ph);
+                pc.end(pr[PR_SM_WAIT_S]);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(st * C::TMEM_STAGE);
                 float s[128];
@@ -340,7 +378,8 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_umma4_kernel(const __
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     if (c * 16 < Fp) {
-                        if (c * 16 + 16 > Ft) {          // only the last chunk holds padded keys (their K_f rows are zero-filled)
+                        // only the last chunk holds padded keys (their K_f rows are zero-filled); with FPC the chunk is known
+                        if (FPC ? (c == FPC / 16 - 1) : (c * 16 + 16 > Ft)) {
 #pragma unroll
                             for (int j = 0; j < 16; ++j)
                                 if (c * 16 + j >= Ft) s[c * 16 + j] = -INFINITY;
@@ -394,12 +433,18 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_umma4_kernel(const __
                 if (lane == 0) mbar_arrive(p_full(st));
             }
         }
+        if (pc.on && warp == 2 && lane == 0) {
+            atomicAdd(p.prof + blockIdx.x * 16 + PR_SM_WAIT_S, pr[PR_SM_WAIT_S]);
+            atomicAdd(p.prof + blockIdx.x * 16 + PR_SM_TOTAL, static_cast<unsigned long long>(clock64() - t_start));
+            atomicAdd(p.prof + blockIdx.x * 16 + PR_TILES, static_cast<unsigned long long>(g));
+        }
     } else {
         // ===================== epilogue (warps 6..9) =====================
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const uint32_t swz = static_cast<uint32_t>(row & 7);
         const T* qkv = static_cast<const T*>(p.qkv);
+        constexpr int HALF32 = HD / 64;                // 32-column TMEM loads per half of the O tile
         uint32_t g = 0;
         for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
             const Unit4 ui = decode_unit4(p, u);
@@ -411,21 +456,40 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_umma4_kernel(const __
                 const int nrows = min(A4_BM, (qt ? Qt : Ft) - row0);
                 const int nvalid = nrows - quarter * 32;       // rows of this warp's slab that exist
                 const bool vterm = qt && nvalid > 0;
-                // this warp's slab of the staging tile is free once its previous bulk store has read it
-                if (lane == 0) tma_store_wait_read<0>();
-                __syncwarp();
+                // own-value rows: coalesced 16-byte loads (8 lanes per row) issued first; their latency runs under the waits, the
+                // first TMEM loads and the previous bulk store's read of the slab
+                uint4 vreg[8][KBOX];
                 if (vterm) {
-                    // own-value rows: coalesced 16-byte loads (8 lanes per row), parked in the slab in the OUTPUT layout; after the
-                    // __syncwarp each thread only touches its own row, which it overwrites with the finished output
                     const T* vbase = qkv + (static_cast<size_t>(p.B) * Ft + static_cast<size_t>(ui.b) * Qt + row0 + quarter * 32) * ld + 2 * E + ui.h * HD + (lane & 7) * 8;
-                    uint4 vreg[8][KBOX];
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int rl = min(it * 4 + (lane >> 3), nvalid - 1);
 #pragma unroll
                         for (int w = 0; w < KBOX; ++w)
-                            vreg[it][w] = __ldg(reinterpret_cast<const uint4*>(vbase + static_cast<size_t>(rl) * ld + w * 64));
+                            vreg[it][w] = ldg_nc_u128_pinned(vbase + static_cast<size_t>(rl) * ld + w * 64);
                     }
+                }
+                pc.begin();
+                mbar_wait(p_full(st), ph);                 // softmax statistics of this tile are in smem
+                pc.end(pr[PR_EP_WAIT_P]);
+                const float inv = lds_f32(stat(st, 0, row));
+                const float wself = lds_f32(stat(st, 1, row));
+                pc.begin();
+                mbar_wait(o_full(st), ph);                 // P.V complete: O in TMEM
+                pc.end(pr[PR_EP_WAIT_O]);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(st * C::TMEM_STAGE);
+                uint32_t o[HALF32][32];
+#pragma unroll
+                for (int i = 0; i < HALF32; ++i) tmem_ld_32x32(taddr + i * 32, o[i]);
+                // this warp's slab of the staging tile is free once its previous bulk store has read it
+                pc.begin();
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp();
+                pc.end(pr[PR_EP_WAIT_READ]);
+                if (vterm) {
+                    // parked in the slab in the OUTPUT layout; after the __syncwarp each thread only touches its own row, which it
+                    // overwrites with the finished output
 #pragma unroll
                     for (int it = 0; it < 8; ++it) {
                         const int rl = it * 4 + (lane >> 3);
@@ -436,39 +500,47 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_umma4_kernel(const __
                     }
                     __syncwarp();
                 }
-                mbar_wait(p_full(st), ph);                 // softmax statistics of this tile are in smem
-                const float inv = lds_f32(stat(st, 0, row));
-                const float wself = lds_f32(stat(st, 1, row));
-                mbar_wait(o_full(st), ph);                 // P.V complete: O in TMEM
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(st * C::TMEM_STAGE);
-                uint32_t o[HD / 32][32];
-#pragma unroll
-                for (int c32 = 0; c32 < HD / 32; ++c32) tmem_ld_32x32(taddr + c32 * 32, o[c32]);
+                pc.begin();
                 tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(t_empty(st));   // the next S into this TMEM stage may be issued
+                pc.end(pr[PR_EP_WAIT_TMEM]);
 #pragma unroll
-                for (int c32 = 0; c32 < HD / 32; ++c32) {
+                for (int half = 0; half < 2; ++half) {
+                    if (half == 1) {
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const uint32_t addr = sOut + (c32 >> 1) * 16384 + row * 128 + ((static_cast<uint32_t>((c32 & 1) * 4 + c) ^ swz) << 4);
-                        float f[8];
+                        for (int i = 0; i < HALF32; ++i) tmem_ld_32x32(taddr + (HALF32 + i) * 32, o[i]);
+                        tmem_ld_wait();
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(t_empty(st));   // the next S into this TMEM stage may be issued
+                    }
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(o[c32][8 * c + j]) * inv;
-                        if (vterm) {
-                            const uint4 q4 = lds_u128(addr);
-                            const float2 v0 = unpack2<T>(q4.x), v1 = unpack2<T>(q4.y), v2 = unpack2<T>(q4.z), v3 = unpack2<T>(q4.w);
-                            f[0] = fmaf(wself, v0.x, f[0]); f[1] = fmaf(wself, v0.y, f[1]);
-                            f[2] = fmaf(wself, v1.x, f[2]); f[3] = fmaf(wself, v1.y, f[3]);
-                            f[4] = fmaf(wself, v2.x, f[4]); f[5] = fmaf(wself, v2.y, f[5]);
-                            f[6] = fmaf(wself, v3.x, f[6]); f[7] = fmaf(wself, v3.y, f[7]);
+                    for (int k16 = 0; k16 < HALF32 * 2; ++k16) {
+                        const int c16 = half * HALF32 * 2 + k16;       // 16-column group of the head row
+                        uint32_t addr[2];
+                        uint4 q4[2];
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            addr[c] = sOut + (c16 >> 2) * 16384 + row * 128 + ((static_cast<uint32_t>((c16 & 3) * 2 + c) ^ swz) << 4);
+                            if (vterm) q4[c] = lds_u128(addr[c]);      // both chunks before either store (in place: kept in this order)
                         }
-                        uint4 q;
-                        q.x = pack2<T>(f[0], f[1]); q.y = pack2<T>(f[2], f[3]);
-                        q.z = pack2<T>(f[4], f[5]); q.w = pack2<T>(f[6], f[7]);
-                        sts_u128(addr, q);
+#pragma unroll
+                        for (int c = 0; c < 2; ++c) {
+                            const int o0 = (k16 & 1) * 16 + 8 * c;
+                            float f[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(o[k16 >> 1][o0 + j]) * inv;
+                            if (vterm) {
+                                const float2 v0 = unpack2<T>(q4[c].x), v1 = unpack2<T>(q4[c].y), v2 = unpack2<T>(q4[c].z), v3 = unpack2<T>(q4[c].w);
+                                f[0] = fmaf(wself, v0.x, f[0]); f[1] = fmaf(wself, v0.y, f[1]);
+                                f[2] = fmaf(wself, v1.x, f[2]); f[3] = fmaf(wself, v1.y, f[3]);
+                                f[4] = fmaf(wself, v2.x, f[4]); f[5] = fmaf(wself, v2.y, f[5]);
+                                f[6] = fmaf(wself, v3.x, f[6]); f[7] = fmaf(wself, v3.y, f[7]);
+                            }
+                            uint4 q;
+                            q.x = pack2<T>(f[0], f[1]); q.y = pack2<T>(f[2], f[3]);
+                            q.z = pack2<T>(f[4], f[5]); q.w = pack2<T>(f[6], f[7]);
+                            sts_u128(addr[c], q);
+                        }
                     }
                 }
                 fence_proxy_async_smem();                  // staged output -> visible to the TMA store
@@ -484,6 +556,11 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_umma4_kernel(const __
         }
         if (lane == 0) tma_store_wait<0>();
         __syncwarp();
+        if (pc.on && warp == 6 && lane == 0) {
+            for (int i = PR_EP_WAIT_READ; i <= PR_EP_WAIT_O; ++i) atomicAdd(p.prof + blockIdx.x * 16 + i, pr[i]);
+            atomicAdd(p.prof + blockIdx.x * 16 + PR_EP_WAIT_TMEM, pr[PR_EP_WAIT_TMEM]);
+            atomicAdd(p.prof + blockIdx.x * 16 + PR_EP_TOTAL, static_cast<unsigned long long>(clock64() - t_start));
+        }
     }
 
     tc_fence_before();
@@ -520,7 +597,11 @@ cudaError_t launch_hd4(const AttnUmmaParams& p, int num_sms, cudaStream_t s) {
     return launch_one<T, HD, 0, false>(p, grid, smem, s);
 }
 
+unsigned long long* g_role_prof = nullptr;
+
 }  // namespace
+
+void set_attention_role_prof(unsigned long long* dev_buf) { g_role_prof = dev_buf; }
 
 bool attention_umma4_supported(int Ft, int hd) {
     if (Ft < 1 || Ft > 128 || (hd != 64 && hd != 128)) return false;
@@ -533,6 +614,7 @@ cudaError_t launch_attention_umma4(AttnUmmaParams p, int hd, int num_sms, cudaSt
     if (!attention_umma4_supported(p.Ft, hd) || p.B <= 0 || p.H <= 0 || p.Qt < 0) return cudaErrorInvalidValue;
     p.Fp = (p.Ft + 15) & ~15;
     p.tiles_q = (p.Qt + A4_BM - 1) / A4_BM;
+    p.prof = g_role_prof;
     const long long items = 1LL * p.B * p.H;
     const int tiles_total = 1 + p.tiles_q;
     // split an item's tiles into several work units when the items alone are too few to balance the persistent CTAs

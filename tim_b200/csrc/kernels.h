@@ -152,7 +152,10 @@ struct AttnUmmaParams {
     int num_units;
     int pf_mode, pf_tiles; // L2 prefetch policy of the TMA producer (see launch_attention_umma)
     DropSite drop;         // attention-probability dropout (training forward; attention_umma.cu / attention_umma4.cu)
+    unsigned long long* prof;  // role profile (tim_debug_role_prof): [CTA][16] cycle counters, NULL = off (attention_umma4.cu)
 };
+// device buffer [>= 148][16] of 64-bit counters the decoupled attention kernel adds its per-role wait / busy cycles to (NULL = off)
+void set_attention_role_prof(unsigned long long* dev_buf);
 bool attention_umma_supported(int Ft, int hd);
 size_t attention_umma_smem(int Ft, int hd);
 // fills Fp / tiles_q / tpu / chunks / num_units from B, Ft, Qt, H (the maps and qkv must already be set)
