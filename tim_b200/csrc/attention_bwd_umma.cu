@@ -11,7 +11,11 @@
 //   dQ  = dS K_f           M=128 rows, N=hd, K=Fp          A = dS K-major, B = K_f MN-major     -> TMEM [0, hd)   (S is consumed)
 //   dV_f += P^T dO         M=128 keys, N=hd, K=128 rows    A = P MN-major, B = dO MN-major      -> TMEM [256, 256 + hd), accumulates over the unit's tiles
 //   dK_f += dS^T Q         same                            A = dS MN-major, B = Q MN-major      -> TMEM [384, 384 + hd)
-// The own-key / own-value terms of query rows are element-wise per row and are done by the thread that owns the row.
+// The own-key / own-value terms of query rows are element-wise per row. Their global traffic runs in the COALESCED pattern - 8 lanes per
+// 128-byte row segment, 4 rows per instruction - and is turned to / from the one-thread-per-row view by shuffles (dot products of the
+// softmax warps, per-row scale factors of the own-key / own-value gradients) or through a staging slab (the epilogue parks the own-key
+// rows in its dQ slab, finishes each row in place and leaves the slab to a bulk store). The r02e form did all of it with one thread
+// per row, 32 different lines per load / store instruction (profiles/r02l_attention_bwd_roles.txt).
 // No atomics, no P / dS in global memory; HBM traffic is the algorithmic 14 KB per token row (+ the own k / v rows once more).
 //
 // One persistent CTA per SM, 320 threads: warp 0 TMA producer, warp 1 MMA issuer (and TMEM allocation), warps 2-5 softmax
@@ -47,7 +51,8 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
     const uint32_t kv_pad = (kv_bytes + 1023u) & ~1023u;
     const uint32_t sKF = base, sVF = base + kv_pad;
     const uint32_t sQ = sVF + kv_pad, sDO = sQ + TILE_BYTES, sP = sDO + TILE_BYTES, sDS = sP + PS_BYTES;
-    const uint32_t stat_base = sDS + PS_BYTES;              // float [2][128]: own-key dS of query rows, double-buffered by tile parity
+    const uint32_t sG = sDS + PS_BYTES;                     // dQ staging tile [KBOX][128 rows][128 B], chunk-swizzled (bulk-store source)
+    const uint32_t stat_base = sG + TILE_BYTES;             // float [2][128]: own-key dS of query rows, double-buffered by tile parity
     const uint32_t bar_base = stat_base + 1024;
     const uint32_t kv_full = bar_base, kv_empty = bar_base + 8, q_full = bar_base + 16, s_full = bar_base + 24, p_full = bar_base + 32,
                    o_full = bar_base + 40, dq_done = bar_base + 48, acc_empty = bar_base + 56, tmem_slot = bar_base + 64;
@@ -64,7 +69,7 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmKV); tma_prefetch_desc(&p.tmQf); tma_prefetch_desc(&p.tmQq);
-        tma_prefetch_desc(&p.tmDf); tma_prefetch_desc(&p.tmDq);
+        tma_prefetch_desc(&p.tmDf); tma_prefetch_desc(&p.tmDq); tma_prefetch_desc(&p.tmGf); tma_prefetch_desc(&p.tmGq);
     }
     if (warp == 1) {
         if (lane == 0) {
@@ -194,28 +199,45 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                 const int nrows = min(BU_BM, (qt ? Qt : Ft) - row0);
                 const bool valid = row < nrows;
                 const size_t grow = qt ? static_cast<size_t>(p.B) * Ft + static_cast<size_t>(b) * Qt + row0 + row : static_cast<size_t>(b) * Ft + row;
-                // own key / value rows of a query row: element-wise terms only - read straight from global memory by the row's thread
+                // own key / value rows of the query rows: s_self = q . k_own, dP_self = dO . v_own. Coalesced: 8 lanes read one 128-byte
+                // segment of a row (4 rows per instruction), take their part of the dot product against the Q / dO tile in shared
+                // memory, the 8 partial sums are folded by shuffles and handed to the thread that owns the row
                 float sself = -INFINITY, dps = 0.0f;
+                const int nv = nrows - quarter * 32;                 // rows of this warp's 32-row slab that exist
+                const size_t slab_row = qt ? static_cast<size_t>(p.B) * Ft + static_cast<size_t>(b) * Qt + row0 + quarter * 32 : 0;
                 mbar_wait(q_full, g & 1u);                           // Q and dO tiles of this tile are in shared memory
-                if (qt && valid) {
-                    const T* own = qkv + grow * ld + h * HD;
-                    float a0 = 0.0f, a1 = 0.0f;
+                if (qt && nv > 0) {
+                    const T* slab = qkv + slab_row * ld + h * HD + (lane & 7) * 8;
 #pragma unroll
-                    for (int c = 0; c < HD / 8; ++c) {
-                        const uint4 kq = __ldg(reinterpret_cast<const uint4*>(own + E + 8 * c));
-                        const uint4 vq = __ldg(reinterpret_cast<const uint4*>(own + 2 * E + 8 * c));
-                        const uint32_t off = static_cast<uint32_t>(c >> 3) * 16384 + row * 128 + ((static_cast<uint32_t>(c & 7) ^ swz) << 4);
-                        const uint4 qq = lds_u128(sQ + off), dd = lds_u128(sDO + off);
-                        const uint32_t kw[4] = {kq.x, kq.y, kq.z, kq.w}, vw[4] = {vq.x, vq.y, vq.z, vq.w};
-                        const uint32_t qw[4] = {qq.x, qq.y, qq.z, qq.w}, dw[4] = {dd.x, dd.y, dd.z, dd.w};
+                    for (int it = 0; it < 8; ++it) {
+                        const int rl = it * 4 + (lane >> 3);
+                        const T* own = slab + static_cast<size_t>(min(rl, nv - 1)) * ld;
+                        float a0 = 0.0f, a1 = 0.0f;
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 kf = unpack2<T>(kw[j]), vf = unpack2<T>(vw[j]), qf = unpack2<T>(qw[j]), df = unpack2<T>(dw[j]);
-                            a0 = fmaf(qf.x, kf.x, fmaf(qf.y, kf.y, a0));
-                            a1 = fmaf(df.x, vf.x, fmaf(df.y, vf.y, a1));
+                        for (int w = 0; w < KBOX; ++w) {
+                            const uint4 kq = __ldg(reinterpret_cast<const uint4*>(own + E + 64 * w));
+                            const uint4 vq = __ldg(reinterpret_cast<const uint4*>(own + 2 * E + 64 * w));
+                            const uint32_t off = static_cast<uint32_t>(w) * 16384 + static_cast<uint32_t>(quarter * 32 + rl) * 128 +
+                                                 ((static_cast<uint32_t>(lane & 7) ^ static_cast<uint32_t>(rl & 7)) << 4);
+                            const uint4 qq = lds_u128(sQ + off), dd = lds_u128(sDO + off);
+                            const uint32_t kw[4] = {kq.x, kq.y, kq.z, kq.w}, vw[4] = {vq.x, vq.y, vq.z, vq.w};
+                            const uint32_t qw[4] = {qq.x, qq.y, qq.z, qq.w}, dw[4] = {dd.x, dd.y, dd.z, dd.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 kf = unpack2<T>(kw[j]), vf = unpack2<T>(vw[j]), qf = unpack2<T>(qw[j]), df = unpack2<T>(dw[j]);
+                                a0 = fmaf(qf.x, kf.x, fmaf(qf.y, kf.y, a0));
+                                a1 = fmaf(df.x, vf.x, fmaf(df.y, vf.y, a1));
+                            }
                         }
+#pragma unroll
+                        for (int o = 1; o <= 4; o <<= 1) {
+                            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                        }
+                        const float t0 = __shfl_sync(0xffffffffu, a0, (lane & 3) * 8), t1 = __shfl_sync(0xffffffffu, a1, (lane & 3) * 8);
+                        if (it == (lane >> 2)) { sself = t0; dps = t1; }
                     }
-                    sself = a0; dps = a1;
+                    if (!valid) { sself = -INFINITY; dps = 0.0f; }
                 }
                 if (g > 0) mbar_wait(o_full, (g - 1) & 1u);          // P / dS tiles of the previous tile are no longer read by the tensor core
                 mbar_wait(s_full, g & 1u);
@@ -326,27 +348,36 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                 if (lane == 0) mbar_arrive(p_full);
                 // ---- own-key / own-value gradients of query rows: dk_own = ln2 dss q~, dv_own = p_self dO ----
                 // (q~ and dO rows come from global memory here, an L2 hit: the shared-memory tiles may already be receiving the next
-                // tile - the producer reloads them as soon as this tile's products retire, which this thread no longer waits for)
-                if (qt && valid) {
-                    T* o = dqkv + grow * ld + h * HD;
-                    const T* qrow = qkv + grow * ld + h * HD;
-                    const T* drow = dOp + grow * static_cast<size_t>(E) + h * HD;
-                    const float kk = qln2 * dss;
+                // tile - the producer reloads them as soon as this tile's products retire, which this thread no longer waits for.)
+                // Coalesced like the dot products above; the per-row factors travel from the row's thread by shuffle.
+                if (qt && nv > 0) {
+                    const float kk = qln2 * dss, pv = ps * m_self;
+                    T* oslab = dqkv + slab_row * ld + h * HD + (lane & 7) * 8;
+                    const T* qslab = qkv + slab_row * ld + h * HD + (lane & 7) * 8;
+                    const T* dslab = dOp + slab_row * static_cast<size_t>(E) + h * HD + (lane & 7) * 8;
 #pragma unroll
-                    for (int c = 0; c < HD / 8; ++c) {
-                        const uint4 qq = __ldg(reinterpret_cast<const uint4*>(qrow + 8 * c)), dd = __ldg(reinterpret_cast<const uint4*>(drow + 8 * c));
-                        const uint32_t qw[4] = {qq.x, qq.y, qq.z, qq.w}, dw[4] = {dd.x, dd.y, dd.z, dd.w};
-                        uint4 ok, ov;
-                        uint32_t* wk = reinterpret_cast<uint32_t*>(&ok);
-                        uint32_t* wv = reinterpret_cast<uint32_t*>(&ov);
+                    for (int it = 0; it < 8; ++it) {
+                        const int rl = it * 4 + (lane >> 3);
+                        const float kk_r = __shfl_sync(0xffffffffu, kk, rl), pv_r = __shfl_sync(0xffffffffu, pv, rl);
+                        if (rl < nv) {
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 qf = unpack2<T>(qw[j]), df = unpack2<T>(dw[j]);
-                            wk[j] = pack2<T>(kk * qf.x, kk * qf.y);
-                            wv[j] = pack2<T>(ps * m_self * df.x, ps * m_self * df.y);
+                            for (int w = 0; w < KBOX; ++w) {
+                                const uint4 qq = __ldg(reinterpret_cast<const uint4*>(qslab + static_cast<size_t>(rl) * ld + 64 * w));
+                                const uint4 dd = __ldg(reinterpret_cast<const uint4*>(dslab + static_cast<size_t>(rl) * E + 64 * w));
+                                const uint32_t qw[4] = {qq.x, qq.y, qq.z, qq.w}, dw[4] = {dd.x, dd.y, dd.z, dd.w};
+                                uint4 ok, ov;
+                                uint32_t* wk = reinterpret_cast<uint32_t*>(&ok);
+                                uint32_t* wv = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float2 qf = unpack2<T>(qw[j]), df = unpack2<T>(dw[j]);
+                                    wk[j] = pack2<T>(kk_r * qf.x, kk_r * qf.y);
+                                    wv[j] = pack2<T>(pv_r * df.x, pv_r * df.y);
+                                }
+                                *reinterpret_cast<uint4*>(oslab + static_cast<size_t>(rl) * ld + E + 64 * w) = ok;
+                                *reinterpret_cast<uint4*>(oslab + static_cast<size_t>(rl) * ld + 2 * E + 64 * w) = ov;
+                            }
                         }
-                        *reinterpret_cast<uint4*>(o + E + 8 * c) = ok;
-                        *reinterpret_cast<uint4*>(o + 2 * E + 8 * c) = ov;
                     }
                 }
             }
@@ -365,28 +396,61 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                 const int nrows = min(BU_BM, (qt ? Qt : Ft) - row0);
                 const bool valid = row < nrows;
                 const size_t grow = qt ? static_cast<size_t>(p.B) * Ft + static_cast<size_t>(b) * Qt + row0 + row : static_cast<size_t>(b) * Ft + row;
-                const T* kown = qkv + (valid ? grow : 0) * ld + E + h * HD;
-                uint4 kreg[HD / 8];                                  // own-key row (query tiles): fetched under the tile's products
-                if (qt && valid) {
+                const int nv = nrows - quarter * 32;                 // rows of this warp's 32-row slab that exist
+                const bool kterm = qt && nv > 0;
+                // own-key rows (query tiles), coalesced (8 lanes per 128-byte row segment), fetched under the tile's products ...
+                uint4 kreg[8][KBOX];
+                if (kterm) {
+                    const T* kslab = qkv + (static_cast<size_t>(p.B) * Ft + static_cast<size_t>(b) * Qt + row0 + quarter * 32) * ld + E + h * HD + (lane & 7) * 8;
 #pragma unroll
-                    for (int c = 0; c < HD / 8; ++c) kreg[c] = __ldg(reinterpret_cast<const uint4*>(kown + 8 * c));
+                    for (int it = 0; it < 8; ++it) {
+                        const int rl = min(it * 4 + (lane >> 3), nv - 1);
+#pragma unroll
+                        for (int w = 0; w < KBOX; ++w) kreg[it][w] = __ldg(reinterpret_cast<const uint4*>(kslab + static_cast<size_t>(rl) * ld + 64 * w));
+                    }
+                }
+                // ... and parked in this warp's slab of the dQ staging tile, in the OUTPUT layout, once the previous bulk store has read
+                // it; after the __syncwarp each thread only touches its own row, which it overwrites with the finished dQ row
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp();
+                if (kterm) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int rl = it * 4 + (lane >> 3);
+#pragma unroll
+                        for (int w = 0; w < KBOX; ++w)
+                            sts_u128(sG + w * 16384 + (quarter * 32 + rl) * 128 + ((static_cast<uint32_t>(lane & 7) ^ static_cast<uint32_t>(rl & 7)) << 4), kreg[it][w]);
+                    }
+                    __syncwarp();
                 }
                 mbar_wait(p_full, g & 1u);                           // the softmax warps' per-row statistics are in shared memory
                 mbar_wait(o_full, g & 1u);
                 tc_fence_after();
                 const float dss = qt ? lds_f32(stat_base + static_cast<uint32_t>((g & 1u) * 512 + row * 4)) : 0.0f;
-                T* oq = dqkv + grow * ld + h * HD;
+                const uint32_t swz = static_cast<uint32_t>(row & 7);
 #pragma unroll
-                for (int c = 0; c < HD / 16; ++c) {
-                    uint32_t v[16];
-                    tmem_ld_32x16(taddr + c * 16, v);
+                for (int c64 = 0; c64 < HD / 64; ++c64) {
+                    uint32_t v[2][32];
+                    tmem_ld_32x32(taddr + c64 * 64, v[0]);
+                    tmem_ld_32x32(taddr + c64 * 64 + 32, v[1]);
                     tmem_ld_wait();
-                    if (valid) {
+                    if (c64 == HD / 64 - 1) {
+                        // dQ has left TMEM columns [0, hd): the next tile's S may be issued (the unit-end read-out below is of other columns)
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(dq_done);
+                    }
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        const int c = c64 * 4 + cc;
+                        const uint32_t a0 = sG + (c >> 2) * 16384 + row * 128 + ((static_cast<uint32_t>((c & 3) * 2) ^ swz) << 4);
+                        const uint32_t a1 = sG + (c >> 2) * 16384 + row * 128 + ((static_cast<uint32_t>((c & 3) * 2 + 1) ^ swz) << 4);
+                        uint4 k0 = make_uint4(0u, 0u, 0u, 0u), k1 = k0;
+                        if (kterm) { k0 = lds_u128(a0); k1 = lds_u128(a1); }
                         float f[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-                        if (qt) {
-                            const uint4 k0 = kreg[2 * c], k1 = kreg[2 * c + 1];
+                        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[cc >> 1][(cc & 1) * 16 + j]);
+                        if (kterm) {
                             const uint32_t kw[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
@@ -399,9 +463,17 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                         o0.z = pack2<T>(f[4] * p.qscale, f[5] * p.qscale); o0.w = pack2<T>(f[6] * p.qscale, f[7] * p.qscale);
                         o1.x = pack2<T>(f[8] * p.qscale, f[9] * p.qscale); o1.y = pack2<T>(f[10] * p.qscale, f[11] * p.qscale);
                         o1.z = pack2<T>(f[12] * p.qscale, f[13] * p.qscale); o1.w = pack2<T>(f[14] * p.qscale, f[15] * p.qscale);
-                        *reinterpret_cast<uint4*>(oq + 16 * c) = o0;
-                        *reinterpret_cast<uint4*>(oq + 16 * c + 8) = o1;
+                        sts_u128(a0, o0);
+                        sts_u128(a1, o1);
                     }
+                }
+                fence_proxy_async_smem();                            // staged dQ rows -> visible to the bulk store
+                __syncwarp();
+                if (lane == 0 && nv > 0) {
+#pragma unroll
+                    for (int j = 0; j < KBOX; ++j)
+                        tma_store_3d(qt ? &p.tmGq : &p.tmGf, sG + j * 16384 + quarter * 4096, h * HD + 64 * j, row0 + quarter * 32, b);
+                    tma_store_commit();
                 }
                 if (t == tiles - 1) {
                     // the unit's accumulators are complete: this thread's TMEM lane is feature key `row`
@@ -437,12 +509,11 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) {
-                    mbar_arrive(dq_done);
-                    if (t == tiles - 1) mbar_arrive(acc_empty);
-                }
+                if (lane == 0 && t == tiles - 1) mbar_arrive(acc_empty);
             }
         }
+        if (lane == 0) tma_store_wait<0>();
+        __syncwarp();
     }
 
     tc_fence_before();
@@ -455,7 +526,7 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
 
 template <int HD> size_t bwd_smem_for(int Fp) {
     const size_t kv = ((static_cast<size_t>(HD / 64) * Fp * 128) + 1023) & ~static_cast<size_t>(1023);
-    return 1024 + 2 * kv + 2 * static_cast<size_t>(HD / 64) * BU_BM * 128 + 2 * 2 * BU_BM * 128 + 1024 + 256;
+    return 1024 + 2 * kv + 3 * static_cast<size_t>(HD / 64) * BU_BM * 128 + 2 * 2 * BU_BM * 128 + 1024 + 256;
 }
 
 template <typename T, int HD>

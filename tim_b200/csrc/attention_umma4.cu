@@ -73,14 +73,6 @@ __device__ __forceinline__ bool mbar_test_all(uint32_t bar, uint32_t parity) {
     return __all_sync(0xffffffffu, done != 0);
 }
 
-// 16-byte read-only global load that stays where it is written (the compiler hoists plain loads above the epilogue arithmetic,
-// where the O tile already fills the register file)
-__device__ __forceinline__ uint4 ldg_nc_u128_pinned(const void* ptr) {
-    uint4 v;
-    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr) : "memory");
-    return v;
-}
-
 // role profile (debug hook, off unless tim_debug_role_prof gave a buffer): cycles one warp of each role spends in its waits
 struct ProfClock {
     bool on;

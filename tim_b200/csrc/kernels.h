@@ -270,6 +270,8 @@ struct AttnBwdUmmaParams {
     CUtensorMap tmQq;     // qkv query rows   (3E, Qt, B), box (64, 128, 1)
     CUtensorMap tmDf;     // dO feature rows  (E, Ft, B),  box (64, 128, 1)
     CUtensorMap tmDq;     // dO query rows    (E, Qt, B),  box (64, 128, 1)
+    CUtensorMap tmGf;     // dqkv feature rows (3E, Ft, B), box (64, 32, 1)  - dQ slabs of the epilogue warps (bulk stores)
+    CUtensorMap tmGq;     // dqkv query rows   (3E, Qt, B), box (64, 32, 1)
     const void* qkv; const void* dO; void* dqkv;
     int B, Ft, Qt, H;
     int Fp, tiles_q, num_units;       // filled by the launcher

@@ -152,6 +152,14 @@ __device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16])
         : "r"(taddr)
         : "memory");
 }
+// 32 lanes x 8 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------ clusters / CTA pairs (cta_group::2)
@@ -226,6 +234,13 @@ template <int N> __device__ __forceinline__ void tma_store_wait() {
 }
 
 // ------------------------------------------------------------------ shared-memory accesses by 32-bit shared address
+// 16-byte read-only global load that stays where it is written (asm volatile): the compiler neither hoists it into a region where the
+// register file is already full nor sinks it next to its first use, so a batch of them is in flight together
+__device__ __forceinline__ uint4 ldg_nc_u128_pinned(const void* ptr) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(ptr) : "memory");
+    return v;
+}
 __device__ __forceinline__ uint4 lds_u128(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");

@@ -138,11 +138,13 @@ int run_attention_bwd(tim_ctx* c, const T* qkv, const T* dO, T* dqkv, void* stat
         TIM_TRY(make_tmap_3d16(c, &ap.tmKV, qkv, ld, Ft, B, ld * 2, ld * 2 * Ft, Fp));
         TIM_TRY(make_tmap_3d16(c, &ap.tmQf, qkv, ld, Ft, B, ld * 2, ld * 2 * Ft, 128));
         TIM_TRY(make_tmap_3d16(c, &ap.tmDf, dO, E, Ft, B, E * 2, E * 2 * Ft, 128));
+        TIM_TRY(make_tmap_3d16(c, &ap.tmGf, dqkv, ld, Ft, B, ld * 2, ld * 2 * Ft, 32));
         if (Qt > 0) {
             TIM_TRY(make_tmap_3d16(c, &ap.tmQq, qkv + static_cast<size_t>(B) * Ft * ld, ld, Qt, B, ld * 2, ld * 2 * Qt, 128));
             TIM_TRY(make_tmap_3d16(c, &ap.tmDq, dO + static_cast<size_t>(B) * Ft * E, E, Qt, B, E * 2, E * 2 * Qt, 128));
+            TIM_TRY(make_tmap_3d16(c, &ap.tmGq, dqkv + static_cast<size_t>(B) * Ft * ld, ld, Qt, B, ld * 2, ld * 2 * Qt, 32));
         } else {
-            ap.tmQq = ap.tmQf; ap.tmDq = ap.tmDf;
+            ap.tmQq = ap.tmQf; ap.tmDq = ap.tmDf; ap.tmGq = ap.tmGf;
         }
         ap.qkv = qkv; ap.dO = dO; ap.dqkv = dqkv; ap.B = B; ap.Ft = Ft; ap.Qt = Qt; ap.H = c->H; ap.qscale = qscale; ap.drop = drop;
         if (drop.thr && 1ull * B * c->H * (Ft + Qt) * DROP_ATTN_KW > 0xffffffffull) return c->fail(TIM_ERR_INVALID, "attention dropout: batch too large for the 32-bit element index");
