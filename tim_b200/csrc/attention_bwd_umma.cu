@@ -19,7 +19,10 @@
 // No atomics, no P / dS in global memory; HBM traffic is the algorithmic 14 KB per token row (+ the own k / v rows once more).
 //
 // One persistent CTA per SM, 320 threads: warp 0 TMA producer, warp 1 MMA issuer (and TMEM allocation), warps 2-5 softmax
-// (TMEM lane quarter = warp % 4), warps 6-9 epilogue (dQ per tile; dK_f / dV_f per unit). Single-stage per tile (the 512 TMEM
+// (TMEM lane quarter = warp % 4; S, D and dS passes only), warps 6-9 epilogue: dQ per tile, dK_f / dV_f per unit, and ALL the own-row
+// work of query tiles - the dot products s_self / dP_self of tile g (handed to the softmax warps through shared memory + a_full, needed
+// only once the softmax over the feature keys is done) and, one tile late, the own-key / own-value gradients. The softmax warps are the
+// serial resource of a tile; the epilogue warps idled 72 % of the time (profiles/r02l). Single-stage per tile (the 512 TMEM
 // columns and 227 KB of shared memory are both full at hd = 128): tiles of one SM run back to back, overlap comes from the
 // roles (the loads of tile t+1 start as soon as the products of tile t have retired, under its epilogue).
 #include <cstdlib>
@@ -52,10 +55,10 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
     const uint32_t sKF = base, sVF = base + kv_pad;
     const uint32_t sQ = sVF + kv_pad, sDO = sQ + TILE_BYTES, sP = sDO + TILE_BYTES, sDS = sP + PS_BYTES;
     const uint32_t sG = sDS + PS_BYTES;                     // dQ staging tile [KBOX][128 rows][128 B], chunk-swizzled (bulk-store source)
-    const uint32_t stat_base = sG + TILE_BYTES;             // float [2][128]: own-key dS of query rows, double-buffered by tile parity
+    const uint32_t stat_base = sG + TILE_BYTES;             // float [2][128], one exchange slot per row: epilogue -> softmax (s_self, dP_self), then softmax -> epilogue (dS_self, p_self)
     const uint32_t bar_base = stat_base + 1024;
     const uint32_t kv_full = bar_base, kv_empty = bar_base + 8, q_full = bar_base + 16, s_full = bar_base + 24, p_full = bar_base + 32,
-                   o_full = bar_base + 40, dq_done = bar_base + 48, acc_empty = bar_base + 56, tmem_slot = bar_base + 64;
+                   o_full = bar_base + 40, dq_done = bar_base + 48, acc_empty = bar_base + 56, a_full = bar_base + 64, tmem_slot = bar_base + 72;
     volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
@@ -74,7 +77,7 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
     if (warp == 1) {
         if (lane == 0) {
             mbar_init(kv_full, 1); mbar_init(kv_empty, 1); mbar_init(q_full, 1); mbar_init(s_full, 1); mbar_init(p_full, 4);
-            mbar_init(o_full, 1); mbar_init(dq_done, 4); mbar_init(acc_empty, 4);
+            mbar_init(o_full, 1); mbar_init(dq_done, 4); mbar_init(acc_empty, 4); mbar_init(a_full, 4);
             fence_mbar_init();
         }
         __syncwarp();
@@ -189,8 +192,7 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
         const int row = quarter * 32 + lane;
         const uint32_t swz = static_cast<uint32_t>(row & 7);
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-        const float qln2 = kLn2u;
-        uint32_t g = 0;
+        uint32_t g = 0, aq = 0;                                      // aq: query tiles so far (phase of a_full)
         for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
             const int b = u / p.H, h = u - b * p.H;
             for (int t = 0; t < tiles; ++t, ++g) {
@@ -198,51 +200,10 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                 const int row0 = qt ? (t - 1) * BU_BM : 0;
                 const int nrows = min(BU_BM, (qt ? Qt : Ft) - row0);
                 const bool valid = row < nrows;
-                const size_t grow = qt ? static_cast<size_t>(p.B) * Ft + static_cast<size_t>(b) * Qt + row0 + row : static_cast<size_t>(b) * Ft + row;
-                // own key / value rows of the query rows: s_self = q . k_own, dP_self = dO . v_own. Coalesced: 8 lanes read one 128-byte
-                // segment of a row (4 rows per instruction), take their part of the dot product against the Q / dO tile in shared
-                // memory, the 8 partial sums are folded by shuffles and handed to the thread that owns the row
-                float sself = -INFINITY, dps = 0.0f;
-                const int nv = nrows - quarter * 32;                 // rows of this warp's 32-row slab that exist
-                const size_t slab_row = qt ? static_cast<size_t>(p.B) * Ft + static_cast<size_t>(b) * Qt + row0 + quarter * 32 : 0;
-                mbar_wait(q_full, g & 1u);                           // Q and dO tiles of this tile are in shared memory
-                if (qt && nv > 0) {
-                    const T* slab = qkv + slab_row * ld + h * HD + (lane & 7) * 8;
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int rl = it * 4 + (lane >> 3);
-                        const T* own = slab + static_cast<size_t>(min(rl, nv - 1)) * ld;
-                        float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll
-                        for (int w = 0; w < KBOX; ++w) {
-                            const uint4 kq = __ldg(reinterpret_cast<const uint4*>(own + E + 64 * w));
-                            const uint4 vq = __ldg(reinterpret_cast<const uint4*>(own + 2 * E + 64 * w));
-                            const uint32_t off = static_cast<uint32_t>(w) * 16384 + static_cast<uint32_t>(quarter * 32 + rl) * 128 +
-                                                 ((static_cast<uint32_t>(lane & 7) ^ static_cast<uint32_t>(rl & 7)) << 4);
-                            const uint4 qq = lds_u128(sQ + off), dd = lds_u128(sDO + off);
-                            const uint32_t kw[4] = {kq.x, kq.y, kq.z, kq.w}, vw[4] = {vq.x, vq.y, vq.z, vq.w};
-                            const uint32_t qw[4] = {qq.x, qq.y, qq.z, qq.w}, dw[4] = {dd.x, dd.y, dd.z, dd.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float2 kf = unpack2<T>(kw[j]), vf = unpack2<T>(vw[j]), qf = unpack2<T>(qw[j]), df = unpack2<T>(dw[j]);
-                                a0 = fmaf(qf.x, kf.x, fmaf(qf.y, kf.y, a0));
-                                a1 = fmaf(df.x, vf.x, fmaf(df.y, vf.y, a1));
-                            }
-                        }
-#pragma unroll
-                        for (int o = 1; o <= 4; o <<= 1) {
-                            a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-                            a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-                        }
-                        const float t0 = __shfl_sync(0xffffffffu, a0, (lane & 3) * 8), t1 = __shfl_sync(0xffffffffu, a1, (lane & 3) * 8);
-                        if (it == (lane >> 2)) { sself = t0; dps = t1; }
-                    }
-                    if (!valid) { sself = -INFINITY; dps = 0.0f; }
-                }
                 if (g > 0) mbar_wait(o_full, (g - 1) & 1u);          // P / dS tiles of the previous tile are no longer read by the tensor core
                 mbar_wait(s_full, g & 1u);
                 tc_fence_after();
-                // ---- P (whole row in registers), softmax statistics ----
+                // ---- P over the feature keys (whole row in registers): max, exp2, sum ----
                 float s[128];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
@@ -254,7 +215,7 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                     }
                 }
                 tmem_ld_wait();
-                float mx[4] = {sself, -INFINITY, -INFINITY, -INFINITY};
+                float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     if (c * 16 < Fp) {
@@ -267,21 +228,32 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                         for (int j = 0; j < 16; ++j) mx[j & 3] = fmaxf(mx[j & 3], s[c * 16 + j]);
                     }
                 }
-                const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+                const float mf = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
                 float ls[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     if (c * 16 < Fp) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const float e = ex2_approx(s[c * 16 + j] - m);
+                            const float e = ex2_approx(s[c * 16 + j] - mf);
                             s[c * 16 + j] = e;
                             ls[j & 3] += e;
                         }
                     }
                 }
+                // ---- the own key joins: s_self and dP_self come from the epilogue warps (computed under the products and the passes above) ----
+                float sself = -INFINITY, dps = 0.0f;
+                if (qt) {
+                    mbar_wait(a_full, aq & 1u);
+                    ++aq;
+                    sself = lds_f32(stat_base + static_cast<uint32_t>(row * 4));
+                    dps = lds_f32(stat_base + static_cast<uint32_t>(512 + row * 4));
+                }
+                const float m = fmaxf(mf, sself);
+                const float rf = ex2_approx(mf - m);                 // the feature-key terms were taken against mf
                 float ps = qt ? ex2_approx(sself - m) : 0.0f;
-                const float inv = valid ? 1.0f / ((ls[0] + ls[1]) + (ls[2] + ls[3]) + ps) : 0.0f;      // padded rows: P = dS = 0
+                const float inv = valid ? 1.0f / (((ls[0] + ls[1]) + (ls[2] + ls[3])) * rf + ps) : 0.0f;      // padded rows: P = dS = 0
+                const float invf = inv * rf;
                 ps *= inv;
                 // dropout of the probabilities in the forward (kernels.h: DropSite): the gradient w.r.t. P is dP o mask, dV_f sees the
                 // dropped P, D and dS use the un-dropped P
@@ -307,7 +279,7 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                         }
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            s[c * 16 + j] *= inv;
+                            s[c * 16 + j] *= invf;
                             dacc[j & 3] = fmaf(s[c * 16 + j], __uint_as_float(v[j]), dacc[j & 3]);
                         }
                     }
@@ -341,52 +313,72 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                         }
                     }
                 }
-                sts_f32(stat_base + static_cast<uint32_t>((g & 1u) * 512 + row * 4), dss);
+                // back through the same exchange slots (this thread read them above): dS_self and the dropped own probability, for the
+                // epilogue warps' dQ correction and own-key / own-value gradients
+                sts_f32(stat_base + static_cast<uint32_t>(row * 4), dss);
+                sts_f32(stat_base + static_cast<uint32_t>(512 + row * 4), ps * m_self);
                 tc_fence_before();
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(p_full);
-                // ---- own-key / own-value gradients of query rows: dk_own = ln2 dss q~, dv_own = p_self dO ----
-                // (q~ and dO rows come from global memory here, an L2 hit: the shared-memory tiles may already be receiving the next
-                // tile - the producer reloads them as soon as this tile's products retire, which this thread no longer waits for.)
-                // Coalesced like the dot products above; the per-row factors travel from the row's thread by shuffle.
-                if (qt && nv > 0) {
-                    const float kk = qln2 * dss, pv = ps * m_self;
-                    T* oslab = dqkv + slab_row * ld + h * HD + (lane & 7) * 8;
-                    const T* qslab = qkv + slab_row * ld + h * HD + (lane & 7) * 8;
-                    const T* dslab = dOp + slab_row * static_cast<size_t>(E) + h * HD + (lane & 7) * 8;
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 6..9): own-row work, dQ per tile, dK_f / dV_f per unit =====================
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t swz = static_cast<uint32_t>(row & 7);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        // own-key / own-value gradients of the PREVIOUS query tile (dk_own = ln2 dS_self q~, dv_own = p_self dO): deferred by one tile
+        // so that the dot products of the next tile, which its softmax is waiting for, go first. Coalesced (8 lanes per 128-byte row
+        // segment); q~ and dO rows come from global memory (an L2 hit), the per-row factors from the row's thread by shuffle.
+        bool pend = false;
+        size_t pend_slab = 0;
+        int pend_nv = 0, pend_h = 0;
+        float pend_kk = 0.0f, pend_pv = 0.0f;
+        auto own_grads = [&]() {
+            if (!pend) return;
+            pend = false;
+            T* oslab = dqkv + pend_slab * ld + pend_h * HD + (lane & 7) * 8;
+            const T* qslab = qkv + pend_slab * ld + pend_h * HD + (lane & 7) * 8;
+            const T* dslab = dOp + pend_slab * static_cast<size_t>(E) + pend_h * HD + (lane & 7) * 8;
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int rl = it * 4 + (lane >> 3);
-                        const float kk_r = __shfl_sync(0xffffffffu, kk, rl), pv_r = __shfl_sync(0xffffffffu, pv, rl);
-                        if (rl < nv) {
+            for (int half = 0; half < 2; ++half) {
+                uint4 qown[4][KBOX], down[4][KBOX];
 #pragma unroll
-                            for (int w = 0; w < KBOX; ++w) {
-                                const uint4 qq = __ldg(reinterpret_cast<const uint4*>(qslab + static_cast<size_t>(rl) * ld + 64 * w));
-                                const uint4 dd = __ldg(reinterpret_cast<const uint4*>(dslab + static_cast<size_t>(rl) * E + 64 * w));
-                                const uint32_t qw[4] = {qq.x, qq.y, qq.z, qq.w}, dw[4] = {dd.x, dd.y, dd.z, dd.w};
-                                uint4 ok, ov;
-                                uint32_t* wk = reinterpret_cast<uint32_t*>(&ok);
-                                uint32_t* wv = reinterpret_cast<uint32_t*>(&ov);
+                for (int i = 0; i < 4; ++i) {
+                    const int rl = min((half * 4 + i) * 4 + (lane >> 3), pend_nv - 1);
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float2 qf = unpack2<T>(qw[j]), df = unpack2<T>(dw[j]);
-                                    wk[j] = pack2<T>(kk_r * qf.x, kk_r * qf.y);
-                                    wv[j] = pack2<T>(pv_r * df.x, pv_r * df.y);
-                                }
-                                *reinterpret_cast<uint4*>(oslab + static_cast<size_t>(rl) * ld + E + 64 * w) = ok;
-                                *reinterpret_cast<uint4*>(oslab + static_cast<size_t>(rl) * ld + 2 * E + 64 * w) = ov;
+                    for (int w = 0; w < KBOX; ++w) {
+                        qown[i][w] = ldg_nc_u128_pinned(qslab + static_cast<size_t>(rl) * ld + 64 * w);
+                        down[i][w] = ldg_nc_u128_pinned(dslab + static_cast<size_t>(rl) * E + 64 * w);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int rl = (half * 4 + i) * 4 + (lane >> 3);
+                    const float kk_r = __shfl_sync(0xffffffffu, pend_kk, rl), pv_r = __shfl_sync(0xffffffffu, pend_pv, rl);
+                    if (rl < pend_nv) {
+#pragma unroll
+                        for (int w = 0; w < KBOX; ++w) {
+                            const uint4 qq = qown[i][w], dd = down[i][w];
+                            const uint32_t qw[4] = {qq.x, qq.y, qq.z, qq.w}, dw[4] = {dd.x, dd.y, dd.z, dd.w};
+                            uint4 ok, ov;
+                            uint32_t* wk = reinterpret_cast<uint32_t*>(&ok);
+                            uint32_t* wv = reinterpret_cast<uint32_t*>(&ov);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 qf = unpack2<T>(qw[j]), df = unpack2<T>(dw[j]);
+                                wk[j] = pack2<T>(kk_r * qf.x, kk_r * qf.y);
+                                wv[j] = pack2<T>(pv_r * df.x, pv_r * df.y);
                             }
+                            *reinterpret_cast<uint4*>(oslab + static_cast<size_t>(rl) * ld + E + 64 * w) = ok;
+                            *reinterpret_cast<uint4*>(oslab + static_cast<size_t>(rl) * ld + 2 * E + 64 * w) = ov;
                         }
                     }
                 }
             }
-        }
-    } else {
-        // ===================== epilogue (warps 6..9): dQ per tile, dK_f / dV_f per unit =====================
-        const int quarter = warp & 3;
-        const int row = quarter * 32 + lane;
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        };
         uint32_t g = 0;
         for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
             const int b = u / p.H, h = u - b * p.H;
@@ -395,39 +387,77 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                 const int row0 = qt ? (t - 1) * BU_BM : 0;
                 const int nrows = min(BU_BM, (qt ? Qt : Ft) - row0);
                 const bool valid = row < nrows;
-                const size_t grow = qt ? static_cast<size_t>(p.B) * Ft + static_cast<size_t>(b) * Qt + row0 + row : static_cast<size_t>(b) * Ft + row;
                 const int nv = nrows - quarter * 32;                 // rows of this warp's 32-row slab that exist
                 const bool kterm = qt && nv > 0;
-                // own-key rows (query tiles), coalesced (8 lanes per 128-byte row segment), fetched under the tile's products ...
-                uint4 kreg[8][KBOX];
-                if (kterm) {
-                    const T* kslab = qkv + (static_cast<size_t>(p.B) * Ft + static_cast<size_t>(b) * Qt + row0 + quarter * 32) * ld + E + h * HD + (lane & 7) * 8;
-#pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int rl = min(it * 4 + (lane >> 3), nv - 1);
-#pragma unroll
-                        for (int w = 0; w < KBOX; ++w) kreg[it][w] = __ldg(reinterpret_cast<const uint4*>(kslab + static_cast<size_t>(rl) * ld + 64 * w));
-                    }
-                }
-                // ... and parked in this warp's slab of the dQ staging tile, in the OUTPUT layout, once the previous bulk store has read
-                // it; after the __syncwarp each thread only touches its own row, which it overwrites with the finished dQ row
+                const size_t slab_row = qt ? static_cast<size_t>(p.B) * Ft + static_cast<size_t>(b) * Qt + row0 + quarter * 32 : 0;
+                // this warp's slab of the dQ staging tile is free once its previous bulk store has read it
                 if (lane == 0) tma_store_wait_read<0>();
                 __syncwarp();
-                if (kterm) {
+                if (qt) {
+                    // ---- s_self = q . k_own, dP_self = dO . v_own for the tile's rows. Coalesced: 8 lanes read one 128-byte segment of a
+                    // row (4 rows per instruction) and take their part of the dot product against the Q / dO tile in shared memory; the 8
+                    // partial sums are folded by shuffles and handed to the lane that owns the row. Two batches of 4 row groups, each
+                    // in flight together; the own-key rows are parked in the dQ slab on the way (output layout, see below) ----
+                    float sself = -INFINITY, dps = 0.0f;
+                    if (nv > 0) {
+                        const T* slab = qkv + slab_row * ld + h * HD + (lane & 7) * 8;
 #pragma unroll
-                    for (int it = 0; it < 8; ++it) {
-                        const int rl = it * 4 + (lane >> 3);
+                        for (int half = 0; half < 2; ++half) {
+                            uint4 kown[4][KBOX], vown[4][KBOX];
 #pragma unroll
-                        for (int w = 0; w < KBOX; ++w)
-                            sts_u128(sG + w * 16384 + (quarter * 32 + rl) * 128 + ((static_cast<uint32_t>(lane & 7) ^ static_cast<uint32_t>(rl & 7)) << 4), kreg[it][w]);
+                            for (int i = 0; i < 4; ++i) {
+                                const T* own = slab + static_cast<size_t>(min((half * 4 + i) * 4 + (lane >> 3), nv - 1)) * ld;
+#pragma unroll
+                                for (int w = 0; w < KBOX; ++w) {
+                                    kown[i][w] = ldg_nc_u128_pinned(own + E + 64 * w);
+                                    vown[i][w] = ldg_nc_u128_pinned(own + 2 * E + 64 * w);
+                                }
+                            }
+                            if (half == 0) mbar_wait(q_full, g & 1u);        // Q and dO tiles of this tile are in shared memory
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int it = half * 4 + i;
+                                const int rl = it * 4 + (lane >> 3);
+                                float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+                                for (int w = 0; w < KBOX; ++w) {
+                                    const uint4 kq = kown[i][w], vq = vown[i][w];
+                                    const uint32_t off = static_cast<uint32_t>(w) * 16384 + static_cast<uint32_t>(quarter * 32 + rl) * 128 +
+                                                         ((static_cast<uint32_t>(lane & 7) ^ static_cast<uint32_t>(rl & 7)) << 4);
+                                    const uint4 qq = lds_u128(sQ + off), dd = lds_u128(sDO + off);
+                                    sts_u128(sG + off, kq);          // parked for the dQ correction
+                                    const uint32_t kw[4] = {kq.x, kq.y, kq.z, kq.w}, vw[4] = {vq.x, vq.y, vq.z, vq.w};
+                                    const uint32_t qw[4] = {qq.x, qq.y, qq.z, qq.w}, dw[4] = {dd.x, dd.y, dd.z, dd.w};
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) {
+                                        const float2 kf = unpack2<T>(kw[j]), vf = unpack2<T>(vw[j]), qf = unpack2<T>(qw[j]), df = unpack2<T>(dw[j]);
+                                        a0 = fmaf(qf.x, kf.x, fmaf(qf.y, kf.y, a0));
+                                        a1 = fmaf(df.x, vf.x, fmaf(df.y, vf.y, a1));
+                                    }
+                                }
+#pragma unroll
+                                for (int o = 1; o <= 4; o <<= 1) {
+                                    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                                    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                                }
+                                const float t0 = __shfl_sync(0xffffffffu, a0, (lane & 3) * 8), t1 = __shfl_sync(0xffffffffu, a1, (lane & 3) * 8);
+                                if (it == (lane >> 2)) { sself = t0; dps = t1; }
+                            }
+                        }
+                        if (!valid) { sself = -INFINITY; dps = 0.0f; }
                     }
+                    sts_f32(stat_base + static_cast<uint32_t>(row * 4), sself);
+                    sts_f32(stat_base + static_cast<uint32_t>(512 + row * 4), dps);
                     __syncwarp();
+                    if (lane == 0) mbar_arrive(a_full);
                 }
-                mbar_wait(p_full, g & 1u);                           // the softmax warps' per-row statistics are in shared memory
+                own_grads();                                         // of the previous query tile, under this tile's softmax
+                mbar_wait(p_full, g & 1u);                           // the softmax warps' per-row results are in shared memory
+                const float dss = qt ? lds_f32(stat_base + static_cast<uint32_t>(row * 4)) : 0.0f;
+                const float pself = qt ? lds_f32(stat_base + static_cast<uint32_t>(512 + row * 4)) : 0.0f;
                 mbar_wait(o_full, g & 1u);
                 tc_fence_after();
-                const float dss = qt ? lds_f32(stat_base + static_cast<uint32_t>((g & 1u) * 512 + row * 4)) : 0.0f;
-                const uint32_t swz = static_cast<uint32_t>(row & 7);
+                // dQ: each thread finishes its own row in place in the slab (dQ + dS_self k_own, scaled), a bulk store takes the slab
 #pragma unroll
                 for (int c64 = 0; c64 < HD / 64; ++c64) {
                     uint32_t v[2][32];
@@ -475,6 +505,10 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                         tma_store_3d(qt ? &p.tmGq : &p.tmGf, sG + j * 16384 + quarter * 4096, h * HD + 64 * j, row0 + quarter * 32, b);
                     tma_store_commit();
                 }
+                if (kterm) {
+                    pend = true; pend_slab = slab_row; pend_nv = nv; pend_h = h;
+                    pend_kk = kLn2u * dss; pend_pv = pself;
+                }
                 if (t == tiles - 1) {
                     // the unit's accumulators are complete: this thread's TMEM lane is feature key `row`
                     const bool kvalid = row < Ft;
@@ -512,6 +546,7 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                 if (lane == 0 && t == tiles - 1) mbar_arrive(acc_empty);
             }
         }
+        own_grads();
         if (lane == 0) tma_store_wait<0>();
         __syncwarp();
     }
