@@ -379,6 +379,56 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                 }
             }
         };
+        // s_self = q . k_own, dP_self = dO . v_own of a query tile's rows, ENTIRELY from global memory (the q / dO rows are an L2 hit: the
+        // producer prefetched them), so that it can run one tile ahead, under the softmax of the tile before. Coalesced: 8 lanes read
+        // one 128-byte segment of a row (4 rows per instruction) and take their part of the dot products; the 8 partial sums are folded
+        // by shuffles and handed to the lane that owns the row. Four batches of 2 row groups, each batch in flight together.
+        auto own_dots = [&](size_t slab_row, int h, int nv, float& sself, float& dps) {
+            sself = -INFINITY; dps = 0.0f;
+            if (nv <= 0) return;
+            const T* qs = qkv + slab_row * ld + h * HD + (lane & 7) * 8;
+            const T* ds = dOp + slab_row * static_cast<size_t>(E) + h * HD + (lane & 7) * 8;
+#pragma unroll
+            for (int bt = 0; bt < 4; ++bt) {
+                uint4 kown[2][KBOX], vown[2][KBOX], qown[2][KBOX], down[2][KBOX];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const size_t r = static_cast<size_t>(min((bt * 2 + i) * 4 + (lane >> 3), nv - 1));
+#pragma unroll
+                    for (int w = 0; w < KBOX; ++w) {
+                        qown[i][w] = ldg_nc_u128_pinned(qs + r * ld + 64 * w);
+                        kown[i][w] = ldg_nc_u128_pinned(qs + r * ld + E + 64 * w);
+                        vown[i][w] = ldg_nc_u128_pinned(qs + r * ld + 2 * E + 64 * w);
+                        down[i][w] = ldg_nc_u128_pinned(ds + r * E + 64 * w);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int it = bt * 2 + i;
+                    float a0 = 0.0f, a1 = 0.0f;
+#pragma unroll
+                    for (int w = 0; w < KBOX; ++w) {
+                        const uint4 kq = kown[i][w], vq = vown[i][w], qq = qown[i][w], dd = down[i][w];
+                        const uint32_t kw[4] = {kq.x, kq.y, kq.z, kq.w}, vw[4] = {vq.x, vq.y, vq.z, vq.w};
+                        const uint32_t qw[4] = {qq.x, qq.y, qq.z, qq.w}, dw[4] = {dd.x, dd.y, dd.z, dd.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 kf = unpack2<T>(kw[j]), vf = unpack2<T>(vw[j]), qf = unpack2<T>(qw[j]), df = unpack2<T>(dw[j]);
+                            a0 = fmaf(qf.x, kf.x, fmaf(qf.y, kf.y, a0));
+                            a1 = fmaf(df.x, vf.x, fmaf(df.y, vf.y, a1));
+                        }
+                    }
+#pragma unroll
+                    for (int o = 1; o <= 4; o <<= 1) {
+                        a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                        a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                    }
+                    const float t0 = __shfl_sync(0xffffffffu, a0, (lane & 3) * 8), t1 = __shfl_sync(0xffffffffu, a1, (lane & 3) * 8);
+                    if (it == (lane >> 2)) { sself = t0; dps = t1; }
+                }
+            }
+            if (lane >= nv) { sself = -INFINITY; dps = 0.0f; }
+        };
         uint32_t g = 0;
         for (int u = blockIdx.x; u < p.num_units; u += gridDim.x) {
             const int b = u / p.H, h = u - b * p.H;
@@ -386,75 +436,53 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                 const bool qt = t > 0;
                 const int row0 = qt ? (t - 1) * BU_BM : 0;
                 const int nrows = min(BU_BM, (qt ? Qt : Ft) - row0);
-                const bool valid = row < nrows;
                 const int nv = nrows - quarter * 32;                 // rows of this warp's 32-row slab that exist
                 const bool kterm = qt && nv > 0;
                 const size_t slab_row = qt ? static_cast<size_t>(p.B) * Ft + static_cast<size_t>(b) * Qt + row0 + quarter * 32 : 0;
-                // this warp's slab of the dQ staging tile is free once its previous bulk store has read it
+                // own-key rows (query tiles), coalesced, parked in this warp's slab of the dQ staging tile in the OUTPUT layout once the
+                // previous bulk store has read it; after the __syncwarp each thread only touches its own row, which it overwrites
+                // with the finished dQ row
+                uint4 kreg[8][KBOX];
+                if (kterm) {
+                    const T* kslab = qkv + slab_row * ld + E + h * HD + (lane & 7) * 8;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int rl = min(it * 4 + (lane >> 3), nv - 1);
+#pragma unroll
+                        for (int w = 0; w < KBOX; ++w) kreg[it][w] = ldg_nc_u128_pinned(kslab + static_cast<size_t>(rl) * ld + 64 * w);
+                    }
+                }
                 if (lane == 0) tma_store_wait_read<0>();
                 __syncwarp();
-                if (qt) {
-                    // ---- s_self = q . k_own, dP_self = dO . v_own for the tile's rows. Coalesced: 8 lanes read one 128-byte segment of a
-                    // row (4 rows per instruction) and take their part of the dot product against the Q / dO tile in shared memory; the 8
-                    // partial sums are folded by shuffles and handed to the lane that owns the row. Two batches of 4 row groups, each
-                    // in flight together; the own-key rows are parked in the dQ slab on the way (output layout, see below) ----
-                    float sself = -INFINITY, dps = 0.0f;
-                    if (nv > 0) {
-                        const T* slab = qkv + slab_row * ld + h * HD + (lane & 7) * 8;
+                if (kterm) {
 #pragma unroll
-                        for (int half = 0; half < 2; ++half) {
-                            uint4 kown[4][KBOX], vown[4][KBOX];
+                    for (int it = 0; it < 8; ++it) {
+                        const int rl = it * 4 + (lane >> 3);
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const T* own = slab + static_cast<size_t>(min((half * 4 + i) * 4 + (lane >> 3), nv - 1)) * ld;
-#pragma unroll
-                                for (int w = 0; w < KBOX; ++w) {
-                                    kown[i][w] = ldg_nc_u128_pinned(own + E + 64 * w);
-                                    vown[i][w] = ldg_nc_u128_pinned(own + 2 * E + 64 * w);
-                                }
-                            }
-                            if (half == 0) mbar_wait(q_full, g & 1u);        // Q and dO tiles of this tile are in shared memory
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const int it = half * 4 + i;
-                                const int rl = it * 4 + (lane >> 3);
-                                float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll
-                                for (int w = 0; w < KBOX; ++w) {
-                                    const uint4 kq = kown[i][w], vq = vown[i][w];
-                                    const uint32_t off = static_cast<uint32_t>(w) * 16384 + static_cast<uint32_t>(quarter * 32 + rl) * 128 +
-                                                         ((static_cast<uint32_t>(lane & 7) ^ static_cast<uint32_t>(rl & 7)) << 4);
-                                    const uint4 qq = lds_u128(sQ + off), dd = lds_u128(sDO + off);
-                                    sts_u128(sG + off, kq);          // parked for the dQ correction
-                                    const uint32_t kw[4] = {kq.x, kq.y, kq.z, kq.w}, vw[4] = {vq.x, vq.y, vq.z, vq.w};
-                                    const uint32_t qw[4] = {qq.x, qq.y, qq.z, qq.w}, dw[4] = {dd.x, dd.y, dd.z, dd.w};
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j) {
-                                        const float2 kf = unpack2<T>(kw[j]), vf = unpack2<T>(vw[j]), qf = unpack2<T>(qw[j]), df = unpack2<T>(dw[j]);
-                                        a0 = fmaf(qf.x, kf.x, fmaf(qf.y, kf.y, a0));
-                                        a1 = fmaf(df.x, vf.x, fmaf(df.y, vf.y, a1));
-                                    }
-                                }
-#pragma unroll
-                                for (int o = 1; o <= 4; o <<= 1) {
-                                    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-                                    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-                                }
-                                const float t0 = __shfl_sync(0xffffffffu, a0, (lane & 3) * 8), t1 = __shfl_sync(0xffffffffu, a1, (lane & 3) * 8);
-                                if (it == (lane >> 2)) { sself = t0; dps = t1; }
-                            }
-                        }
-                        if (!valid) { sself = -INFINITY; dps = 0.0f; }
+                        for (int w = 0; w < KBOX; ++w)
+                            sts_u128(sG + w * 16384 + (quarter * 32 + rl) * 128 + ((static_cast<uint32_t>(lane & 7) ^ static_cast<uint32_t>(rl & 7)) << 4), kreg[it][w]);
                     }
-                    sts_f32(stat_base + static_cast<uint32_t>(row * 4), sself);
-                    sts_f32(stat_base + static_cast<uint32_t>(512 + row * 4), dps);
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(a_full);
                 }
                 own_grads();                                         // of the previous query tile, under this tile's softmax
+                // the dot products of the NEXT tile (same unit: a query tile), also under this tile's softmax; published below
+                const bool next_q = t + 1 < tiles;
+                float n_sself = -INFINITY, n_dps = 0.0f;
+                if (next_q) {
+                    const int n_row0 = t * BU_BM;
+                    const int n_nv = min(BU_BM, Qt - n_row0) - quarter * 32;
+                    own_dots(static_cast<size_t>(p.B) * Ft + static_cast<size_t>(b) * Qt + n_row0 + quarter * 32, h, n_nv, n_sself, n_dps);
+                }
                 mbar_wait(p_full, g & 1u);                           // the softmax warps' per-row results are in shared memory
                 const float dss = qt ? lds_f32(stat_base + static_cast<uint32_t>(row * 4)) : 0.0f;
                 const float pself = qt ? lds_f32(stat_base + static_cast<uint32_t>(512 + row * 4)) : 0.0f;
+                if (next_q) {
+                    // the exchange slots are free again (this thread has just read them): the next tile's dot products go in
+                    sts_f32(stat_base + static_cast<uint32_t>(row * 4), n_sself);
+                    sts_f32(stat_base + static_cast<uint32_t>(512 + row * 4), n_dps);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(a_full);
+                }
                 mbar_wait(o_full, g & 1u);
                 tc_fence_after();
                 // dQ: each thread finishes its own row in place in the slab (dQ + dS_self k_own, scaled), a bulk store takes the slab
@@ -510,34 +538,36 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                     pend_kk = kLn2u * dss; pend_pv = pself;
                 }
                 if (t == tiles - 1) {
-                    // the unit's accumulators are complete: this thread's TMEM lane is feature key `row`
-                    const bool kvalid = row < Ft;
-                    T* ok = dqkv + (static_cast<size_t>(b) * Ft + (kvalid ? row : 0)) * ld + E + h * HD;
+                    // the unit's accumulators are complete: this thread's TMEM lane is feature key `row`. dK_f, then dV_f, through the
+                    // slab (each thread its own row) and a bulk store into the feature rows' k / v columns
+                    const int nk = Ft - quarter * 32;                // feature keys of this warp's lane quarter that exist
 #pragma unroll
-                    for (int c = 0; c < HD / 16; ++c) {
-                        uint32_t vv[16], vk[16];
-                        tmem_ld_32x16(taddr + 256 + c * 16, vv);
-                        tmem_ld_32x16(taddr + 384 + c * 16, vk);
-                        tmem_ld_wait();
-                        if (kvalid) {
-                            uint4 a0, a1, b0, b1;
-                            uint32_t* w;
-                            w = reinterpret_cast<uint32_t*>(&a0);
+                    for (int which = 0; which < 2; ++which) {        // 0: dK_f (TMEM [384, 384 + hd), x ln 2), 1: dV_f (TMEM [256, 256 + hd))
+                        const float sc = which == 0 ? kLn2u : 1.0f;
+                        if (lane == 0) tma_store_wait_read<0>();
+                        __syncwarp();
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) w[j] = pack2<T>(kLn2u * __uint_as_float(vk[2 * j]), kLn2u * __uint_as_float(vk[2 * j + 1]));
-                            w = reinterpret_cast<uint32_t*>(&a1);
+                        for (int c64 = 0; c64 < HD / 64; ++c64) {
+                            uint32_t v[2][32];
+                            tmem_ld_32x32(taddr + (which == 0 ? 384 : 256) + c64 * 64, v[0]);
+                            tmem_ld_32x32(taddr + (which == 0 ? 384 : 256) + c64 * 64 + 32, v[1]);
+                            tmem_ld_wait();
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) w[j] = pack2<T>(kLn2u * __uint_as_float(vk[8 + 2 * j]), kLn2u * __uint_as_float(vk[8 + 2 * j + 1]));
-                            w = reinterpret_cast<uint32_t*>(&b0);
+                            for (int c8 = 0; c8 < 8; ++c8) {
+                                const uint32_t* f = &v[c8 >> 2][(c8 & 3) * 8];
+                                uint4 o;
+                                o.x = pack2<T>(sc * __uint_as_float(f[0]), sc * __uint_as_float(f[1])); o.y = pack2<T>(sc * __uint_as_float(f[2]), sc * __uint_as_float(f[3]));
+                                o.z = pack2<T>(sc * __uint_as_float(f[4]), sc * __uint_as_float(f[5])); o.w = pack2<T>(sc * __uint_as_float(f[6]), sc * __uint_as_float(f[7]));
+                                sts_u128(sG + c64 * 16384 + row * 128 + ((static_cast<uint32_t>(c8) ^ swz) << 4), o);
+                            }
+                        }
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0 && nk > 0) {
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) w[j] = pack2<T>(__uint_as_float(vv[2 * j]), __uint_as_float(vv[2 * j + 1]));
-                            w = reinterpret_cast<uint32_t*>(&b1);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) w[j] = pack2<T>(__uint_as_float(vv[8 + 2 * j]), __uint_as_float(vv[8 + 2 * j + 1]));
-                            *reinterpret_cast<uint4*>(ok + 16 * c) = a0;
-                            *reinterpret_cast<uint4*>(ok + 16 * c + 8) = a1;
-                            *reinterpret_cast<uint4*>(ok + E + 16 * c) = b0;
-                            *reinterpret_cast<uint4*>(ok + E + 16 * c + 8) = b1;
+                            for (int j = 0; j < KBOX; ++j)
+                                tma_store_3d(&p.tmGf, sG + j * 16384 + quarter * 4096, (which == 0 ? E : 2 * E) + h * HD + 64 * j, quarter * 32, b);
+                            tma_store_commit();
                         }
                     }
                 }
