@@ -97,7 +97,9 @@ int tim_encoder_fwd(tim_ctx* ctx, const float* vis, const float* aud, const floa
 /* The same forward with the input windows gathered ON THE DEVICE from feature banks resident in HBM (SURVEY.md section 8f row 4;
  * the reference's loader gathers feats[video][feat_indices, aug_indices] on the host, datasets/sliding_window.py:356-375, and
  * ships [B, F, D] fp32 over PCIe every step). vis_rows / aud_rows [B * num_feats] (device, int64) give the bank row of every
- * feature token, clip-major; a row outside the bank reads as zeros. Banks may be fp32 or 16-bit. */
+ * feature token, clip-major. Banks may be fp32 or 16-bit. A row index outside its bank (the reference's host-side indexing raises
+ * IndexError) reads as zeros and is COUNTED: tim_index_check() blocks for the verdict on the last indexed forward (TIM_ERR_INVALID and a
+ * message with the count), and any later indexed forward on the context fails if an earlier one saw bad indices. */
 typedef struct {
     const void* vis_bank;           /* [vis_bank_rows, vis_dim], device; NULL if the modality is absent */
     const void* aud_bank;           /* [aud_bank_rows, aud_dim] */
@@ -108,6 +110,7 @@ typedef struct {
 } tim_feature_bank;
 int tim_encoder_fwd_indexed(tim_ctx* ctx, const tim_feature_bank* bank, const float* time_enc, int B, int T, int Qv, int Qa,
                             const tim_outputs* outs, void* stream);
+int tim_index_check(tim_ctx* ctx);
 
 /* End-to-end call on HOST buffers (pinned or pageable): time_mlp + encoder with the H2D input copies and D2H
  * result copies inside the call, chunked over clips and overlapped on three internal streams. Blocks until the

@@ -445,7 +445,7 @@ def test_indexed_encoder_equals_dense(lib, dt, bank_dt):
     vrows = torch.randint(0, 37, (B, F), generator=g).to(dev)
     arows = torch.randint(0, 29, (B, F), generator=g).to(dev)
     vrows[0, 0] = vrows[0, 1]                  # a repeated row
-    arows[1, 2] = 29                           # one past the end: reads as zeros
+    arows[1, 2] = 29                           # one past the end: reads as zeros - and is reported (below)
     vis = vbank.float()[vrows]
     aud = torch.cat([abank.float(), torch.zeros(1, cfg.audio_input_dim, device=dev)])[arows]
     times = torch.from_numpy(synth_inputs(cfg, B, Qv, Qa, 8)["times"]).to(dev)
@@ -459,6 +459,23 @@ def test_indexed_encoder_equals_dense(lib, dt, bank_dt):
         assert (v is None) == (idx[k] is None)
         if v is not None:
             assert torch.equal(v, idx[k]), k
+    # the reference's host-side indexing raises on an out-of-range row; here the verdict is asynchronous: index_check() blocks for it
+    from tim_b200._lib import TimError
+    with pytest.raises(TimError, match="out of range"):
+        eng.index_check()
+    eng.index_check()                           # reported once, then cleared
+    arows[1, 2] = 28
+    eng.encoder_indexed(vbank, vrows, abank, arows, te, Qv, Qa)
+    eng.index_check()                           # all rows inside their banks
+    # ... and a forward that is never checked makes the NEXT indexed forward fail
+    vrows[2, 1] = -1
+    eng.encoder_indexed(vbank, vrows, abank, arows, te, Qv, Qa)
+    torch.cuda.synchronize()
+    vrows[2, 1] = 0
+    with pytest.raises(TimError, match="earlier call"):
+        eng.encoder_indexed(vbank, vrows, abank, arows, te, Qv, Qa)
+    eng.encoder_indexed(vbank, vrows, abank, arows, te, Qv, Qa)
+    eng.index_check()
     eng.close()
 
 

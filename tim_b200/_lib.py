@@ -79,6 +79,7 @@ SYMBOLS = {
                                       C.POINTER(tim_outputs), C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_uint64),
                                       C.POINTER(C.c_uint64)]),
     "tim_fold_check": (C.c_int, [C.c_void_p]),
+    "tim_index_check": (C.c_int, [C.c_void_p]),
     "tim_train_enable": (C.c_int, [C.c_void_p]),
     "tim_bind_grad": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p]),
     "tim_set_dropout": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_uint64]),

@@ -109,6 +109,10 @@ struct tim_ctx {
     bool fold_tripped = false;
     bool last_folded = false;           // the most recent encoder forward took the folded flow
     cudaEvent_t fold_event = nullptr;   // recorded behind the alarm's D2H copy of that forward (tim_fold_check waits on it)
+    // out-of-range rows of tim_encoder_fwd_indexed: counted on the device, copied to pinned host memory behind the forward
+    int* idx_alarm_dev = nullptr;
+    volatile int* idx_alarm_host = nullptr;
+    cudaEvent_t idx_event = nullptr;
     std::vector<cudaEvent_t> host_events;   // reused by tim_forward_host_ex (three per chunk) + one for the caller's stream
 
     // optional live profiling: CUDA-event pairs around every launch, accumulated per kernel class
@@ -701,7 +705,7 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
         if (fb) {
             if (!fb->vis_bank || !fb->vis_rows) return c->fail(TIM_ERR_INVALID, "visual feature bank / row indices are NULL");
             LAUNCH(c, launch_gather_rows<T>(fb->vis_bank, fb->bank_dtype, fb->vis_bank_rows, reinterpret_cast<const long long*>(fb->vis_rows), vis16, Mv,
-                                            g.vis_dim, s));
+                                            g.vis_dim, s, c->idx_alarm_dev));
             A = vis16;
         } else {
             if (!vis) return c->fail(TIM_ERR_INVALID, "visual input is NULL");
@@ -715,7 +719,7 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
         if (fb) {
             if (!fb->aud_bank || !fb->aud_rows) return c->fail(TIM_ERR_INVALID, "audio feature bank / row indices are NULL");
             LAUNCH(c, launch_gather_rows<T>(fb->aud_bank, fb->bank_dtype, fb->aud_bank_rows, reinterpret_cast<const long long*>(fb->aud_rows), aud16, Ma,
-                                            g.aud_dim, s));
+                                            g.aud_dim, s, c->idx_alarm_dev));
             A = aud16;
         } else {
             if (!aud) return c->fail(TIM_ERR_INVALID, "audio input is NULL");
@@ -1011,6 +1015,8 @@ void tim_destroy(tim_ctx* c) {
     for (void* p : c->allocs) cudaFree(p);
     if (c->ws) cudaFree(c->ws);
     if (c->fold_alarm_host) cudaFreeHost(const_cast<int*>(c->fold_alarm_host));
+    if (c->idx_alarm_host) cudaFreeHost(const_cast<int*>(c->idx_alarm_host));
+    if (c->idx_event) cudaEventDestroy(c->idx_event);
     if (c->fold_event) cudaEventDestroy(c->fold_event);
     for (cudaEvent_t e : c->host_events) cudaEventDestroy(e);
     if (c->train) {
@@ -1114,13 +1120,48 @@ int tim_encoder_fwd_indexed(tim_ctx* c, const tim_feature_bank* fb, const float*
     if (fb->bank_dtype < TIM_FP32 || fb->bank_dtype > TIM_FP16) return c->fail(TIM_ERR_INVALID, "tim_encoder_fwd_indexed: bad bank_dtype");
     TIM_TRY(check_ready(c));
     CU_OK(c, cudaSetDevice(c->device));
+    // a row index outside the bank (the reference's host-side indexing would raise IndexError): counted by the gather kernel, the count
+    // reaches pinned host memory behind this forward. The verdict is asynchronous like everything on this entry point: a later call on
+    // the context fails if an earlier forward saw bad indices, tim_index_check() blocks for the verdict on the last one.
+    if (!c->idx_alarm_dev) {
+        TIM_TRY(dev_alloc(c, reinterpret_cast<void**>(&c->idx_alarm_dev), sizeof(int)));
+        if (cudaMemset(c->idx_alarm_dev, 0, sizeof(int)) != cudaSuccess ||
+            cudaHostAlloc(reinterpret_cast<void**>(const_cast<int**>(&c->idx_alarm_host)), sizeof(int), cudaHostAllocDefault) != cudaSuccess ||
+            cudaEventCreateWithFlags(&c->idx_event, cudaEventDisableTiming) != cudaSuccess)
+            return c->fail(TIM_ERR_NOMEM, "index alarm allocation failed");
+        *c->idx_alarm_host = 0;
+    }
+    if (*c->idx_alarm_host) {
+        const int n = *c->idx_alarm_host;
+        *c->idx_alarm_host = 0;
+        cudaMemsetAsync(c->idx_alarm_dev, 0, sizeof(int), static_cast<cudaStream_t>(stream));
+        return c->fail(TIM_ERR_INVALID, "tim_encoder_fwd_indexed: %d feature-bank row indices of an earlier call were out of range (those rows were read as zeros)", n);
+    }
     size_t need = 0;
     TIM_TRY(encoder_ws(c, B, T_, Qv, Qa, &need, true));
     TIM_TRY(ensure_ws(c, need));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    return dispatch_dtype(c, [&](auto tag) {
+    const int r = dispatch_dtype(c, [&](auto tag) {
         return encoder_impl<decltype(tag)>(c, nullptr, nullptr, te, B, T_, Qv, Qa, outs, s, c->ws, nullptr, fb, true);
     });
+    if (r != TIM_OK) return r;
+    CU_OK(c, cudaMemcpyAsync(const_cast<int*>(c->idx_alarm_host), c->idx_alarm_dev, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU_OK(c, cudaEventRecord(c->idx_event, s));
+    return TIM_OK;
+}
+
+// Blocks until the index check of the last tim_encoder_fwd_indexed is known: TIM_OK, or TIM_ERR_INVALID (tim_last_error says how many row
+// indices were outside their bank; the outputs of that forward are to be discarded). Clears the count.
+int tim_index_check(tim_ctx* c) {
+    if (!c) return TIM_ERR_INVALID;
+    if (!c->idx_event) return TIM_OK;
+    CU_OK(c, cudaSetDevice(c->device));
+    CU_OK(c, cudaEventSynchronize(c->idx_event));
+    const int n = *c->idx_alarm_host;
+    if (!n) return TIM_OK;
+    *c->idx_alarm_host = 0;
+    CU_OK(c, cudaMemset(c->idx_alarm_dev, 0, sizeof(int)));
+    return c->fail(TIM_ERR_INVALID, "tim_encoder_fwd_indexed: %d feature-bank row indices were out of range (those rows were read as zeros)", n);
 }
 
 // Chunk sizes of tim_forward_host (pure host arithmetic; tim_host_chunk_schedule exposes it to the CPU tests). cpc = target clips

@@ -308,16 +308,18 @@ __global__ void __launch_bounds__(ROWS_PER_CTA * 32) fold_ln_kernel(const float*
 
 // Window gather on the device (the reference gathers `feats[video][feat_indices, aug_indices]` on the host,
 // recognition/.../datasets/sliding_window.py:356-375, and ships the result over PCIe): out[m, :] = TO(bank[rows[m], :]) for a
-// feature bank resident in HBM (fp32 or 16-bit). One warp per row, 16-byte loads; a row index outside the bank yields zeros.
+// feature bank resident in HBM (fp32 or 16-bit). One warp per row, 16-byte loads; a row index outside the bank yields zeros AND is counted
+// in *bad (the reference's host-side indexing raises: the context turns the count into an error, tim_index_check).
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(ROWS_PER_CTA * 32) gather_rows_kernel(const TI* __restrict__ bank, long long bank_rows,
                                                                         const long long* __restrict__ rows, TO* __restrict__ out,
-                                                                        long long M, int D) {
+                                                                        long long M, int D, int* __restrict__ bad) {
     const int lane = threadIdx.x & 31;
     const long long m = static_cast<long long>(blockIdx.x) * ROWS_PER_CTA + (threadIdx.x >> 5);
     if (m >= M) return;
     const long long r = rows[m];
     const bool ok = r >= 0 && r < bank_rows;
+    if (!ok && lane == 0 && bad) atomicAdd(bad, 1);
     const TI* src = bank + (ok ? r : 0) * D;
     TO* dst = out + m * D;
     for (int c = lane * 4; c < D; c += 128) {
@@ -451,21 +453,21 @@ cudaError_t launch_scale_copy(const float* in, float* out, size_t rows, size_t c
 
 template <typename TO>
 cudaError_t launch_gather_rows(const void* bank, int bank_dtype, long long bank_rows, const long long* rows, TO* out, long long M, int D,
-                               cudaStream_t s) {
+                               cudaStream_t s, int* bad) {
     if (M <= 0) return cudaSuccess;
     if (D % 4 || bank_rows <= 0) return cudaErrorInvalidValue;
     const unsigned grid = static_cast<unsigned>((M + ROWS_PER_CTA - 1) / ROWS_PER_CTA);
     switch (bank_dtype) {      // TIM_FP32 = 0, TIM_BF16 = 1, TIM_FP16 = 2
-        case 0: gather_rows_kernel<float, TO><<<grid, ROWS_PER_CTA * 32, 0, s>>>(static_cast<const float*>(bank), bank_rows, rows, out, M, D); break;
-        case 1: gather_rows_kernel<__nv_bfloat16, TO><<<grid, ROWS_PER_CTA * 32, 0, s>>>(static_cast<const __nv_bfloat16*>(bank), bank_rows, rows, out, M, D); break;
-        case 2: gather_rows_kernel<__half, TO><<<grid, ROWS_PER_CTA * 32, 0, s>>>(static_cast<const __half*>(bank), bank_rows, rows, out, M, D); break;
+        case 0: gather_rows_kernel<float, TO><<<grid, ROWS_PER_CTA * 32, 0, s>>>(static_cast<const float*>(bank), bank_rows, rows, out, M, D, bad); break;
+        case 1: gather_rows_kernel<__nv_bfloat16, TO><<<grid, ROWS_PER_CTA * 32, 0, s>>>(static_cast<const __nv_bfloat16*>(bank), bank_rows, rows, out, M, D, bad); break;
+        case 2: gather_rows_kernel<__half, TO><<<grid, ROWS_PER_CTA * 32, 0, s>>>(static_cast<const __half*>(bank), bank_rows, rows, out, M, D, bad); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
 }
-template cudaError_t launch_gather_rows<float>(const void*, int, long long, const long long*, float*, long long, int, cudaStream_t);
-template cudaError_t launch_gather_rows<__half>(const void*, int, long long, const long long*, __half*, long long, int, cudaStream_t);
-template cudaError_t launch_gather_rows<__nv_bfloat16>(const void*, int, long long, const long long*, __nv_bfloat16*, long long, int, cudaStream_t);
+template cudaError_t launch_gather_rows<float>(const void*, int, long long, const long long*, float*, long long, int, cudaStream_t, int*);
+template cudaError_t launch_gather_rows<__half>(const void*, int, long long, const long long*, __half*, long long, int, cudaStream_t, int*);
+template cudaError_t launch_gather_rows<__nv_bfloat16>(const void*, int, long long, const long long*, __nv_bfloat16*, long long, int, cudaStream_t, int*);
 
 cudaError_t launch_row_stats_finalize(const float2* part, int P, int width, float2* stats, int M, float alarm_ratio, int* alarm,
                                       cudaStream_t s) {

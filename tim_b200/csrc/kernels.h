@@ -222,7 +222,7 @@ cudaError_t launch_scale_copy(const float* in, float* out, size_t rows, size_t c
 // out[m, :] = TO(bank[rows[m], :]); bank_dtype 0 fp32 / 1 bf16 / 2 fp16; rows outside [0, bank_rows) give zeros
 template <typename TO>
 cudaError_t launch_gather_rows(const void* bank, int bank_dtype, long long bank_rows, const long long* rows, TO* out, long long M, int D,
-                               cudaStream_t s);
+                               cudaStream_t s, int* bad = nullptr);
 
 // (mean, rstd) per row from the partial sums a mode-5 GEMM wrote: part [P][M] (sum, sum of squares), width columns in total;
 // *alarm (device int, optional) is set when some row has mean^2 > alarm_ratio * var

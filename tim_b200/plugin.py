@@ -155,7 +155,8 @@ class TIMEngine:
                         want_feats: bool = True) -> Dict[str, Optional[torch.Tensor]]:
         """encoder() with the input windows gathered on the device from feature banks resident in HBM: *_bank [rows, dim] (fp32,
         fp16 or bf16, same dtype for both), *_rows [B, num_feats] int64 = bank row of every feature token (what the reference's
-        loader indexes on the host: datasets/sliding_window.py:356-375)."""
+        loader indexes on the host: datasets/sliding_window.py:356-375). A row index outside its bank is an error, reported
+        asynchronously: by index_check() (blocks) or by the next encoder_indexed() on this engine."""
         cfg = self.cfg
         B, T = int(time_enc.shape[0]), int(time_enc.shape[1])
         time_enc = self._check_in(time_enc, "time_encodings", (B, T, cfg.d_model))
@@ -313,6 +314,11 @@ class TIMEngine:
                                                     int(Qv or 0), int(Qa or 0), C.byref(co), int(clips_per_chunk), in_code, out_code,
                                                     self._stream(), C.byref(up), C.byref(down)), self._ctx)
         return outs, int(up.value), int(down.value)
+
+    def index_check(self) -> None:
+        """Blocks until the row indices of the last encoder_indexed() are known to have been inside their banks; raises TimError
+        otherwise (the reference's host-side indexing raises IndexError; see tim_index_check in include/tim_b200.h)."""
+        _lib.check(self.lib.tim_index_check(self._ctx), self._ctx)
 
     def fold_check(self) -> bool:
         """Blocks until the last encoder forward's precision check is known; True = recompute it (see tim_fold_check)."""
