@@ -219,6 +219,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
                 fa = st.y; fb = -st.x * st.y;
             }
             float st_sum = 0.0f, st_sq = 0.0f;            // MODE 5: sum / sum of squares of this thread's z columns in this tile
+            float2 st_sum2 = make_float2(0.0f, 0.0f), st_sq2 = make_float2(0.0f, 0.0f);      // MODE 7: the same as (even, odd) column pairs
 
             if (RES && my_blocks > 0) {             // prefetch the residual of the first block
                 const uint32_t b = nbuf & 1u;
@@ -290,30 +291,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
                                          ::"r"(buf + my_row + ((chunk ^ swz) << 4)), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
                         }
                     } else if (PLANES) {
-                        // residual = hi + lo (two 32 x 32 16-bit tiles, 64-byte rows, 64-byte swizzle); the output planes overwrite them
+                        // residual = hi + lo (two 32 x 32 16-bit tiles, 64-byte rows, 64-byte swizzle); the output planes overwrite them.
+                        // The eight epilogue warps are the serial resource of out_proj (K = 1024: 6 us of MMA per tile against 10 us of
+                        // epilogue, issue slots 46 % busy with two warps per scheduler), so the arithmetic runs on packed fp32 pairs
+                        // (FADD2 / FFMA2) and gamma / beta come as 16-byte loads off one hoisted pointer.
+                        const float2 rs2 = make_float2(ln_rstd, ln_rstd), nm2 = make_float2(ln_nmr, ln_nmr);
+                        const float2 neg1 = make_float2(-1.0f, -1.0f);
+                        const float4* g4p = reinterpret_cast<const float4*>(p.rgamma + n);
+                        const float4* e4p = reinterpret_cast<const float4*>(p.rbeta + n);
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             const uint32_t a_hi = buf + static_cast<uint32_t>(lane) * 64u + ((static_cast<uint32_t>(c) ^ sw64) << 4);
                             const uint32_t a_lo = a_hi + EPI_BUF / 2;
                             const uint4 qh = lds_u128(a_hi), ql = lds_u128(a_lo);
                             const uint32_t hw[4] = {qh.x, qh.y, qh.z, qh.w}, lw[4] = {ql.x, ql.y, ql.z, ql.w};
+                            float2 g2[4], e2[4];
+                            if (ln_res) {
+                                const float4 ga = __ldg(g4p + 2 * c), gb = __ldg(g4p + 2 * c + 1);
+                                const float4 ea = __ldg(e4p + 2 * c), eb = __ldg(e4p + 2 * c + 1);
+                                g2[0] = make_float2(ga.x, ga.y); g2[1] = make_float2(ga.z, ga.w); g2[2] = make_float2(gb.x, gb.y); g2[3] = make_float2(gb.z, gb.w);
+                                e2[0] = make_float2(ea.x, ea.y); e2[1] = make_float2(ea.z, ea.w); e2[2] = make_float2(eb.x, eb.y); e2[3] = make_float2(eb.z, eb.w);
+                            }
                             uint32_t oh[4], ol[4];
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const float2 h2 = unpack2<T>(hw[j]), l2 = unpack2<T>(lw[j]);
-                                float r0 = h2.x + l2.x, r1 = h2.y + l2.y;
-                                const int col = n + 8 * c + 2 * j;
-                                if (ln_res) {
-                                    const float2 g2 = __ldg(reinterpret_cast<const float2*>(p.rgamma + col));
-                                    const float2 e2 = __ldg(reinterpret_cast<const float2*>(p.rbeta + col));
-                                    r0 = fmaf(fmaf(r0, ln_rstd, ln_nmr), g2.x, e2.x);
-                                    r1 = fmaf(fmaf(r1, ln_rstd, ln_nmr), g2.y, e2.y);
-                                }
-                                const float o0 = f[8 * c + 2 * j] + r0, o1 = f[8 * c + 2 * j + 1] + r1;
-                                oh[j] = pack2<T>(o0, o1);
-                                const float2 hb = unpack2<T>(oh[j]);
-                                ol[j] = pack2<T>(o0 - hb.x, o1 - hb.y);
-                                st_sum += o0 + o1; st_sq = fmaf(o0, o0, fmaf(o1, o1, st_sq));
+                                float2 r = __fadd2_rn(unpack2<T>(hw[j]), unpack2<T>(lw[j]));
+                                if (ln_res) r = __ffma2_rn(__ffma2_rn(r, rs2, nm2), g2[j], e2[j]);
+                                const float2 o = __fadd2_rn(make_float2(f[8 * c + 2 * j], f[8 * c + 2 * j + 1]), r);
+                                oh[j] = pack2<T>(o.x, o.y);
+                                const float2 d = __ffma2_rn(unpack2<T>(oh[j]), neg1, o);      // o - hi, exact product
+                                ol[j] = pack2<T>(d.x, d.y);
+                                st_sum2 = __fadd2_rn(st_sum2, o);
+                                st_sq2 = __ffma2_rn(o, o, st_sq2);
                             }
                             sts_u128(a_hi, make_uint4(oh[0], oh[1], oh[2], oh[3]));
                             sts_u128(a_lo, make_uint4(ol[0], ol[1], ol[2], ol[3]));
@@ -365,6 +374,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
                 }
                 ++nbuf;
             }
+            if (PLANES) { st_sum = st_sum2.x + st_sum2.y; st_sq = st_sq2.x + st_sq2.y; }
             if ((DUAL || PLANES) && row_ok)              // also when this half owns no column of a ragged last tile: (0, 0)
                 p.opart[static_cast<size_t>(tn * 2 + half) * p.M + row0 + lane] = make_float2(st_sum, st_sq);
             // all of this warp's TMEM reads of the accumulator are done

@@ -17,12 +17,18 @@ MARKS = ("SYNCS", "UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "BAR.", "EXIT", "UTCB
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("rep")
+    ap.add_argument("--launch", type=int, default=0, help="which captured launch of the report")
     ap.add_argument("--segments", default="", help="a:b:name,... instruction index ranges to summarise by opcode / stall reason")
     args = ap.parse_args()
     txt = subprocess.run(["ncu", "-i", args.rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
+    # one block per captured launch: a kernel-name row, the header row, then one row per SASS instruction
+    starts = [i for i, r in enumerate(rows) if i + 1 < len(rows) and "Source" in rows[i + 1] and "# Samples" in rows[i + 1]]
+    a = starts[args.launch]
+    b = starts[args.launch + 1] if args.launch + 1 < len(starts) else len(rows)
+    rows = rows[a:b]
     print(rows[0][1] if len(rows[0]) > 1 else rows[0])
-    hdr, data = rows[1], rows[2:]
+    hdr, data = rows[1], [r for r in rows[2:] if len(r) == len(rows[1])]
     isrc, isamp, iex = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
     stall_cols = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
     total = sum(int(r[isamp]) for r in data)
