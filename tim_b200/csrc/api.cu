@@ -89,6 +89,7 @@ struct tim_ctx {
     tim_train_state* train = nullptr;   // training leg (train.inl); allocated by tim_train_enable
     int class_override = -1;            // profiling class forced onto run_linear launches (dgrad GEMMs)
     int wgrad_splits = 0;               // 0: chosen per shape (TIM_B200_WGRAD_SPLITS overrides)
+    bool train_fuse = true;             // training leg: linear1 + GELU and linear2-dgrad + GELU' as single launches (TIM_B200_TRAIN_FUSE=0: separate row kernels)
     int device = 0, num_sms = 0;
     int d = 0, E = 0, FF = 0, H = 0, hd = 0, L = 0, F = 0, Fv = 0, Fa = 0, Ft = 0;
     bool vis_data = false, aud_data = false, vn_tokens = false;
@@ -465,6 +466,7 @@ int run_linear(tim_ctx* c, const void* A, int lda, const LinearW& w, RowMap rm, 
     }
     if constexpr (std::is_same<T, float>::value) {
         if (ep.rstats) return c->fail(TIM_ERR_INVALID, "linear: LayerNorm-on-read residual is a 16-bit path feature");
+        if (ep.out_act || ep.dact_of) return c->fail(TIM_ERR_INVALID, "linear: fused activation outputs are a 16-bit path feature");
         ep.out_fp32 = 1;
         LAUNCH_C(c, 0, 2.0 * rm.G * rm.R * w.N * w.K, s,
                  launch_linear_simt(static_cast<const float*>(A), lda, static_cast<const float*>(w.w), w.N, w.K, rm, ep, s));
@@ -487,10 +489,18 @@ int run_linear(tim_ctx* c, const void* A, int lda, const LinearW& w, RowMap rm, 
                 TIM_TRY(make_tmap_2d(c, &q.tmRes, ep.resid, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, w.N, M, static_cast<long long>(ep.ldr) * 4, 32, 32));
             q.bias = ep.bias; q.M = M; q.N = w.N; q.K = w.K;
             q.rstats = ep.rstats; q.rgamma = ep.rgamma; q.rbeta = ep.rbeta;
-            const int mode = ep.out_fp32 ? (ep.resid ? (ep.rstats ? 3 : 2) : 1) : 0;
+            int mode = ep.out_fp32 ? (ep.resid ? (ep.rstats ? 3 : 2) : 1) : 0;
+            if (ep.out_act || ep.dact_of) {         // training-leg fusions (modes 8 / 9): 16-bit output, no residual, one of the two
+                if (mode != 0 || (ep.out_act && ep.dact_of) || (ep.out_act && ep.act != ACT_GELU) || (ep.dact_of && ep.act != ACT_NONE) ||
+                    ((reinterpret_cast<uintptr_t>(ep.out_act) | reinterpret_cast<uintptr_t>(ep.dact_of)) & 15))
+                    return c->fail(TIM_ERR_INVALID, "linear: unsupported combination for a fused activation output");
+                if (ep.out_act) { TIM_TRY(make_tmap_2d(c, &q.tmOut16, ep.out_act, op_dtype(c), 2, w.N, M, static_cast<long long>(ep.ldo) * 2, 64, 32)); mode = 8; }
+                else { TIM_TRY(make_tmap_2d(c, &q.tmRes, ep.dact_of, op_dtype(c), 2, w.N, M, static_cast<long long>(ep.ldo) * 2, 64, 32)); mode = 9; }
+            }
             LAUNCH_C(c, 0, 2.0 * M * w.N * w.K, s, launch_linear_umma2<T>(q, mode, ep.act, c->num_sms, s));
             return TIM_OK;
         }
+        if (ep.out_act || ep.dact_of) return c->fail(TIM_ERR_INVALID, "linear: fused activation outputs need the CTA-pair kernel (check fused_act_ok first)");
         UmmaParams p;
         std::memset(&p, 0, sizeof(p));
         TIM_TRY(make_tmap(c, &p.tmA, A, w.K, rm.a_group_rows, rm.G, rm.box_r, rm.box_g));
@@ -531,10 +541,17 @@ cudaError_t launch_attention_tc(const tim_ctx* c, const AttnUmmaParams& ap, cuda
                                                                           : launch_attention_umma<T>(ap, c->hd, c->num_sms, s);
 }
 
+// whether run_linear sends a plain [M, w.N] 16-bit-output linear (row stride ldo elements) to the CTA-pair kernel: the precondition of the
+// fused activation outputs (Epilogue::out_act / dact_of)
+inline bool fused_act_ok(const tim_ctx* c, const LinearW& w, int M, int ldo) {
+    return c->gemm_version >= 2 && w.has_tmB2 && umma2_supported(M, w.N, w.K) && (static_cast<size_t>(ldo) * 2) % 16 == 0;
+}
+
 inline Epilogue epi(void* out, int ldo, bool out_fp32, int act = ACT_NONE, const float* resid = nullptr, int ldr = 0) {
     Epilogue e;
     e.bias = nullptr; e.resid = resid; e.ldr = ldr; e.out = out; e.ldo = ldo; e.out_fp32 = out_fp32 ? 1 : 0; e.act = act;
     e.rstats = nullptr; e.rgamma = nullptr; e.rbeta = nullptr;
+    e.out_act = nullptr; e.dact_of = nullptr;
     return e;
 }
 
@@ -749,6 +766,7 @@ int encoder_impl(tim_ctx* c, const float* vis, const float* aud, const float* te
     }
     const bool planes = folded && planes_ws;
     ap.xlo = planes ? xlo : nullptr;
+    if (planes && c->L > 0) ap.x32 = nullptr;       // the planes flow never reads the fp32 tokens: 4 of the 8 bytes per element stay unwritten
     LAUNCH_C(c, 3, 0.0, s, launch_assemble<T>(ap, s));
 
     // ---- encoder layers (post-LN): x = LN1(x + out_proj(attn(in_proj(x)))); x = LN2(x + W2 gelu(W1 x)) ----
@@ -986,6 +1004,7 @@ int tim_create(tim_ctx** out, const tim_config* cfg, int device) {
     if (const char* gv = std::getenv("TIM_B200_GEMM")) c->gemm_version = std::atoi(gv) == 1 ? 1 : 2;
     if (const char* av = std::getenv("TIM_B200_ATTN")) { const int v = std::atoi(av); c->attn_version = v < 1 ? 1 : (v > 4 ? 4 : v); }
     if (const char* wv = std::getenv("TIM_B200_WGRAD_SPLITS")) c->wgrad_splits = std::atoi(wv);
+    if (const char* tf = std::getenv("TIM_B200_TRAIN_FUSE")) c->train_fuse = std::atoi(tf) != 0;
     if (c->d % 4) return bail(c->fail(TIM_ERR_INVALID, "d_model must be a multiple of 4"));
     if (c->vis_data && !g.n_action) return bail(c->fail(TIM_ERR_INVALID, "visual data modality needs n_action > 0"));
     if (c->aud_data && !g.n_audio) return bail(c->fail(TIM_ERR_INVALID, "audio data modality needs n_audio > 0"));

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(ROWS_PER_CTA * 32) assemble_kernel(const Assem
     float mean = 0.0f, rstd = 1.0f;
     if (g) row_stats(left, d, lane, mean, rstd);
     const float* te = p.te + (static_cast<size_t>(b) * p.T + te_row) * d;
-    float* o32 = p.x32 + row * E;
+    float* o32 = p.x32 ? p.x32 + row * E : nullptr;      // not written on the two-plane residual stream: (x16, xlo) carry the tokens
     T* o16 = p.x16 ? reinterpret_cast<T*>(p.x16) + row * E : nullptr;
     T* olo = p.xlo ? reinterpret_cast<T*>(p.xlo) + row * E : nullptr;
     for (int c = lane * 4; c < E; c += 128) {
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(ROWS_PER_CTA * 32) assemble_kernel(const Assem
             const float4 m = __ldg(reinterpret_cast<const float4*>(mod + c));
             v.x += m.x; v.y += m.y; v.z += m.z; v.w += m.w;
         }
-        store4<float>(o32 + c, v.x, v.y, v.z, v.w);
+        if (o32) store4<float>(o32 + c, v.x, v.y, v.z, v.w);
         if (o16) store4<T>(o16 + c, v.x, v.y, v.z, v.w);
         if (olo) {
             const float h0 = to_float<T>(from_float<T>(v.x)), h1 = to_float<T>(from_float<T>(v.y));

@@ -46,9 +46,10 @@ template <typename T> struct FmtOf2;
 template <> struct FmtOf2<__half> { static constexpr uint32_t v = 0; };
 template <> struct FmtOf2<__nv_bfloat16> { static constexpr uint32_t v = 1; };
 
-template <int ACT> __device__ __forceinline__ float apply_act(float v) {
-    if (ACT == ACT_RELU) return fmaxf(v, 0.0f);
-    if (ACT == ACT_GELU) return gelu_erf_fast(v);
+// activations on PAIRS of values: the epilogue arithmetic runs on the packed fp32 instructions (FADD2 / FFMA2 / FMUL2, ptx.cuh)
+template <int ACT> __device__ __forceinline__ float2 apply_act2(float2 v) {
+    if (ACT == ACT_RELU) return make_float2(fmaxf(v.x, 0.0f), fmaxf(v.y, 0.0f));
+    if (ACT == ACT_GELU) return gelu_erf_fast2(v);
     return v;
 }
 
@@ -60,6 +61,9 @@ template <int ACT> __device__ __forceinline__ float apply_act(float v) {
 //    thread owns in the tile: p.opart[(2 tn + half) * M + row]  (row_stats_finalize_kernel turns them into (mean, rstd));
 // 6: consumer - A = the 16-bit copy of z, W pre-multiplied by gamma: out = T(act(rstd * (acc - mean * cs[n]) + bw[n])) with
 //    (mean, rstd) = p.rstats[row], cs[n] = sum_k W'[n,k], bw[n] = sum_k beta[k] W[n,k] + bias[n] (passed as p.bias),
+// Training-leg fusions: 8: two 16-bit outputs, T(acc + bias) -> tmOut (the pre-activation the backward needs) and T(act(that)) -> tmOut16
+//    (linear1 + GELU without the separate activation pass); 9: 16-bit out = T((acc + bias) * gelu'(u)) with the 16-bit pre-activation
+//    tile u read through tmRes (TMA, same box as the output, overwritten in place) - linear2's dgrad with the GELU backward inside.
 // 7: producer on a TWO-PLANE residual stream: z is kept as hi = T(z), lo = T(z - hi) (two 16-bit planes, ~22 significant bits with
 //    fp16; tools/residual_split_study.py: 5.9e-7 end to end) instead of fp32 + a 16-bit copy. The hi plane IS the A operand of the
 //    consumer GEMM, so a producer writes 4 bytes per element where mode 5 writes 6, reads the residual as two 16-bit tiles (TMA, box
@@ -98,8 +102,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
         tma_prefetch_desc(&p.tmOut);
-        if (MODE == 2 || MODE == 3 || MODE == 5 || MODE == 7) tma_prefetch_desc(&p.tmRes);
-        if (MODE == 5) tma_prefetch_desc(&p.tmOut16);
+        if (MODE == 2 || MODE == 3 || MODE == 5 || MODE == 7 || MODE == 9) tma_prefetch_desc(&p.tmRes);
+        if (MODE == 5 || MODE == 8) tma_prefetch_desc(&p.tmOut16);
         if (MODE == 7) { tma_prefetch_desc(&p.tmResLo); tma_prefetch_desc(&p.tmOutLo); }
     }
     if (warp == 1) {
@@ -181,8 +185,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
         const uint32_t my_row = static_cast<uint32_t>(lane) * 128u;
         const uint32_t swz = static_cast<uint32_t>(lane & 7);
         const uint32_t tempty_leader0 = mapa_shared(tempty_bar(0), 0), tempty_leader1 = mapa_shared(tempty_bar(1), 0);
-        constexpr bool OUT16 = MODE == 0 || MODE == 6;
-        constexpr bool RES = MODE == 2 || MODE == 3 || MODE == 5 || MODE == 7;
+        constexpr bool OUT16 = MODE == 0 || MODE == 6 || MODE == 8 || MODE == 9;
+        constexpr bool RES = MODE == 2 || MODE == 3 || MODE == 5 || MODE == 7 || MODE == 9;      // a tile comes in through tmRes
+        constexpr bool TWO_OUT = MODE == 8;               // pre-activation -> tmOut (slot 0), activation -> tmOut16 (slot 1)
+        constexpr bool DACT = MODE == 9;                  // the tmRes tile is the 16-bit pre-activation u: out = (acc + bias) * gelu'(u)
+        constexpr int ACT_F = TWO_OUT ? ACT_NONE : ACT;
         constexpr bool DUAL = MODE == 5;
         constexpr bool PLANES = MODE == 7;
         constexpr bool FOLD = MODE == 6;
@@ -238,7 +245,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
             for (int i = 0; i < my_blocks; ++i) {
                 const int cb = block_of(i);
                 const int col0 = n0 + cb * COLS_PER_BLOCK;
-                const uint32_t b = nbuf & 1u;
+                const uint32_t b = TWO_OUT ? 0u : (nbuf & 1u);
                 const uint32_t buf = buf0 + b * EPI_BUF;
                 if (RES) {
                     if (i + 1 < my_blocks) {              // prefetch the next block's residual into the other buffer
@@ -253,7 +260,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
                     }
                     mbar_wait(epild_bar(e, b), (nbuf >> 1) & 1u);
                 } else {
-                    if (lane == 0) tma_store_wait_read<EPI_BUFS - 1>();   // the store that last used this buffer has read it
+                    if (lane == 0) {                      // the store(s) that last used this buffer have read it
+                        if (TWO_OUT) tma_store_wait_read<0>(); else tma_store_wait_read<EPI_BUFS - 1>();
+                    }
                     __syncwarp();
                 }
 #pragma unroll
@@ -263,32 +272,52 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
                     tmem_ld_wait();
                     float f[32];
                     const int n = col0 + part * 32;
+                    const float2 fa2 = make_float2(fa, fa), fb2 = make_float2(fb, fb);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+                        float2 lo = make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+                        float2 hi = make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
                         if (FOLD) {
                             const float4 c4 = __ldg(reinterpret_cast<const float4*>(p.cs + n + j));
-                            f[j] = apply_act<ACT>(fmaf(fa, __uint_as_float(v[j]), fmaf(fb, c4.x, b4.x)));
-                            f[j + 1] = apply_act<ACT>(fmaf(fa, __uint_as_float(v[j + 1]), fmaf(fb, c4.y, b4.y)));
-                            f[j + 2] = apply_act<ACT>(fmaf(fa, __uint_as_float(v[j + 2]), fmaf(fb, c4.z, b4.z)));
-                            f[j + 3] = apply_act<ACT>(fmaf(fa, __uint_as_float(v[j + 3]), fmaf(fb, c4.w, b4.w)));
+                            lo = __ffma2_rn(fa2, lo, __ffma2_rn(fb2, make_float2(c4.x, c4.y), make_float2(b4.x, b4.y)));
+                            hi = __ffma2_rn(fa2, hi, __ffma2_rn(fb2, make_float2(c4.z, c4.w), make_float2(b4.z, b4.w)));
                         } else {
-                            f[j] = apply_act<ACT>(__uint_as_float(v[j]) + b4.x);
-                            f[j + 1] = apply_act<ACT>(__uint_as_float(v[j + 1]) + b4.y);
-                            f[j + 2] = apply_act<ACT>(__uint_as_float(v[j + 2]) + b4.z);
-                            f[j + 3] = apply_act<ACT>(__uint_as_float(v[j + 3]) + b4.w);
+                            lo = __fadd2_rn(lo, make_float2(b4.x, b4.y));
+                            hi = __fadd2_rn(hi, make_float2(b4.z, b4.w));
                         }
+                        lo = apply_act2<ACT_F>(lo); hi = apply_act2<ACT_F>(hi);
+                        f[j] = lo.x; f[j + 1] = lo.y; f[j + 2] = hi.x; f[j + 3] = hi.y;
                     }
                     if (OUT16) {
                         // 32 columns -> 64 B = logical 16-byte chunks part*4 .. part*4+3 of this row
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
+                            const uint32_t chunk = static_cast<uint32_t>(part * 4 + c);
+                            const uint32_t addr = buf + my_row + ((chunk ^ swz) << 4);
+                            if (DACT) {                   // the same 16 bytes of the pre-activation tile that the result overwrites
+                                const uint4 uq = lds_u128(addr);
+                                const uint32_t uw[4] = {uq.x, uq.y, uq.z, uq.w};
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const float2 d2 = __fmul2_rn(make_float2(f[8 * c + 2 * k], f[8 * c + 2 * k + 1]), gelu_grad_fast2(unpack2<T>(uw[k])));
+                                    f[8 * c + 2 * k] = d2.x; f[8 * c + 2 * k + 1] = d2.y;
+                                }
+                            }
                             uint4 q;
                             q.x = pack2<T>(f[8 * c], f[8 * c + 1]); q.y = pack2<T>(f[8 * c + 2], f[8 * c + 3]);
                             q.z = pack2<T>(f[8 * c + 4], f[8 * c + 5]); q.w = pack2<T>(f[8 * c + 6], f[8 * c + 7]);
-                            const uint32_t chunk = static_cast<uint32_t>(part * 4 + c);
-                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                                         ::"r"(buf + my_row + ((chunk ^ swz) << 4)), "r"(q.x), "r"(q.y), "r"(q.z), "r"(q.w) : "memory");
+                            sts_u128(addr, q);
+                            if (TWO_OUT) {                // act() of the ROUNDED pre-activation: what a separate pass over `out` would compute
+                                const uint32_t qw[4] = {q.x, q.y, q.z, q.w};
+                                uint32_t hw[4];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const float2 h2 = apply_act2<ACT>(unpack2<T>(qw[k]));
+                                    hw[k] = pack2<T>(h2.x, h2.y);
+                                }
+                                sts_u128(addr + EPI_BUF, make_uint4(hw[0], hw[1], hw[2], hw[3]));
+                            }
                         }
                     } else if (PLANES) {
                         // residual = hi + lo (two 32 x 32 16-bit tiles, 64-byte rows, 64-byte swizzle); the output planes overwrite them.
@@ -336,13 +365,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
                                 float4 r;
                                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                                              : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+                                float2 r01 = make_float2(r.x, r.y), r23 = make_float2(r.z, r.w);
                                 if (ln_res) {
-                                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.rgamma + n + 4 * c));
-                                    const float4 e4 = __ldg(reinterpret_cast<const float4*>(p.rbeta + n + 4 * c));
-                                    r.x = fmaf(fmaf(r.x, ln_rstd, ln_nmr), g4.x, e4.x); r.y = fmaf(fmaf(r.y, ln_rstd, ln_nmr), g4.y, e4.y);
-                                    r.z = fmaf(fmaf(r.z, ln_rstd, ln_nmr), g4.z, e4.z); r.w = fmaf(fmaf(r.w, ln_rstd, ln_nmr), g4.w, e4.w);
+                                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.rgamma + n) + c);
+                                    const float4 e4 = __ldg(reinterpret_cast<const float4*>(p.rbeta + n) + c);
+                                    const float2 rs2 = make_float2(ln_rstd, ln_rstd), nm2 = make_float2(ln_nmr, ln_nmr);
+                                    r01 = __ffma2_rn(__ffma2_rn(r01, rs2, nm2), make_float2(g4.x, g4.y), make_float2(e4.x, e4.y));
+                                    r23 = __ffma2_rn(__ffma2_rn(r23, rs2, nm2), make_float2(g4.z, g4.w), make_float2(e4.z, e4.w));
                                 }
-                                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+                                const float2 o01 = __fadd2_rn(make_float2(o.x, o.y), r01), o23 = __fadd2_rn(make_float2(o.z, o.w), r23);
+                                o = make_float4(o01.x, o01.y, o23.x, o23.y);
                             }
                             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};"
                                          ::"r"(addr), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
@@ -368,6 +400,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
                 __syncwarp();
                 if (lane == 0) {
                     tma_store_2d(&p.tmOut, buf, col0, row0);
+                    if (TWO_OUT) tma_store_2d(&p.tmOut16, buf + EPI_BUF, col0, row0);
                     if (DUAL && (i & 1)) tma_store_2d(&p.tmOut16, buf16, col0 - 32, row0);
                     if (PLANES) tma_store_2d(&p.tmOutLo, buf + EPI_BUF / 2, col0, row0);
                     tma_store_commit();
@@ -424,6 +457,8 @@ cudaError_t launch_linear_umma2(Umma2Params p, int mode, int act, int num_sms, c
     TIM_U2(5, ACT_NONE)
     TIM_U2(6, ACT_NONE) TIM_U2(6, ACT_GELU)
     TIM_U2(7, ACT_NONE)
+    TIM_U2(8, ACT_GELU)
+    TIM_U2(9, ACT_NONE)
 #undef TIM_U2
     return cudaErrorInvalidValue;
 }

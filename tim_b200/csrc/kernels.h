@@ -84,6 +84,11 @@ struct Epilogue {
     int ldo;
     int out_fp32;         // 1: float*, 0: T*
     int act;              // Act
+    // training-leg fusions of the CTA-pair kernel (16-bit output only; gemm_umma2.cu modes 8 / 9):
+    void* out_act;        // when set: `out` receives T(acc + bias) (the pre-activation kept for the backward) and out_act [rows, ldo]
+                          // receives T(act(float(that rounded value))) - linear1 + GELU of the training forward in one launch
+    const void* dact_of;  // when set (T [rows, ldo]): out = T((acc + bias) * gelu'(float(dact_of))) - linear2's dgrad with the GELU
+                          // backward in its epilogue
 };
 
 // ---- tcgen05 GEMM: C[rows, N] = A[rows, K] * W[N, K]^T, 16-bit operands, fp32 accumulate in TMEM ----
@@ -122,7 +127,8 @@ struct Umma2Params {
 bool umma2_supported(int M, int N, int K);
 // mode 0: out = T(act(acc + bias)); 1: out = float(act(acc + bias)); 2: out = float(act(acc + bias) + resid);
 // mode 3: out = float(act(acc + bias) + LayerNorm(resid)) with the row statistics given (Epilogue::rstats)
-// modes 5 / 6: the folded-LayerNorm producer / consumer pair, see gemm_umma2.cu; mode 7: producer on the two-plane residual stream
+// modes 5 / 6: the folded-LayerNorm producer / consumer pair, see gemm_umma2.cu; mode 7: producer on the two-plane residual stream;
+// mode 8: two 16-bit outputs (pre-activation in tmOut, activation in tmOut16); mode 9: 16-bit out = (acc + bias) * gelu'(tmRes tile, 16-bit)
 template <typename T>
 cudaError_t launch_linear_umma2(Umma2Params p, int mode, int act, int num_sms, cudaStream_t s);
 

@@ -383,4 +383,60 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
     return fmaf(-0.5f * ax, e, fmaxf(x, 0.0f));
 }
 
+// d/dx [x Phi(x)] = Phi(x) + x phi(x) for the 16-bit training paths: Phi(x) from the same degree-6 fit of log2 erfc(|x| / sqrt2) as
+// gelu_erf_fast (relative error 3e-5 of erfc), phi(x) = 2^(-x^2 log2(e) / 2) / sqrt(2 pi): two MUFU.EX2 and ~16 FMAs, no erff() / expf()
+// call sequences - the first version of act_bwd_kernel was instruction-bound on those (781 us for 2.5 GB,
+// profiles/r02b_launches_train_cfg2.csv). Used by the row kernels (train_rows.cu) and by the dgrad epilogue of gemm_umma2.cu (mode 9).
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+    const float ax = fabsf(x);
+    const float u = fminf(ax, 5.656854249f);
+    float p = 2.513894565e-05f;
+    p = fmaf(p, u, -6.454259847e-04f);
+    p = fmaf(p, u, 7.399560496e-03f);
+    p = fmaf(p, u, -5.173896880e-02f);
+    p = fmaf(p, u, -4.605998700e-01f);
+    p = fmaf(p, u, -1.150469307e+00f);
+    p = fmaf(p, u, -4.401278411e-05f);
+    float e, g;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p));
+    const float h = 0.5f * e;                                   // 0.5 erfc(|x| / sqrt2) = Phi(-|x|)
+    const float cdf = x >= 0.0f ? 1.0f - h : h;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g) : "f"(-0.72134752044448170368f * x * x));
+    return fmaf(x, 0.39894228040143267794f * g, cdf);
+}
+
+// The same two functions on a pair of values with the packed fp32 instructions of sm_100 (FFMA2 / FMUL2 / FADD2: two lanes per issue
+// slot) - for the GEMM epilogues, where eight warps per SM are the serial resource and instruction count is what they are bound by.
+// Same polynomial, same MUFU.EX2 calls: bit-identical to the scalar versions.
+__device__ __forceinline__ float2 gelu_poly2(float2 u) {
+    float2 p = make_float2(2.513894565e-05f, 2.513894565e-05f);
+    p = __ffma2_rn(p, u, make_float2(-6.454259847e-04f, -6.454259847e-04f));
+    p = __ffma2_rn(p, u, make_float2(7.399560496e-03f, 7.399560496e-03f));
+    p = __ffma2_rn(p, u, make_float2(-5.173896880e-02f, -5.173896880e-02f));
+    p = __ffma2_rn(p, u, make_float2(-4.605998700e-01f, -4.605998700e-01f));
+    p = __ffma2_rn(p, u, make_float2(-1.150469307e+00f, -1.150469307e+00f));
+    p = __ffma2_rn(p, u, make_float2(-4.401278411e-05f, -4.401278411e-05f));
+    return p;
+}
+__device__ __forceinline__ float2 ex2_approx2(float2 x) {
+    float2 r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(x.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(x.y));
+    return r;
+}
+__device__ __forceinline__ float2 gelu_erf_fast2(float2 x) {
+    const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+    const float2 e = ex2_approx2(gelu_poly2(make_float2(fminf(ax.x, 5.656854249f), fminf(ax.y, 5.656854249f))));
+    return __ffma2_rn(__fmul2_rn(ax, make_float2(-0.5f, -0.5f)), e, make_float2(fmaxf(x.x, 0.0f), fmaxf(x.y, 0.0f)));
+}
+__device__ __forceinline__ float2 gelu_grad_fast2(float2 x) {
+    const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+    const float2 e = ex2_approx2(gelu_poly2(make_float2(fminf(ax.x, 5.656854249f), fminf(ax.y, 5.656854249f))));
+    const float2 h = __fmul2_rn(e, make_float2(0.5f, 0.5f));
+    const float2 hc = __ffma2_rn(h, make_float2(-1.0f, -1.0f), make_float2(1.0f, 1.0f));      // 1 - h
+    const float2 cdf = make_float2(x.x >= 0.0f ? hc.x : h.x, x.y >= 0.0f ? hc.y : h.y);
+    const float2 g = ex2_approx2(__fmul2_rn(__fmul2_rn(x, make_float2(-0.72134752044448170368f, -0.72134752044448170368f)), x));
+    return __ffma2_rn(x, __fmul2_rn(g, make_float2(0.39894228040143267794f, 0.39894228040143267794f)), cdf);
+}
+
 }  // namespace tim

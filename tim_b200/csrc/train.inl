@@ -408,8 +408,15 @@ int encoder_train_fwd(tim_ctx* c, const float* vis, const float* aud, const floa
                 TIM_TRY(run_linear<T>(c, t.att, E, ly.out_proj, plain_rows(Mi), e1, s));
             }
             LAUNCH_C(c, 2, 0.0, s, launch_layernorm<T>(t.z1, E, ly.n1g, ly.n1b, nullptr, 0, static_cast<T*>(t.x1), E, Mi, E, s, t.st1));
-            TIM_TRY(run_linear<T>(c, t.x1, E, ly.lin1, plain_rows(Mi), epi(t.u, FF, false, ACT_NONE), s));
-            LAUNCH(c, launch_gelu_fwd<T>(static_cast<const T*>(t.u), static_cast<T*>(t.hid), M * FF, s, d_ffn));
+            if (!d_ffn.thr && c->train_fuse && fused_act_ok(c, ly.lin1, Mi, FF)) {
+                // linear1 writes the pre-activation u (kept for the backward) AND hid = GELU(u) from one epilogue (gemm_umma2.cu mode 8)
+                Epilogue eu = epi(t.u, FF, false, ACT_GELU);
+                eu.out_act = t.hid;
+                TIM_TRY(run_linear<T>(c, t.x1, E, ly.lin1, plain_rows(Mi), eu, s));
+            } else {
+                TIM_TRY(run_linear<T>(c, t.x1, E, ly.lin1, plain_rows(Mi), epi(t.u, FF, false, ACT_NONE), s));
+                LAUNCH(c, launch_gelu_fwd<T>(static_cast<const T*>(t.u), static_cast<T*>(t.hid), M * FF, s, d_ffn));
+            }
             if (d_sub2.thr) {
                 TIM_TRY(run_linear<T>(c, t.hid, FF, ly.lin2, plain_rows(Mi), epi(sub32, E, true), s));
                 LAUNCH(c, launch_residual_drop(sub32, t.z1, t.st1, ly.n1g, ly.n1b, t.z2, Mi, E, d_sub2, s));
@@ -596,8 +603,18 @@ int encoder_train_bwd(tim_ctx* c, const tim_outputs* go, float* d_te, cudaStream
         // norm2 backward: g32 = d / d LN2(z2) -> dz2 (in place, + operand copy); dz2 (o dropout2's mask) is the gradient of linear2's output
         LAUNCH_C(c, 2, 0.0, s, launch_ln_bwd<T>(g32, E, t.z2, E, ly.n2g, g16w, E, g_n2g, g_n2b, g_b2, Mi, E, s, d_sub2));
         TIM_TRY(run_wgrad<T>(c, gop, E, t.hid, FF, g_w2, FF, Mi, E, FF, s));
-        TIM_TRY(run_dgrad<T>(c, gop, ly.lin2, Mi, epi(dh, FF, f32), s));
-        LAUNCH(c, (launch_act_bwd<T, T, T>(0, dh, static_cast<const T*>(t.u), dh, Mi, FF, g_b1, s, d_ffn)));
+        bool fused_dact = false;
+        if constexpr (!f32) fused_dact = !d_ffn.thr && c->train_fuse && ly.lin2.has_tmBt2 && fused_act_ok(c, dgrad_view(c, ly.lin2), Mi, FF);
+        if (fused_dact) {
+            // d / d u = (dz2 W2) o GELU'(u) straight from the dgrad epilogue (gemm_umma2.cu mode 9); the bias gradient is its column sum
+            Epilogue ed = epi(dh, FF, false);
+            ed.dact_of = t.u;
+            TIM_TRY(run_dgrad<T>(c, gop, ly.lin2, Mi, ed, s));
+            LAUNCH(c, launch_colsum<T>(static_cast<const T*>(dh), FF, 1, 0, 0, Mi, 0, FF, g_b1, s));
+        } else {
+            TIM_TRY(run_dgrad<T>(c, gop, ly.lin2, Mi, epi(dh, FF, f32), s));
+            LAUNCH(c, (launch_act_bwd<T, T, T>(0, dh, static_cast<const T*>(t.u), dh, Mi, FF, g_b1, s, d_ffn)));
+        }
         TIM_TRY(run_wgrad<T>(c, dh, FF, t.x1, E, g_w1, E, Mi, FF, E, s));
         // d / d x1 = du W1 + dz2 (the residual branch), in place in g32
         TIM_TRY(run_dgrad<T>(c, dh, ly.lin1, Mi, epi(g32, E, true, ACT_NONE, g32, E), s));

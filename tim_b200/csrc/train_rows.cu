@@ -22,25 +22,6 @@ __device__ __forceinline__ float gelu_grad(float x) {          // d/dx [x Phi(x)
     const float cdf = 0.5f * (1.0f + erff(x * kInvSqrt2));
     return fmaf(x * kInvSqrt2Pi, __expf(-0.5f * x * x), cdf);
 }
-// 16-bit paths: Phi(x) from the same degree-6 fit of log2 erfc(|x| / sqrt2) the forward's gelu_erf_fast uses (ptx.cuh; relative
-// error 3e-5 of erfc), phi(x) = 2^(-x^2 log2(e) / 2) / sqrt(2 pi): two MUFU.EX2 and ~16 FMAs, no erff() / expf() call sequences - the
-// first version of act_bwd_kernel was instruction-bound on those (781 us for 2.5 GB, profiles/r02b_launches_train_cfg2.csv).
-__device__ __forceinline__ float gelu_grad_fast(float x) {
-    const float ax = fabsf(x);
-    const float u = fminf(ax, 5.656854249f);
-    float p = 2.513894565e-05f;
-    p = fmaf(p, u, -6.454259847e-04f);
-    p = fmaf(p, u, 7.399560496e-03f);
-    p = fmaf(p, u, -5.173896880e-02f);
-    p = fmaf(p, u, -4.605998700e-01f);
-    p = fmaf(p, u, -1.150469307e+00f);
-    p = fmaf(p, u, -4.401278411e-05f);
-    const float h = 0.5f * ex2_approx(p);                      // 0.5 erfc(|x| / sqrt2) = Phi(-|x|)
-    const float cdf = x >= 0.0f ? 1.0f - h : h;
-    const float pdf = kInvSqrt2Pi * ex2_approx(-0.72134752044448170368f * x * x);
-    return fmaf(x, pdf, cdf);
-}
-
 template <typename T> __device__ __forceinline__ void load4(const T* p, float (&v)[4]);
 template <> __device__ __forceinline__ void load4<float>(const float* p, float (&v)[4]) {
     const float4 t = *reinterpret_cast<const float4*>(p);
