@@ -351,6 +351,21 @@ def measure_sweep(X: Ctx, dtype, pk, steps=3, hbm_frac=0.35):
                     f"{hbm_frac:.2f} of HBM for workspace + inputs; device-resident forward, CUDA events, max over ranks", "n_gpus": X.world, "rows": rows}
 
 
+def sustained_gemm_vs_cublas(M, dtype):
+    """tools/sustained_gemm.py in its own process (cuBLAS is never loaded into the bench process): {cublas_tflops, tim_b200_tflops, ratio, ...}"""
+    try:
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "sustained_gemm.py"), "--m", str(M), "--seconds", "1.5", "--shapes", "in_proj",
+                            "--dtypes", dtype], capture_output=True, text=True, timeout=240)
+        rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+        by = {x["impl"]: x for x in rows}
+        return {"what": "in_proj-shaped GEMM [M, 1024] x [3072, 1024]^T launched back to back for 1.5 s per implementation (power-capped clocks settle), own process",
+                "M": M, "operands": dtype, "cublas_tflops": by["cublas"]["tflops"], "cublas_sm_mhz": by["cublas"]["sm_mhz_median"],
+                "tim_b200_tflops": by["tim_b200"]["tflops"], "tim_b200_sm_mhz": by["tim_b200"]["sm_mhz_median"],
+                "ratio": by["tim_b200"]["tflops"] / by["cublas"]["tflops"]}
+    except Exception as e:      # a baseline, never a reason to lose the bench line
+        return {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+
+
 def eager_reference(workload, clips, steps):
     """The unmodified reference through eager PyTorch on this GPU (tools/eager_reference.py, own process: imports baseline/_ref)."""
     try:
@@ -607,7 +622,7 @@ def main():
     torch.cuda.empty_cache()
 
     # ---- sub-records: the training step of this workload; cfg4 (the north-star scaling config); the cfg5 sweep; eager PyTorch ----
-    train = cfg4 = sweep = eager = None
+    train = cfg4 = sweep = eager = gemm_vs_cublas = None
     if not args.no_extras:
         tsteps = max(3, args.steps // 4)
         train = measure_train(X, cfg, Qv, Qa, B, args.dtype, tsteps, 3, pk)
@@ -635,6 +650,10 @@ def main():
                 for m in eager["modes"].values():
                     m["tim_b200_speedup"] = (value / world) / m["clips_x_queries_per_sec"]
         X.barrier()
+        # the same layer GEMM (in_proj shape of this step) back to back for ~1.5 s through cuBLAS and through this library's kernel, same
+        # operand type, same box, same power cap: what "peak" means for THIS shape on THIS part (tools/sustained_gemm.py). One GPU only.
+        if world == 1 and args.dtype in ("fp16", "bf16"):
+            gemm_vs_cublas = sustained_gemm_vs_cublas(B * cfg.seq_len(Qv, Qa), args.dtype)
 
     if rank == 0:
         cb = None
@@ -647,7 +666,7 @@ def main():
                 "data": "synthetic", "config": conf, "input_bytes_per_step": in_bytes,
                 "clips_per_sec": world * B / (ms * 1e-3), "tokens_per_sec": world * B * cfg.seq_len(Qv, Qa) / (ms * 1e-3),
                 "gpu_launches": int(launches), "e2e": e2e, "e2e_fp32_io": e2e_fp32, "e2e_fp32_logits": e2e_32out, "e2e_resident_bank": e2e_bank, "roofline": roofline, "cpu_baseline": cb, "clocks": clocks,
-                "parity": parity, "train": train, "cfg4": cfg4, "sweep_cfg5": sweep, "gpu_eager_baseline": eager}
+                "parity": parity, "train": train, "cfg4": cfg4, "sweep_cfg5": sweep, "gpu_eager_baseline": eager, "gemm_vs_cublas": gemm_vs_cublas}
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()

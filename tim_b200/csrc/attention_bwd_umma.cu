@@ -229,15 +229,19 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                     }
                 }
                 const float mf = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-                float ls[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                // the three passes below run on packed fp32 pairs (FADD2 / FMUL2 / FFMA2, two elements per issue slot): the softmax warps
+                // are the serial resource of a tile (profiles/r02q_attention_bwd_roles.txt) and their instruction count is its critical path
+                float2 lsA = make_float2(0.0f, 0.0f), lsB = make_float2(0.0f, 0.0f);
+                const float2 nmf = make_float2(-mf, -mf);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     if (c * 16 < Fp) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float e = ex2_approx(s[c * 16 + j] - mf);
-                            s[c * 16 + j] = e;
-                            ls[j & 3] += e;
+                        for (int j = 0; j < 16; j += 4) {
+                            const float2 a = ex2_approx2(__fadd2_rn(make_float2(s[c * 16 + j], s[c * 16 + j + 1]), nmf));
+                            const float2 b2 = ex2_approx2(__fadd2_rn(make_float2(s[c * 16 + j + 2], s[c * 16 + j + 3]), nmf));
+                            s[c * 16 + j] = a.x; s[c * 16 + j + 1] = a.y; s[c * 16 + j + 2] = b2.x; s[c * 16 + j + 3] = b2.y;
+                            lsA = __fadd2_rn(lsA, a); lsB = __fadd2_rn(lsB, b2);
                         }
                     }
                 }
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                 const float m = fmaxf(mf, sself);
                 const float rf = ex2_approx(mf - m);                 // the feature-key terms were taken against mf
                 float ps = qt ? ex2_approx(sself - m) : 0.0f;
-                const float inv = valid ? 1.0f / (((ls[0] + ls[1]) + (ls[2] + ls[3])) * rf + ps) : 0.0f;      // padded rows: P = dS = 0
+                const float inv = valid ? 1.0f / (((lsA.x + lsA.y) + (lsB.x + lsB.y)) * rf + ps) : 0.0f;      // padded rows: P = dS = 0
                 const float invf = inv * rf;
                 ps *= inv;
                 // dropout of the probabilities in the forward (kernels.h: DropSite): the gradient w.r.t. P is dP o mask, dV_f sees the
@@ -262,7 +266,8 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                 const float m_self = p.drop.thr ? drop_one(2u * drop_pair0 + static_cast<uint32_t>(Ft), p.drop.key, p.drop.thr, p.drop.scale) : 1.0f;
                 dps *= m_self;
                 // ---- D = sum_j P_j dP_j (+ own key): first pass over dP ----
-                float dacc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                float2 dA = make_float2(0.0f, 0.0f), dB = make_float2(0.0f, 0.0f);
+                const float2 invf2 = make_float2(invf, invf);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     if (c * 16 < Fp) {
@@ -278,13 +283,17 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                             }
                         }
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            s[c * 16 + j] *= invf;
-                            dacc[j & 3] = fmaf(s[c * 16 + j], __uint_as_float(v[j]), dacc[j & 3]);
+                        for (int j = 0; j < 16; j += 4) {
+                            const float2 pa = __fmul2_rn(make_float2(s[c * 16 + j], s[c * 16 + j + 1]), invf2);
+                            const float2 pb = __fmul2_rn(make_float2(s[c * 16 + j + 2], s[c * 16 + j + 3]), invf2);
+                            s[c * 16 + j] = pa.x; s[c * 16 + j + 1] = pa.y; s[c * 16 + j + 2] = pb.x; s[c * 16 + j + 3] = pb.y;
+                            dA = __ffma2_rn(pa, make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), dA);
+                            dB = __ffma2_rn(pb, make_float2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), dB);
                         }
                     }
                 }
-                const float D = (dacc[0] + dacc[1]) + (dacc[2] + dacc[3]) + ps * dps;
+                const float D = (dA.x + dA.y) + (dB.x + dB.y) + ps * dps;
+                const float2 nD = make_float2(-D, -D);
                 const float dss = ps * (dps - D);
                 // ---- second pass: dS = P o (dP - D); P and dS -> shared memory (K-major, 128-byte swizzle; 64-key blocks 16 KB apart) ----
 #pragma unroll
@@ -301,11 +310,17 @@ __global__ void __launch_bounds__(BU_THREADS, 1) attention_bwd_umma_kernel(const
                             uint32_t* wd = reinterpret_cast<uint32_t*>(&qd);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const float p0 = s[c8 * 8 + 2 * j], p1 = s[c8 * 8 + 2 * j + 1];
-                                float m0 = 1.0f, m1 = 1.0f;
-                                if (p.drop.thr) drop_pair(drop_pair0 + c8 * 4 + j, p.drop.key, p.drop.thr, p.drop.scale, m0, m1);
-                                wp[j] = pack2<T>(p0 * m0, p1 * m1);
-                                wd[j] = pack2<T>(p0 * (__uint_as_float(v[h8 * 8 + 2 * j]) * m0 - D), p1 * (__uint_as_float(v[h8 * 8 + 2 * j + 1]) * m1 - D));
+                                const float2 pp = make_float2(s[c8 * 8 + 2 * j], s[c8 * 8 + 2 * j + 1]);
+                                float2 vv = make_float2(__uint_as_float(v[h8 * 8 + 2 * j]), __uint_as_float(v[h8 * 8 + 2 * j + 1]));
+                                float2 pm = pp;
+                                if (p.drop.thr) {
+                                    float2 mm;
+                                    drop_pair(drop_pair0 + c8 * 4 + j, p.drop.key, p.drop.thr, p.drop.scale, mm.x, mm.y);
+                                    vv = __fmul2_rn(vv, mm); pm = __fmul2_rn(pp, mm);
+                                }
+                                wp[j] = pack2<T>(pm.x, pm.y);
+                                const float2 ds = __fmul2_rn(pp, __fadd2_rn(vv, nD));
+                                wd[j] = pack2<T>(ds.x, ds.y);
                             }
                             const uint32_t off = static_cast<uint32_t>(c8 >> 3) * 16384 + row * 128 + ((static_cast<uint32_t>(c8 & 7) ^ swz) << 4);
                             sts_u128(sP + off, qp);

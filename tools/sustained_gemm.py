@@ -61,20 +61,21 @@ def timed(fn, seconds):
     return e0.elapsed_time(e1) / n, median([r[0] for r in rows]), median([r[1] for r in rows]), n
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--m", type=int, default=204800)
-    ap.add_argument("--seconds", type=float, default=4.0)
-    ap.add_argument("--out", default="")
-    args = ap.parse_args()
+SHAPES = {"in_proj": (3072, 1024), "linear1": (2048, 1024)}
+DTYPES = {"fp16": (torch.float16, 2), "bf16": (torch.bfloat16, 1)}
+
+
+def run(M, seconds, shapes=("in_proj", "linear1"), dtypes=("fp16", "bf16"), verbose=False):
+    """rows of {shape, operands, impl (cublas | tim_b200), tflops, sm_mhz_median, power_w_median, ...}; used by bench.py too"""
     lib = _lib.load()
-    dev = torch.device("cuda", 0)
-    M = args.m
+    dev = torch.device("cuda", torch.cuda.current_device())
     g = torch.Generator(device=dev).manual_seed(0)
     res = []
-    for name, N, K in [("in_proj", 3072, 1024), ("linear1", 2048, 1024)]:
+    for name in shapes:
+        N, K = SHAPES[name]
         flops = 2.0 * M * N * K
-        for dt_name, tdt, code in [("fp16", torch.float16, 2), ("bf16", torch.bfloat16, 1)]:
+        for dt_name in dtypes:
+            tdt, code = DTYPES[dt_name]
             A = torch.randn(M, K, generator=g, device=dev).to(tdt)
             W = (torch.randn(N, K, generator=g, device=dev) / math.sqrt(K)).to(tdt)
             bias = torch.zeros(N, device=dev)
@@ -92,12 +93,25 @@ def main():
                 assert r == 0, lib.tim_last_error(None)
 
             for impl, fn in [("cublas", cublas), ("tim_b200", ours)]:
-                ms, clk, pw, n = timed(fn, args.seconds)
+                ms, clk, pw, n = timed(fn, seconds)
                 row = {"shape": name, "M": M, "N": N, "K": K, "operands": dt_name, "impl": impl, "launches": n, "ms_per_launch": ms,
                        "tflops": flops / (ms * 1e-3) / 1e12, "sm_mhz_median": clk, "power_w_median": pw}
                 res.append(row)
-                print(json.dumps(row), flush=True)
-            del A, W, out
+                if verbose:
+                    print(json.dumps(row), flush=True)
+            del A, W, out, Wt
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--m", type=int, default=204800)
+    ap.add_argument("--seconds", type=float, default=4.0)
+    ap.add_argument("--out", default="")
+    ap.add_argument("--shapes", default="in_proj,linear1")
+    ap.add_argument("--dtypes", default="fp16,bf16")
+    args = ap.parse_args()
+    res = run(args.m, args.seconds, tuple(args.shapes.split(",")), tuple(args.dtypes.split(",")), verbose=True)
     if args.out:
         json.dump({"what": "sustained back-to-back GEMM launches, one shape at a time", "rows": res}, open(args.out, "w"), indent=1)
 
