@@ -157,6 +157,8 @@ __global__ void __launch_bounds__(A4_THREADS, 1) attention_umma4_kernel(const __
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    pdl_launch_dependents();          // programmatic dependent launch (ptx.cuh): the set-up above overlapped the previous kernel's tail
+    pdl_wait();
     ProfClock pc;
     pc.on = p.prof != nullptr;
     unsigned long long pr[PR_COUNT] = {};
@@ -575,8 +577,7 @@ cudaError_t launch_one(const AttnUmmaParams& p, int grid, size_t smem, cudaStrea
     auto kern = attention_umma4_kernel<T, HD, FPC, DROP>;
     static SmemAttrCache cache;
     if (cudaError_t e = ensure_dynamic_smem(kern, smem, cache); e != cudaSuccess) return e;
-    kern<<<grid, A4_THREADS, smem, s>>>(p);
-    return cudaGetLastError();
+    return launch_maybe_pdl(kern, static_cast<unsigned>(grid), A4_THREADS, smem, s, pdl_enabled(), p);
 }
 
 template <typename T, int HD>

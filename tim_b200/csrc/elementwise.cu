@@ -267,6 +267,7 @@ __global__ void __launch_bounds__(256) cast_tail_kernel(const float* __restrict_
 __global__ void __launch_bounds__(256) row_stats_finalize_kernel(const float2* __restrict__ part, int P, float inv_width,
                                                                  float2* __restrict__ stats, int M, float alarm_ratio,
                                                                  int* __restrict__ alarm) {
+    pdl_launch_dependents();          // the consumer GEMM behind this kernel may set itself up while these few CTAs run (ptx.cuh)
     const int row = blockIdx.x * 256 + threadIdx.x;
     if (row >= M) return;
     float s = 0.0f, q = 0.0f;

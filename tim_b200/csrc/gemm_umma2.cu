@@ -20,6 +20,8 @@
 // Epilogue modes (template MODE): 0 16-bit out; 1 fp32 out; 2 fp32 out + fp32 residual; 3 as 2 with LayerNorm applied to the
 // residual rows on read; 5 / 6 the folded-LayerNorm producer / consumer pair that removes the LayerNorm kernels of the encoder
 // stack (transformers.py:105,109) - described in front of the kernel. Measured per-launch numbers: profiles/README.md.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -122,6 +124,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1) linear_u
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    // everything above touched only this CTA's shared memory / TMEM and the kernel parameters: under a programmatic dependent launch it
+    // ran while the previous kernel of the stream was draining. From here on global memory is read and written.
+    pdl_launch_dependents();
+    pdl_wait();
 
     // Producer and MMA warps run their loops WARP-UNIFORMLY (all 32 lanes wait on the barriers and carry the loop state) and
     // only the asynchronous-issue instructions sit under elect_one(): the descriptors, coordinates and barrier addresses are
@@ -437,11 +443,15 @@ cudaError_t launch_mode(const Umma2Params& p, int num_sms, cudaStream_t s) {
     if (tiles <= 0) return cudaSuccess;
     int clusters = num_sms / 2;
     if (clusters > tiles) clusters = tiles;
-    kern<<<2 * clusters, THREADS, SMEM_BYTES, s>>>(p);
-    return cudaGetLastError();
+    return launch_maybe_pdl(kern, 2u * clusters, THREADS, SMEM_BYTES, s, pdl_enabled(), p);
 }
 
 }  // namespace
+
+bool pdl_enabled() {
+    static const bool on = [] { const char* e = std::getenv("TIM_B200_PDL"); return e ? std::atoi(e) != 0 : true; }();
+    return on;
+}
 
 bool umma2_supported(int M, int N, int K) { return M > 0 && N >= 128 && (N % 64) == 0 && K >= 64 && (K % 8) == 0; }
 

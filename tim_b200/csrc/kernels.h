@@ -125,6 +125,22 @@ struct Umma2Params {
     int tiles_m, tiles_n;
 };
 bool umma2_supported(int M, int N, int K);
+// programmatic dependent launch of the pair GEMM and the tcgen05 attention forward (ptx.cuh: pdl_wait); TIM_B200_PDL=0 switches it off.
+// Measured (profiles/r02z, r03a): e2e call 25.0-25.6 -> 23.9-24.4 ms, device-resident step -0.1 ... -0.4 ms; extending it to the row kernels
+// and the single-CTA GEMM gave nothing and cost 0.3 ms of the device-resident step, the training kernels showed no change - both left out.
+bool pdl_enabled();
+// <<<grid, block, smem, s>>> with the programmatic-stream-serialization attribute when `pdl`
+// (every kernel launched this way executes pdl_wait() before its first global access)
+template <typename... KA, typename... A>
+inline cudaError_t launch_maybe_pdl(void (*kern)(KA...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, bool pdl, A&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KA>(args)...);
+}
 // mode 0: out = T(act(acc + bias)); 1: out = float(act(acc + bias)); 2: out = float(act(acc + bias) + resid);
 // mode 3: out = float(act(acc + bias) + LayerNorm(resid)) with the row statistics given (Epilogue::rstats)
 // modes 5 / 6: the folded-LayerNorm producer / consumer pair, see gemm_umma2.cu; mode 7: producer on the two-plane residual stream;

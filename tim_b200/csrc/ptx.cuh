@@ -60,6 +60,15 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become resident while its predecessor in the stream is
+// still draining: everything in front of pdl_wait() (barrier init, TMEM allocation, descriptor prefetch) overlaps the predecessor's tail;
+// pdl_wait() returns when the predecessor grid has COMPLETED and its memory is visible. pdl_launch_dependents() is the predecessor's side:
+// once every CTA has issued it (or exited) the dependent grid may be scheduled onto whatever resources come free. Both are no-ops in a
+// kernel launched the ordinary way / without a dependent.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
