@@ -547,6 +547,47 @@ def test_fold_precision_guard(lib):
     assert rel_l2(action.cpu().numpy(), ref["action"]) <= TOL_SMALL["fp16"]
 
 
+@pytest.mark.parametrize("dt", ["fp16", "fp32"])
+def test_forward_under_cuda_graph_capture(lib, dt):
+    """the device entry points only enqueue on the stream they are given, so a caller may capture them into a CUDA
+    graph (what PyTorch users do for inference loops). Real-width case (head_dim 128: the pair GEMM and the tcgen05 attention, both
+    launched with the programmatic-dependent-launch attribute, sit inside the captured region). The replayed graph, fed new inputs
+    in place, must reproduce the eager call bit for bit."""
+    from tim_b200.plugin import TIMEngine
+    cfg, sd, inp, gold, c = load_case("recog_cfg1")
+    Qv, Qa = c["Qv"], c["Qa"]
+    dev = torch.device("cuda", 0)
+    eng = TIMEngine(cfg, 0, dt)
+    eng.load_state_dict(sd)
+    vis, aud, times = (torch.from_numpy(inp[k]).to(dev) for k in ("vis", "aud", "times"))
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):               # warm-up: workspace allocation, weight folding - nothing of that may happen under capture
+        for _ in range(2):
+            eng.encoder(vis, aud, eng.time_mlp(times), Qv, Qa)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out_g = eng.encoder(vis, aud, eng.time_mlp(times), Qv, Qa)
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    vis.copy_(torch.randn(vis.shape, generator=gen)); aud.copy_(torch.randn(aud.shape, generator=gen))
+    g.replay()
+    torch.cuda.synchronize(dev)
+    got = {k: v.clone() for k, v in out_g.items() if v is not None}
+    eager = eng.encoder(vis, aud, eng.time_mlp(times), Qv, Qa)
+    torch.cuda.synchronize(dev)
+    for k, v in got.items():
+        assert torch.isfinite(v).all(), k
+        assert torch.equal(v, eager[k]), k
+    g.replay()                                   # and again: the graph owns its buffers, a second replay gives the same answer
+    torch.cuda.synchronize(dev)
+    for k, v in got.items():
+        assert torch.equal(out_g[k], v), k
+    del g
+    eng.close()
+
+
 @pytest.mark.parametrize("dt", ["fp16", "bf16"])
 def test_host_path_16bit_io(lib, dt):
     """tim_forward_host_ex with a 16-bit HOST feature bank (features already in the operand type: half the H2D bytes, no cast pass)
