@@ -669,7 +669,13 @@ def main():
                 "parity": parity, "train": train, "cfg4": cfg4, "sweep_cfg5": sweep, "gpu_eager_baseline": eager, "gemm_vs_cublas": gemm_vs_cublas}
         os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
+        # the line is out; the teardown of the process group (NCCL proxy threads) has been seen to hang once behind a completed run
+        # (profiles/README.md, r03e) - a watchdog ends the process if it does not return, so the driver never waits on a finished bench
+        w = threading.Timer(45.0, lambda: os._exit(0))
+        w.daemon = True
+        w.start()
         dist.destroy_process_group()
+        w.cancel()
 
 
 if __name__ == "__main__":

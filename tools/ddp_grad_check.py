@@ -98,7 +98,12 @@ def main():
         if args.out:
             json.dump(report, open(args.out, "w"), indent=1)
         assert all(c.get("ok", True) for c in report["cases"].values()), report
+    import threading
+    w = threading.Timer(45.0, lambda: os._exit(0))       # results are out; never hang in the process-group teardown
+    w.daemon = True
+    w.start()
     dist.destroy_process_group()
+    w.cancel()
 
 
 if __name__ == "__main__":
