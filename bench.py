@@ -674,7 +674,10 @@ def main():
         w = threading.Timer(45.0, lambda: os._exit(0))
         w.daemon = True
         w.start()
-        dist.destroy_process_group()
+        try:
+            dist.destroy_process_group()
+        except Exception:      # peers may already be gone (their watchdog): the results are out
+            pass
         w.cancel()
 
 
