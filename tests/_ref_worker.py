@@ -121,16 +121,21 @@ def main():
         rec = {}
         if mode == "eval":
             model.eval()
+            torch.manual_seed(4321)
             with torch.no_grad():
                 ref = run_model(model, cfg, t, Qv, Qa)
+            rng_ref = torch.get_rng_state()        # the reference's detection inference draws from the CPU generator (tim.py:364)
             ref = {k: (v.clone() if v is not None else None) for k, v in ref.items()}
             for dt in ("fp32", "fp16"):
                 m2 = build_reference(cfg).to(dev)
                 m2.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()}, strict=True)
                 m2 = patch_model(m2.eval(), compute_dtype=dt)
+                torch.manual_seed(4321)
                 with torch.no_grad():
                     got = run_model(m2, cfg, t, Qv, Qa)
                 torch.cuda.synchronize()
+                # the drop-in leaves torch's CPU generator where the reference leaves it: whatever the caller draws next is unchanged
+                assert torch.equal(torch.get_rng_state(), rng_ref), (name, dt, "CPU RNG state differs from the reference's after the forward")
                 for k, v in ref.items():
                     assert (v is None) == (got[k] is None), (name, k)
                     if v is not None:

@@ -620,6 +620,9 @@ def _forward_detection(self, inputs, forward_type, feature_times=None, target=No
         all_times = torch.cat([all_times, v_queries], dim=1)
         v_queries = torch.flatten(v_queries, 0, 1)
     if "audio" in cfg.data_modality:
+        # the reference draws a permutation here and discards it (detection/.../tim.py:364): one draw from torch's default CPU generator per
+        # audio-modality inference forward. Reproduced so that whatever the caller draws next sees the generator state it would see there.
+        torch.randperm(self.inference_queries.shape[1])
         a_queries = self.inference_queries.repeat(B, 1, 1).to(device=dev)
         na = a_queries.shape[1]
         if label_queries:
