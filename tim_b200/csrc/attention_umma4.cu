@@ -619,8 +619,10 @@ cudaError_t launch_attention_umma4(AttnUmmaParams p, int hd, int num_sms, cudaSt
     const long long units = items * p.chunks;
     if (units > 0x7fffffffLL) return cudaErrorInvalidValue;
     p.num_units = static_cast<int>(units);
-    // L2 prefetch policy (TIM_B200_ATTN_PF = "<mode>,<tiles>"): mode 0 off, 1 K_f / V_f of upcoming units only, 2 everything
-    p.pf_mode = 2; p.pf_tiles = A4_PF;
+    // L2 prefetch policy (TIM_B200_ATTN_PF = "<mode>,<tiles>"): mode 0 off, 1 K_f / V_f of upcoming units only, 2 everything.
+    // Measured at HEAD (isolated launches, profiles/README.md r03j): two tiles per unit (cfg2) 271 us with mode 2 against 283 with mode 1;
+    // 17 tiles per unit (cfg4) 306 us with mode 1 against 319 with mode 2 - the query tiles of a long unit stream in order anyway.
+    p.pf_mode = tiles_total > 4 ? 1 : 2; p.pf_tiles = A4_PF;
     if (const char* e = std::getenv("TIM_B200_ATTN_PF")) {
         int m = 0, t = A4_PF;
         const int n = std::sscanf(e, "%d,%d", &m, &t);
